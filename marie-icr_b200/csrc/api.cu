@@ -1,0 +1,77 @@
+// Context management and error plumbing of the C ABI (include/marie_b200.h).
+#include "common.cuh"
+#include <stdarg.h>
+
+int mb_set_err(mb_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+void* mb_scratch(mb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return ctx->scratch;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t want = mb_align_up(bytes + bytes / 4, (size_t)1 << 20);
+    if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) {
+        cudaGetLastError();
+        mb_set_err(ctx, MB_ERR_OOM, "scratch allocation of %zu bytes failed", want);
+        return nullptr;
+    }
+    ctx->scratch_bytes = want;
+    return ctx->scratch;
+}
+
+void mb_free_models(mb_ctx* ctx);   // craft.cu / trocr.cu
+
+extern "C" const char* mb_version(void) { return "marie_b200 0.1 (sm_100a)"; }
+
+extern "C" int mb_init(int device, mb_ctx** out) {
+    if (!out) return MB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return MB_ERR_NO_DEVICE;   // no CPU fallback by design
+    }
+    if (device < 0 || device >= count) return MB_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MB_ERR_CUDA;
+    if (prop.major != 10) return MB_ERR_NO_DEVICE;   // kernels are sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return MB_ERR_CUDA;
+    mb_ctx* ctx = new mb_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaMalloc(&ctx->dev_diag, 64) != cudaSuccess) {
+        delete ctx;
+        return MB_ERR_CUDA;
+    }
+    cudaMemset(ctx->dev_diag, 0, 64);
+    *out = ctx;
+    return MB_OK;
+}
+
+extern "C" void mb_free(mb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    mb_free_models(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->dev_diag) cudaFree(ctx->dev_diag);
+    delete ctx;
+}
+
+extern "C" const char* mb_last_error(const mb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" unsigned long long mb_launch_count(const mb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Reads (and clears) the diagnostic word kernels write before trapping (debug aid for tests).
+extern "C" unsigned int mb_debug_diag(mb_ctx* ctx) {
+    unsigned int v = 0;
+    if (ctx && ctx->dev_diag) cudaMemcpy(&v, ctx->dev_diag, 4, cudaMemcpyDeviceToHost);
+    return v;
+}

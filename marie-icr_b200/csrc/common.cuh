@@ -1,0 +1,112 @@
+// Shared declarations for libmarie_b200.so (sm_100a only).
+// Host-side context, error plumbing and small device helpers used by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/marie_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define MB_NUM_SMS_DEFAULT 148
+
+// Every C-ABI entry point funnels errors through this: negative code + message kept in the ctx.
+struct mb_ctx {
+    int device = 0;
+    int num_sms = MB_NUM_SMS_DEFAULT;
+    char err[512] = {0};
+    // scratch owned by the context (grown on demand, never shrunk)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // model state (opaque here; defined in craft.cu / trocr.cu)
+    struct CraftModel* craft = nullptr;
+    struct TrocrModel* trocr = nullptr;
+    // device-side diagnostic word written by kernels before __trap()
+    unsigned int* dev_diag = nullptr;
+    // kernel launch counter (bench.py "gpu_launches")
+    unsigned long long launches = 0;
+};
+
+int mb_set_err(mb_ctx* ctx, int code, const char* fmt, ...);
+void* mb_scratch(mb_ctx* ctx, size_t bytes);   // returns nullptr + sets error on failure
+
+#define MB_CUDA(ctx, expr)                                                             \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            return mb_set_err((ctx), MB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, \
+                              #expr, cudaGetErrorString(_e));                          \
+    } while (0)
+
+#define MB_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                               \
+        (ctx)->launches++;                                                             \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess)                                                         \
+            return mb_set_err((ctx), MB_ERR_CUDA, "%s:%d launch -> %s", __FILE__,       \
+                              __LINE__, cudaGetErrorString(_e));                       \
+    } while (0)
+
+#define MB_REQUIRE(ctx, cond, ...)                                   \
+    do {                                                             \
+        if (!(cond)) return mb_set_err((ctx), MB_ERR_ARG, __VA_ARGS__); \
+    } while (0)
+
+static inline int mb_cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t mb_align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------
+// tap-GEMM (gemm_tc.cu): D = epilogue( sum_taps A_tap * W^T ), bf16 in, fp32 accumulate in TMEM.
+// One kernel serves 3x3 / dilated / 1x1 convolutions over NHWC activations (implicit GEMM through
+// shifted TMA boxes, zero padding by TMA out-of-bounds fill) and plain row-major GEMMs
+// (n = h = 1, w = M rows).
+// ---------------------------------------------------------------------------------------------
+enum { MB_ACT_NONE = 0, MB_ACT_RELU = 1, MB_ACT_GELU = 2 };
+enum { MB_OUT_BF16 = 0, MB_OUT_F32 = 1, MB_OUT_F32_PLANAR = 2 };
+
+struct TapGemm {
+    // activations: up to two NHWC sources concatenated along channels (k index = tap*(c0+c1)+c)
+    const bf16* a0 = nullptr; int c0 = 0; int a0_ld = 0;   // a0_ld: pixel pitch in elements
+    const bf16* a1 = nullptr; int c1 = 0; int a1_ld = 0;
+    int n = 1, h = 1, w = 1;      // output (and input) spatial extent; plain GEMM: w = M
+    int taps = 1;                 // 1 or 9 (3x3, padding = dilation)
+    int dil = 1;
+    const bf16* wgt = nullptr;    // [n_rows_w, taps*(c0+c1)] row-major (K contiguous)
+    int n_rows_w = 0;             // rows present in wgt (>= n_out, padding rows are zero)
+    int n_out = 0;                // columns written
+    int block_n = 0;              // 0 = pick automatically
+    const float* bias = nullptr;  // [n_out] fp32 or null
+    int act = MB_ACT_NONE;
+    const bf16* residual = nullptr; int res_ld = 0;  // added after activation
+    void* out = nullptr; long long out_ld = 0; int out_mode = MB_OUT_BF16;
+    long long out_plane = 0;      // MB_OUT_F32_PLANAR: elements between channel planes
+};
+int mb_tap_gemm(mb_ctx* ctx, const TapGemm& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float bf16_bits_to_f32(unsigned short b) {
+    return __uint_as_float(((unsigned int)b) << 16);
+}
+__device__ __forceinline__ unsigned int pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned int*>(&v);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif

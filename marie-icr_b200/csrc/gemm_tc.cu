@@ -1,0 +1,523 @@
+// tap-GEMM: the one tensor-core kernel of the library (sm_100a: tcgen05.mma + TMEM + TMA).
+//
+//   D[pixel, n] = epilogue( sum_{tap} sum_{c} A[pixel + offset(tap), c] * W[n, tap*C + c] )
+//
+// * A is one (or two channel-concatenated) NHWC bf16 tensor(s).  An M tile is 128 consecutive pixels of one
+//   image row; the A tile for tap (dy,dx) is the TMA box shifted by (dy,dx)*dilation — out-of-bounds
+//   pixels are zero-filled by TMA, which is exactly the convolution's zero padding.  A plain GEMM is the
+//   degenerate case n = h = 1, w = M, taps = 1.
+// * W is [N, K] K-major; both operands land in shared memory in the 128-byte-swizzled K-major canonical
+//   layout that tcgen05.mma consumes through shared-memory descriptors.
+// * Warp roles (persistent CTA, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (single thread),
+//   warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).  The accumulator is
+//   double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Replaces cuDNN/cuBLAS behind nn.Conv2d / nn.Linear on the reference's hot path
+// (marie/models/craft/basenet/vgg16_bn.py:33-47, marie/models/craft/craft.py:14-51,
+//  marie/models/unilm/trocr/deit.py:105-146, trocr_models.py:142-147).
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct KParams {
+    int n, h, w;
+    int w_tiles, m_tiles, n_tiles;
+    int taps, dil;
+    int kb0, kb1;          // 64-wide k blocks per tap from source 0 / source 1
+    int block_n;
+    int n_out;
+    int stages;
+    const float* bias;
+    int act;
+    const bf16* residual;
+    long long res_ld;
+    void* out;
+    long long out_ld;
+    int out_mode;
+    long long out_plane;
+    unsigned int* diag;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* diag, int who) {
+    uint32_t done = 0;
+    unsigned int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) {   // a lost arrival must fault, never hang the box
+            if (diag) atomicExch(diag, 0xDEAD0000u | (unsigned)who);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor v1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);      // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024 B alignment is required by the 128B swizzle; do not trust the declared alignment alone.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + p.stages * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + MAX_STAGES;
+    uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;
+    uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(smem_u32(&full_bar[i]), 1);
+            mbar_init(smem_u32(&empty_bar[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[i]), 4);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_ptr_smem)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int kb_per_tap = p.kb0 + p.kb1;
+    const int k_iters = p.taps * kb_per_tap;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one lane)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int mt = tile / p.n_tiles;
+                const int wt = mt % p.w_tiles;
+                const int rest = mt / p.w_tiles;
+                const int hh = rest % p.h;
+                const int nn = rest / p.h;
+                const int w0 = wt * BLOCK_M;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
+                    const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.diag, 1);
+                        const uint32_t fb = smem_u32(&full_bar[stage]);
+                        mbar_arrive_expect_tx(fb, tx_bytes);
+                        const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+                        const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
+                        if (kb < p.kb0)
+                            tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K, w0 + dx, hh + dy, nn);
+                        else
+                            tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 + dx, hh + dy, nn);
+                        tma_load_2d(sb, &tmB, fb, (tap * kb_per_tap + kb) * BLOCK_K, nt * p.block_n);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1, p.diag, 2);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase, p.diag, 3);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 elements = 32 B along K inside the swizzle row: +2 in 16 B units
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                  (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(smem_u32(&empty_bar[stage]));     // frees the smem slot when MMAs retire
+                    if (it == k_iters - 1) tcgen05_commit(smem_u32(&tmem_full_bar[as]));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (4 warps, 128 rows)
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int mt = tile / p.n_tiles;
+            const int wt = mt % p.w_tiles;
+            const int rest = mt / p.w_tiles;
+            const int hh = rest % p.h;
+            const int nn = rest / p.h;
+            const int wcol = wt * BLOCK_M + q * 32 + lane;
+            const bool valid = wcol < p.w;
+            const long long pix = ((long long)nn * p.h + hh) * p.w + wcol;
+
+            mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t v[32];
+                __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the masked stores
+                tmem_ld32(taddr + (uint32_t)c, v);
+                tmem_wait_ld();
+                const int n0 = nt * p.block_n + c;
+                if (!valid || n0 >= p.n_out) continue;
+                const int ncols = min(32, p.n_out - n0);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias != nullptr && j < ncols) x += __ldg(p.bias + n0 + j);
+                    if (p.act == MB_ACT_RELU) x = fmaxf(x, 0.0f);
+                    else if (p.act == MB_ACT_GELU) x = gelu_erf(x);
+                    f[j] = x;
+                }
+                if (p.residual != nullptr) {
+                    const bf16* r = p.residual + pix * p.res_ld + n0;
+                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + j4);
+                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                f[j4 * 8 + 2 * t] += __uint_as_float(rw[t] << 16);
+                                f[j4 * 8 + 2 * t + 1] += __uint_as_float(rw[t] & 0xFFFF0000u);
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(r[j]);
+                    }
+                }
+                if (p.out_mode == MB_OUT_BF16) {
+                    bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.out_ld + n0;
+                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint4 ov;
+                            ov.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
+                            ov.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
+                            ov.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
+                            ov.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+                            reinterpret_cast<uint4*>(o)[j4] = ov;
+                        }
+                    } else {
+                        for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else if (p.out_mode == MB_OUT_F32) {
+                    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n0;
+                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            reinterpret_cast<float4*>(o)[j4] =
+                                make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+                    } else {
+                        for (int j = 0; j < ncols; ++j) o[j] = f[j];
+                    }
+                } else {   // MB_OUT_F32_PLANAR: channel planes, pixel-contiguous (coalesced across lanes)
+                    float* o = reinterpret_cast<float*>(p.out) + pix;
+                    for (int j = 0; j < ncols; ++j) o[(long long)(n0 + j) * p.out_plane] = f[j];
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// NHWC activation map: dims {C, W, H, N}, box {64, 128, 1, 1}
+int encode_act_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int c, int ld, int n, int h, int w) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+    cuuint32_t box[4] = {BLOCK_K, BLOCK_M, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled(act c=%d ld=%d n=%d h=%d w=%d) -> %d", c,
+                          ld, n, h, w, (int)r);
+    return 0;
+}
+
+int encode_wgt_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int ktot, int rows, int block_n) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)block_n};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled(wgt k=%d rows=%d bn=%d) -> %d", ktot,
+                          rows, block_n, (int)r);
+    return 0;
+}
+
+}  // namespace
+
+int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
+    MB_REQUIRE(ctx, g.a0 && g.wgt && g.out, "tap_gemm: null pointer");
+    MB_REQUIRE(ctx, g.c0 > 0 && g.c0 % BLOCK_K == 0 && g.c1 >= 0 && g.c1 % BLOCK_K == 0,
+               "tap_gemm: channel counts must be multiples of 64 (c0=%d c1=%d)", g.c0, g.c1);
+    MB_REQUIRE(ctx, g.taps == 1 || g.taps == 9, "tap_gemm: taps must be 1 or 9");
+    MB_REQUIRE(ctx, g.a0_ld % 8 == 0 && (g.c1 == 0 || g.a1_ld % 8 == 0), "tap_gemm: pixel pitch must be a multiple of 8");
+    MB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(g.a0) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.wgt) & 15) == 0 &&
+                        (g.c1 == 0 || (reinterpret_cast<uintptr_t>(g.a1) & 15) == 0),
+               "tap_gemm: operands must be 16-byte aligned");
+    MB_REQUIRE(ctx, g.n_out > 0 && g.n_rows_w >= g.n_out, "tap_gemm: bad n_out/n_rows_w");
+    MB_REQUIRE(ctx, g.n > 0 && g.h > 0 && g.w > 0, "tap_gemm: empty problem");
+
+    int block_n = g.block_n;
+    if (block_n == 0) {
+        if (g.n_out >= 256) block_n = 256;
+        else if (g.n_out > 128) block_n = 256;
+        else if (g.n_out > 64) block_n = 128;
+        else if (g.n_out > 32) block_n = 64;
+        else if (g.n_out > 16) block_n = 32;
+        else block_n = 16;
+    }
+    MB_REQUIRE(ctx, block_n % 16 == 0 && block_n >= 16 && block_n <= 256, "tap_gemm: bad block_n %d", block_n);
+
+    KParams p;
+    p.n = g.n; p.h = g.h; p.w = g.w;
+    p.w_tiles = mb_cdiv(g.w, BLOCK_M);
+    p.m_tiles = g.n * g.h * p.w_tiles;
+    p.n_tiles = mb_cdiv(g.n_out, block_n);
+    p.taps = g.taps; p.dil = g.dil;
+    p.kb0 = g.c0 / BLOCK_K; p.kb1 = g.c1 / BLOCK_K;
+    p.block_n = block_n;
+    p.n_out = g.n_out;
+    const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+    const int bar_bytes = (2 * MAX_STAGES + 4) * 8 + 16;
+    int stages = (SMEM_LIMIT - 1024 - bar_bytes) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.stages = stages;
+    p.bias = g.bias; p.act = g.act;
+    p.residual = g.residual; p.res_ld = g.res_ld;
+    p.out = g.out; p.out_ld = g.out_ld; p.out_mode = g.out_mode; p.out_plane = g.out_plane;
+    p.diag = ctx->dev_diag;
+
+    CUtensorMap tmA0, tmA1, tmB;
+    int rc = encode_act_map(ctx, &tmA0, g.a0, g.c0, g.a0_ld, g.n, g.h, g.w);
+    if (rc) return rc;
+    if (g.c1 > 0) {
+        MB_REQUIRE(ctx, g.a1 != nullptr, "tap_gemm: c1>0 but a1 null");
+        rc = encode_act_map(ctx, &tmA1, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w);
+        if (rc) return rc;
+    } else {
+        tmA1 = tmA0;
+    }
+    rc = encode_wgt_map(ctx, &tmB, g.wgt, g.taps * (g.c0 + g.c1), g.n_rows_w, block_n);
+    if (rc) return rc;
+
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MB_CUDA(ctx, cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SMEM_LIMIT));
+        attr_set = true;
+    }
+    const long long total = (long long)p.m_tiles * p.n_tiles;
+    const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
+    tap_gemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int mb_gemm_bf16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w,
+                            int M, int N, int K, const float* bias_dev, int act, const void* residual_dev,
+                            long long res_ld, void* out_dev, long long out_ld, int out_mode, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TapGemm g;
+    g.a0 = (const bf16*)a_dev; g.c0 = K; g.a0_ld = (int)lda;
+    g.n = 1; g.h = 1; g.w = M;
+    g.taps = 1; g.dil = 1;
+    g.wgt = (const bf16*)w_dev; g.n_rows_w = n_rows_w; g.n_out = N;
+    g.bias = bias_dev; g.act = act;
+    g.residual = (const bf16*)residual_dev; g.res_ld = (int)res_ld;
+    g.out = out_dev; g.out_ld = out_ld; g.out_mode = out_mode;
+    return mb_tap_gemm(ctx, g, (cudaStream_t)stream);
+}
+
+extern "C" int mb_conv_bf16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, const void* a1_dev, int c1,
+                            int a1_ld, int n, int h, int w, int taps, int dil, const void* w_dev,
+                            int n_rows_w, int n_out, const float* bias_dev, int act, void* out_dev,
+                            long long out_ld, int out_mode, long long out_plane, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TapGemm g;
+    g.a0 = (const bf16*)a0_dev; g.c0 = c0; g.a0_ld = a0_ld;
+    g.a1 = (const bf16*)a1_dev; g.c1 = c1; g.a1_ld = a1_ld;
+    g.n = n; g.h = h; g.w = w;
+    g.taps = taps; g.dil = dil;
+    g.wgt = (const bf16*)w_dev; g.n_rows_w = n_rows_w; g.n_out = n_out;
+    g.bias = bias_dev; g.act = act;
+    g.out = out_dev; g.out_ld = out_ld; g.out_mode = out_mode; g.out_plane = out_plane;
+    return mb_tap_gemm(ctx, g, (cudaStream_t)stream);
+}

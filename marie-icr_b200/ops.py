@@ -1,0 +1,63 @@
+"""Thin torch-tensor wrappers over the stage-level C-ABI entry points (used by tests and the plugins)."""
+import ctypes
+
+import torch
+
+from ._lib import Context, c_float, c_int, c_ll, c_void_p, cur_stream, ptr
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+OUT_BF16, OUT_F32, OUT_F32_PLANAR = 0, 1, 2
+
+
+def _ctx(t):
+    return Context.get(t.device.index or 0)
+
+
+def gemm_bf16(a, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16, n_out=None):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w bf16 row-major; K % 64 == 0."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.stride(-1) == 1 and w.is_contiguous()
+    M, K = a.shape
+    n_rows = w.shape[0]
+    N = n_rows if n_out is None else n_out
+    out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+    _ctx(a).call(
+        "mb_gemm_bf16", ptr(a), c_ll(a.stride(0)), ptr(w), c_int(n_rows), c_int(M), c_int(N), c_int(K),
+        ptr(bias), c_int(act), ptr(residual), c_ll(residual.stride(0) if residual is not None else 0),
+        ptr(out), c_ll(out.stride(0)), c_int(OUT_BF16 if out_dtype == torch.bfloat16 else OUT_F32),
+        cur_stream())
+    return out
+
+
+def conv_bf16(x0, w, bias=None, act=ACT_NONE, x1=None, taps=9, dil=1, n_out=None, out_dtype=torch.bfloat16,
+              planar=False):
+    """NHWC implicit-GEMM convolution. x0/x1: [N,H,W,C] bf16; w: [rows, taps*(C0+C1)] bf16."""
+    assert x0.is_cuda and x0.dtype == torch.bfloat16 and x0.is_contiguous()
+    n, h, wd, c0 = x0.shape
+    c1 = 0
+    if x1 is not None:
+        assert x1.shape[:3] == x0.shape[:3] and x1.is_contiguous()
+        c1 = x1.shape[3]
+    rows = w.shape[0]
+    N = rows if n_out is None else n_out
+    if planar:
+        out = torch.empty((n, N, h, wd), device=x0.device, dtype=torch.float32)
+        assert n == 1 or True
+        mode, out_ld, plane = OUT_F32_PLANAR, 1, h * wd
+        assert n == 1, "planar output is per image"
+    else:
+        out = torch.empty((n, h, wd, N), device=x0.device, dtype=out_dtype)
+        mode, out_ld, plane = (OUT_BF16 if out_dtype == torch.bfloat16 else OUT_F32), N, 0
+    _ctx(x0).call(
+        "mb_conv_bf16", ptr(x0), c_int(c0), c_int(c0), ptr(x1), c_int(c1), c_int(c1), c_int(n), c_int(h),
+        c_int(wd), c_int(taps), c_int(dil), ptr(w), c_int(rows), c_int(N), ptr(bias), c_int(act), ptr(out),
+        c_ll(out_ld), c_int(mode), c_ll(plane), cur_stream())
+    return out
+
+
+def pack_conv_weight(w_oihw):
+    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] bf16 (k = (ky*3+kx)*Cin + c), the layout mb_conv_bf16 reads."""
+    co, ci, kh, kw = w_oihw.shape
+    return w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(torch.bfloat16)
