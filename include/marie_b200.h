@@ -67,6 +67,25 @@ int mb_conv_bf16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, const void*
                  int n_out, const float* bias_dev, int act, void* out_dev, long long out_ld,
                  int out_mode, long long out_plane, void* stream);
 
+/* ---- K5-K7: score-map post-processing ---------------------------------------------------------
+ * Replaces getDetBoxes_core / getDetBoxes / adjustResultCoordinates (marie/models/craft/craft_utils.py:25-98,
+ * 257-274) and the box -> int rect conversion of BoxProcessorCraft.extract_bounding_boxes
+ * (marie/boxes/craft_box_processor.py:499-521) for a batch of n_img score-map pairs [n_img, h, w] fp32.
+ *   labels   [n_img, h, w]  i32   component ids in cv2.connectedComponentsWithStats order (0 = background)
+ *   n_labels [n_img]        i32   number of labels including background
+ *   stats    [n_img, max_labels, 5] i32  cv2 layout (left, top, width, height, area); row 0 is zeroed
+ *   det      [n_img, max_boxes, 4, 2] f32  boxes in heat-map coordinates (getDetBoxes_core `det`)
+ *   adj      [n_img, max_boxes, 4, 2] f32  boxes * (ratio_w*2, ratio_h*2) (adjustResultCoordinates)
+ *   rects    [n_img, max_boxes, 4]  i32   (x, y, w, h) after int32 truncation, boundingRect, +4 px, clamps
+ *   mapper   [n_img, max_boxes]     i32   label id of each box;  n_boxes [n_img] i32
+ * ratios_dev: [n_img, 2] f64 = (ratio_w*2, ratio_h*2) or NULL (= 1); page_hw_dev: [n_img, 2] i32 page (H, W) used
+ * for the clamps, or NULL.  Synchronises `stream` (reports capacity overflow as MB_ERR_STATE). */
+int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* link_dev, int n_img, int h, int w,
+                  float text_threshold, float link_threshold, float low_text, const double* ratios_dev,
+                  const int32_t* page_hw_dev, int32_t* labels_dev, int32_t* n_labels_dev, int32_t* stats_dev,
+                  int max_labels, float* det_dev, float* adj_dev, int32_t* rects_dev, int32_t* mapper_dev,
+                  int32_t* n_boxes_dev, int max_boxes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

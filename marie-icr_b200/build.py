@@ -47,7 +47,12 @@ def _compile_one(src):
     dig = _digest(path)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, ""
-    cmd = ["nvcc", *NVCC_FLAGS, "-c", path, "-o", obj]
+    extra = []
+    with open(path) as f:
+        first = f.readline()
+    if first.startswith("// NVCC_FLAGS:"):
+        extra = first.split(":", 1)[1].split()
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -44,9 +44,8 @@ def conv_bf16(x0, w, bias=None, act=ACT_NONE, x1=None, taps=9, dil=1, n_out=None
     N = rows if n_out is None else n_out
     if planar:
         out = torch.empty((n, N, h, wd), device=x0.device, dtype=torch.float32)
-        assert n == 1 or True
-        mode, out_ld, plane = OUT_F32_PLANAR, 1, h * wd
-        assert n == 1, "planar output is per image"
+        out = torch.empty((N, n, h, wd), device=x0.device, dtype=torch.float32)   # channel planes over the batch
+        mode, out_ld, plane = OUT_F32_PLANAR, 1, n * h * wd
     else:
         out = torch.empty((n, h, wd, N), device=x0.device, dtype=out_dtype)
         mode, out_ld, plane = (OUT_BF16 if out_dtype == torch.bfloat16 else OUT_F32), N, 0
@@ -61,3 +60,31 @@ def pack_conv_weight(w_oihw):
     """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] bf16 (k = (ky*3+kx)*Cin + c), the layout mb_conv_bf16 reads."""
     co, ci, kh, kw = w_oihw.shape
     return w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(torch.bfloat16)
+
+
+def craft_post(text, link, text_threshold, link_threshold, low_text, ratios=None, page_hw=None, max_labels=8192,
+               max_boxes=4096):
+    """Batched score-map post-processing on device. text/link: [n,h,w] fp32 cuda.  Returns a dict of tensors."""
+    assert text.is_cuda and text.dtype == torch.float32 and text.is_contiguous() and link.is_contiguous()
+    n, h, w = text.shape
+    dev = text.device
+    out = dict(
+        labels=torch.empty((n, h, w), dtype=torch.int32, device=dev),
+        n_labels=torch.zeros((n,), dtype=torch.int32, device=dev),
+        stats=torch.zeros((n, max_labels, 5), dtype=torch.int32, device=dev),
+        det=torch.zeros((n, max_boxes, 4, 2), dtype=torch.float32, device=dev),
+        adj=torch.zeros((n, max_boxes, 4, 2), dtype=torch.float32, device=dev),
+        rects=torch.zeros((n, max_boxes, 4), dtype=torch.int32, device=dev),
+        mapper=torch.zeros((n, max_boxes), dtype=torch.int32, device=dev),
+        n_boxes=torch.zeros((n,), dtype=torch.int32, device=dev),
+    )
+    if ratios is not None:
+        ratios = torch.as_tensor(ratios, dtype=torch.float64).reshape(n, 2).to(dev)
+    if page_hw is not None:
+        page_hw = torch.as_tensor(page_hw, dtype=torch.int32).reshape(n, 2).to(dev)
+    _ctx(text).call(
+        "mb_craft_post", ptr(text), ptr(link), c_int(n), c_int(h), c_int(w), c_float(text_threshold),
+        c_float(link_threshold), c_float(low_text), ptr(ratios), ptr(page_hw), ptr(out["labels"]),
+        ptr(out["n_labels"]), ptr(out["stats"]), c_int(max_labels), ptr(out["det"]), ptr(out["adj"]),
+        ptr(out["rects"]), ptr(out["mapper"]), ptr(out["n_boxes"]), c_int(max_boxes), cur_stream())
+    return out
