@@ -86,6 +86,29 @@ int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* link_dev, int
                   int max_labels, float* det_dev, float* adj_dev, int32_t* rects_dev, int32_t* mapper_dev,
                   int32_t* n_boxes_dev, int max_boxes, void* stream);
 
+/* ---- K1: page preprocessing -------------------------------------------------------------------
+ * Replaces imgproc.resize_aspect_ratio + normalizeMeanVariance (marie/models/craft/imgproc.py:45-73,26-32) and
+ * the HWC->CHW / H2D pre-amble of get_prediction (marie/boxes/craft_box_processor.py:96-106).
+ * pages: [n_pages, page_h, page_w, 3] u8 BGR on the device.  The image is resampled to (target_h, target_w) with
+ * cv2's INTER_LINEAR u8 fixed-point arithmetic, pasted on a zero canvas (out_h, out_w) (multiples of 32),
+ * normalised (v-127.5)/127.5 and written as NHWC bf16 with C padded to 4: out [n_pages, out_h, out_w, 4]. */
+int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_pages, int page_h, int page_w,
+                       int target_h, int target_w, int out_h, int out_w, void* out_dev, void* stream);
+
+/* ---- K9: crop -> 384x384 network input ----------------------------------------------------------
+ * Replaces crop_poly_low on the expanded rect (marie/boxes/craft_box_processor.py:42-73,524),
+ * MemoryDataset.__getitem__ (BGR->RGB; marie/models/icr/memory_dataset.py:43-53) and preprocess_image /
+ * preprocess_samples (PIL bicubic 384x384, ToTensor, Normalize(0.5,0.5), stack;
+ * marie/document/trocr_ocr_processor.py:95-101,116-139).
+ * mb_pack_crops: crop i = pages[page_idx[i]][y:y+h+1, x:x+w+1] for rects[i] = (x,y,w,h) (numpy clipping).
+ * mb_pack_fragments: crop i = the [h_i, w_i, 3] u8 BGR image at buf + offsets[i] (hw = [n,2] (h,w)).
+ * layout 0: out [n, 3, 384, 384] bf16 (RGB planes); layout 1: out [n*576, 768] bf16 patch rows
+ * (k = c*256 + py*16 + px), the A operand of the ViT patch embedding.  Both synchronise `stream`. */
+int mb_pack_crops(mb_ctx* ctx, const uint8_t* pages_dev, int page_h, int page_w, const int32_t* rects_dev,
+                  const int32_t* page_idx_dev, int n_crops, void* out_dev, int layout, void* stream);
+int mb_pack_fragments(mb_ctx* ctx, const uint8_t* buf_dev, const long long* offsets_dev, const int32_t* hw_dev,
+                      int n_crops, void* out_dev, int layout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,3 +88,61 @@ def craft_post(text, link, text_threshold, link_threshold, low_text, ratios=None
         ptr(out["n_labels"]), ptr(out["stats"]), c_int(max_labels), ptr(out["det"]), ptr(out["adj"]),
         ptr(out["rects"]), ptr(out["mapper"]), ptr(out["n_boxes"]), c_int(max_boxes), cur_stream())
     return out
+
+
+def craft_canvas_dims(page_h, page_w, canvas_size=None, mag_ratio=1.0):
+    """Size arithmetic of resize_aspect_ratio (marie/models/craft/imgproc.py:45-70): returns
+    (target_h, target_w, out_h, out_w, ratio)."""
+    canvas_size = page_w if canvas_size is None else canvas_size
+    target_size = mag_ratio * max(page_h, page_w)
+    if target_size > canvas_size:
+        target_size = canvas_size
+    ratio = target_size / max(page_h, page_w)
+    th, tw = int(page_h * ratio), int(page_w * ratio)
+    oh = th if th % 32 == 0 else th + (32 - th % 32)
+    ow = tw if tw % 32 == 0 else tw + (32 - tw % 32)
+    return th, tw, oh, ow, ratio
+
+
+def page_preprocess(pages_u8, canvas_size=None, mag_ratio=1.0):
+    """pages_u8: [n, H, W, 3] u8 cuda (BGR). Returns (x [n, oh, ow, 4] bf16 NHWC, ratio)."""
+    assert pages_u8.is_cuda and pages_u8.dtype == torch.uint8 and pages_u8.is_contiguous()
+    n, ph, pw, _ = pages_u8.shape
+    th, tw, oh, ow, ratio = craft_canvas_dims(ph, pw, canvas_size, mag_ratio)
+    out = torch.empty((n, oh, ow, 4), dtype=torch.bfloat16, device=pages_u8.device)
+    _ctx(pages_u8).call("mb_page_preprocess", ptr(pages_u8), c_int(n), c_int(ph), c_int(pw), c_int(th), c_int(tw),
+                        c_int(oh), c_int(ow), ptr(out), cur_stream())
+    return out, ratio
+
+
+def pack_crops(pages_u8, rects, page_idx, layout=0):
+    """rects [n,4] i32 (x,y,w,h), page_idx [n] i32 on device -> [n,3,384,384] or [n*576,768] bf16."""
+    n = rects.shape[0]
+    _, ph, pw, _ = pages_u8.shape
+    shape = (n, 3, 384, 384) if layout == 0 else (n * 576, 768)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=pages_u8.device)
+    _ctx(pages_u8).call("mb_pack_crops", ptr(pages_u8), c_int(ph), c_int(pw), ptr(rects.contiguous()),
+                        ptr(page_idx.contiguous()), c_int(n), ptr(out), c_int(layout), cur_stream())
+    return out
+
+
+def pack_fragments(fragments, device="cuda", layout=0):
+    """fragments: list of [h,w,3] u8 BGR numpy arrays (host).  One H2D copy of the packed bytes."""
+    import numpy as np
+    n = len(fragments)
+    sizes = [int(f.shape[0]) * int(f.shape[1]) * 3 for f in fragments]
+    offsets = np.zeros(n, np.int64)
+    if n > 1:
+        offsets[1:] = np.cumsum(np.asarray(sizes[:-1], np.int64))
+    buf = np.empty(int(sum(sizes)), np.uint8)
+    for f, o, s in zip(fragments, offsets, sizes):
+        buf[o:o + s] = np.ascontiguousarray(f, dtype=np.uint8).reshape(-1)
+    hw = np.array([[f.shape[0], f.shape[1]] for f in fragments], np.int32).reshape(n, 2)
+    dbuf = torch.from_numpy(buf).to(device)
+    doff = torch.from_numpy(offsets).to(device)
+    dhw = torch.from_numpy(hw).to(device)
+    shape = (n, 3, 384, 384) if layout == 0 else (n * 576, 768)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=device)
+    _ctx(dbuf).call("mb_pack_fragments", ptr(dbuf), ptr(doff), ptr(dhw), c_int(n), ptr(out), c_int(layout),
+                    cur_stream())
+    return out
