@@ -44,16 +44,23 @@ const char* mb_version(void);
 int mb_init(int device, mb_ctx** out);
 void mb_free(mb_ctx* ctx);
 const char* mb_last_error(const mb_ctx* ctx);
+/* 16-bit element type of every activation / weight buffer that crosses this ABI ("16-bit" below): fp16 (default)
+ * or bf16; accumulation is always fp32.  fp16 is the reference's own TrOCR dtype (`.half()`,
+ * marie/document/trocr_ocr_processor.py:75-76) and keeps the CRAFT score maps within 1e-2 of the fp32 reference
+ * (bf16's 8-bit mantissa does not: DESIGN.md §precision).  Changing the dtype unloads any loaded weights. */
+enum { MB_DTYPE_BF16 = 0, MB_DTYPE_F16 = 1 };
+int mb_set_dtype(mb_ctx* ctx, int dtype);
+int mb_get_dtype(const mb_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py "gpu_launches"). */
 unsigned long long mb_launch_count(const mb_ctx* ctx);
 
 /* ---- tensor-core building block --------------------------------------------------------------
- * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual); bf16 operands, fp32 accumulation in TMEM.
+ * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual); 16-bit operands, fp32 accumulation in TMEM.
  * Replaces the cuBLAS calls behind nn.Linear in timm's ViT blocks (marie/models/unilm/trocr/deit.py:105-146)
  * and fairseq's TransformerDecoder (built at marie/models/unilm/trocr/trocr_models.py:142-147).
  * K must be a multiple of 64; lda/ldw/out_ld in elements. act: 0 none, 1 relu, 2 gelu(erf).
- * out_mode: 0 bf16, 1 fp32. */
-int mb_gemm_bf16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w,
+ * out_mode: 0 16-bit, 1 fp32. */
+int mb_gemm16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w,
                  int M, int N, int K, const float* bias_dev, int act, const void* residual_dev,
                  long long res_ld, void* out_dev, long long out_ld, int out_mode, void* stream);
 
@@ -62,7 +69,7 @@ int mb_gemm_bf16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_de
  * Weights are [n_rows_w, taps*(c0+c1)] with k = (ky*3+kx)*(c0+c1) + c.  Replaces cuDNN behind nn.Conv2d in
  * marie/models/craft/basenet/vgg16_bn.py:33-47 and marie/models/craft/craft.py:14-51.
  * out_mode 2 writes fp32 channel planes `out_plane` elements apart (the score maps). */
-int mb_conv_bf16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, const void* a1_dev, int c1,
+int mb_conv16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, const void* a1_dev, int c1,
                  int a1_ld, int n, int h, int w, int taps, int dil, const void* w_dev, int n_rows_w,
                  int n_out, const float* bias_dev, int act, void* out_dev, long long out_ld,
                  int out_mode, long long out_plane, void* stream);
@@ -91,7 +98,7 @@ int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* link_dev, int
  * the HWC->CHW / H2D pre-amble of get_prediction (marie/boxes/craft_box_processor.py:96-106).
  * pages: [n_pages, page_h, page_w, 3] u8 BGR on the device.  The image is resampled to (target_h, target_w) with
  * cv2's INTER_LINEAR u8 fixed-point arithmetic, pasted on a zero canvas (out_h, out_w) (multiples of 32),
- * normalised (v-127.5)/127.5 and written as NHWC bf16 with C padded to 4: out [n_pages, out_h, out_w, 4]. */
+ * normalised (v-127.5)/127.5 and written as NHWC 16-bit with C padded to 4: out [n_pages, out_h, out_w, 4]. */
 int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_pages, int page_h, int page_w,
                        int target_h, int target_w, int out_h, int out_w, void* out_dev, void* stream);
 
@@ -102,12 +109,24 @@ int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_pages, int p
  * marie/document/trocr_ocr_processor.py:95-101,116-139).
  * mb_pack_crops: crop i = pages[page_idx[i]][y:y+h+1, x:x+w+1] for rects[i] = (x,y,w,h) (numpy clipping).
  * mb_pack_fragments: crop i = the [h_i, w_i, 3] u8 BGR image at buf + offsets[i] (hw = [n,2] (h,w)).
- * layout 0: out [n, 3, 384, 384] bf16 (RGB planes); layout 1: out [n*576, 768] bf16 patch rows
+ * layout 0: out [n, 3, 384, 384] 16-bit (RGB planes); layout 1: out [n*576, 768] 16-bit patch rows
  * (k = c*256 + py*16 + px), the A operand of the ViT patch embedding.  Both synchronise `stream`. */
 int mb_pack_crops(mb_ctx* ctx, const uint8_t* pages_dev, int page_h, int page_w, const int32_t* rects_dev,
                   const int32_t* page_idx_dev, int n_crops, void* out_dev, int layout, void* stream);
 int mb_pack_fragments(mb_ctx* ctx, const uint8_t* buf_dev, const long long* offsets_dev, const int32_t* hw_dev,
                       int n_crops, void* out_dev, int layout, void* stream);
+
+/* ---- K2-K4: CRAFT network ------------------------------------------------------------------------
+ * mb_load_craft: takes the flat blob produced by marie-icr_b200/weights.py:pack_craft from the reference's own
+ * state dict (replaces CRAFT() + load_state_dict + .cuda() in BoxProcessorCraft.__load,
+ * marie/boxes/craft_box_processor.py:260-285; DataParallel is dropped: SURVEY.md C1).
+ * mb_craft_forward: replaces CRAFT.forward (marie/models/craft/craft.py:59-81).  x: [n, h, w, 4] 16-bit NHWC
+ * (mb_page_preprocess output), h and w multiples of 32.  scores: [2, n, h/2, w/2] fp32 — plane 0 = text/region,
+ * plane 1 = link/affinity (y[..., 0] / y[..., 1] of the reference).  feature_dev (optional, may be NULL):
+ * [n, h/2, w/2, 64] 16-bit, channels 0..31 = the reference's `feature`, 32..63 zero. */
+int mb_load_craft(mb_ctx* ctx, const void* blob_host, size_t nbytes);
+int mb_craft_forward(mb_ctx* ctx, const void* x_dev, int n, int h, int w, float* scores_dev, void* feature_dev,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,18 @@ class Context:
         self.check(fn(self.handle, *args), name)
 
     @property
+    def torch_dtype(self):
+        """torch dtype of the library's 16-bit buffers (mb_get_dtype): float16 (default) or bfloat16."""
+        import torch
+        self.lib.mb_get_dtype.argtypes = [c_void_p]
+        return torch.float16 if self.lib.mb_get_dtype(self.handle) == 1 else torch.bfloat16
+
+    def set_dtype(self, dtype):
+        """dtype: torch.float16 / torch.bfloat16 (or 'fp16' / 'bf16').  Only before weights are loaded."""
+        code = 1 if str(dtype) in ("torch.float16", "fp16", "f16", "float16") else 0
+        self.call("mb_set_dtype", c_int(code))
+
+    @property
     def launches(self):
         return int(self.lib.mb_launch_count(self.handle))
 

@@ -65,6 +65,15 @@ extern "C" void mb_free(mb_ctx* ctx) {
     delete ctx;
 }
 
+extern "C" int mb_set_dtype(mb_ctx* ctx, int dtype) {
+    if (!ctx) return MB_ERR_ARG;
+    if (dtype != MB_DTYPE_BF16 && dtype != MB_DTYPE_F16) return mb_set_err(ctx, MB_ERR_ARG, "mb_set_dtype: unknown dtype %d", dtype);
+    if ((dtype == MB_DTYPE_F16) != (ctx->f16 != 0)) mb_free_models(ctx);   // packed weights are dtype-specific: unload
+    ctx->f16 = dtype == MB_DTYPE_F16;
+    return MB_OK;
+}
+extern "C" int mb_get_dtype(const mb_ctx* ctx) { return ctx && ctx->f16 ? MB_DTYPE_F16 : MB_DTYPE_BF16; }
+
 extern "C" const char* mb_last_error(const mb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
 extern "C" unsigned long long mb_launch_count(const mb_ctx* ctx) { return ctx ? ctx->launches : 0; }

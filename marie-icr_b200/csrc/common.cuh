@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -28,6 +29,8 @@ struct mb_ctx {
     struct TrocrModel* trocr = nullptr;
     // device-side diagnostic word written by kernels before __trap()
     unsigned int* dev_diag = nullptr;
+    // 16-bit element type of activations / weights: 0 = bf16, 1 = fp16 (default; mb_set_dtype)
+    int f16 = 1;
     // kernel launch counter (bench.py "gpu_launches")
     unsigned long long launches = 0;
 };
@@ -98,6 +101,34 @@ __device__ __forceinline__ float bf16_bits_to_f32(unsigned short b) {
 __device__ __forceinline__ unsigned int pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<unsigned int*>(&v);
+}
+// Runtime-selected 16-bit element type (f16 != 0: IEEE half, else bfloat16).  Buffers are typed `bf16*` in the
+// sources purely as "16-bit element"; all arithmetic is fp32.
+__device__ __forceinline__ float2 unpack2(unsigned int v, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+__device__ __forceinline__ unsigned int pack2(float lo, float hi, int f16) {
+    if (f16) {
+        lo = fminf(fmaxf(lo, -65504.f), 65504.f);   // saturate instead of overflowing to inf
+        hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<unsigned int*>(&h);
+    }
+    return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float load16(const bf16* p, int f16) {
+    const unsigned short b = *reinterpret_cast<const unsigned short*>(p);
+    if (f16) return __half2float(__ushort_as_half(b));
+    return bf16_bits_to_f32(b);
+}
+__device__ __forceinline__ void store16(bf16* p, float v, int f16) {
+    if (f16) {
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+    } else {
+        *p = __float2bfloat16_rn(v);
+    }
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

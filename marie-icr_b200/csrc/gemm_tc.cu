@@ -46,6 +46,7 @@ struct KParams {
     long long out_ld;
     int out_mode;
     long long out_plane;
+    int f16;               // operand / 16-bit output element type: 0 = bf16, 1 = fp16
     unsigned int* diag;
 };
 
@@ -238,7 +239,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+            const uint32_t ab_fmt = p.f16 ? 0u : ((1u << 7) | (1u << 10));   // a/b format: 0 = f16, 1 = bf16
+            const uint32_t idesc = (1u << 4) | ab_fmt |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -312,12 +314,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                f[j4 * 8 + 2 * t] += __uint_as_float(rw[t] << 16);
-                                f[j4 * 8 + 2 * t + 1] += __uint_as_float(rw[t] & 0xFFFF0000u);
+                                const float2 rr = unpack2(rw[t], p.f16);
+                                f[j4 * 8 + 2 * t] += rr.x;
+                                f[j4 * 8 + 2 * t + 1] += rr.y;
                             }
                         }
                     } else {
-                        for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(r[j]);
+                        for (int j = 0; j < ncols; ++j) f[j] += load16(r + j, p.f16);
                     }
                 }
                 if (p.out_mode == MB_OUT_BF16) {
@@ -326,14 +329,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             uint4 ov;
-                            ov.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
-                            ov.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
-                            ov.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
-                            ov.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+                            ov.x = pack2(f[j4 * 8 + 0], f[j4 * 8 + 1], p.f16);
+                            ov.y = pack2(f[j4 * 8 + 2], f[j4 * 8 + 3], p.f16);
+                            ov.z = pack2(f[j4 * 8 + 4], f[j4 * 8 + 5], p.f16);
+                            ov.w = pack2(f[j4 * 8 + 6], f[j4 * 8 + 7], p.f16);
                             reinterpret_cast<uint4*>(o)[j4] = ov;
                         }
                     } else {
-                        for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(f[j]);
+                        for (int j = 0; j < ncols; ++j) store16(o + j, f[j], p.f16);
                     }
                 } else if (p.out_mode == MB_OUT_F32) {
                     float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n0;
@@ -388,14 +391,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC activation map: dims {C, W, H, N}, box {64, 128, 1, 1}
-int encode_act_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int c, int ld, int n, int h, int w) {
+int encode_act_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int c, int ld, int n, int h, int w, int f16) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
     cuuint32_t box[4] = {BLOCK_K, BLOCK_M, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, es,
+    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -404,14 +407,14 @@ int encode_act_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int c, int ld,
     return 0;
 }
 
-int encode_wgt_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int ktot, int rows, int block_n) {
+int encode_wgt_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int ktot, int rows, int block_n, int f16) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
     cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)block_n};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, es,
+    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -462,19 +465,20 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.bias = g.bias; p.act = g.act;
     p.residual = g.residual; p.res_ld = g.res_ld;
     p.out = g.out; p.out_ld = g.out_ld; p.out_mode = g.out_mode; p.out_plane = g.out_plane;
+    p.f16 = ctx->f16;
     p.diag = ctx->dev_diag;
 
     CUtensorMap tmA0, tmA1, tmB;
-    int rc = encode_act_map(ctx, &tmA0, g.a0, g.c0, g.a0_ld, g.n, g.h, g.w);
+    int rc = encode_act_map(ctx, &tmA0, g.a0, g.c0, g.a0_ld, g.n, g.h, g.w, ctx->f16);
     if (rc) return rc;
     if (g.c1 > 0) {
         MB_REQUIRE(ctx, g.a1 != nullptr, "tap_gemm: c1>0 but a1 null");
-        rc = encode_act_map(ctx, &tmA1, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w);
+        rc = encode_act_map(ctx, &tmA1, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w, ctx->f16);
         if (rc) return rc;
     } else {
         tmA1 = tmA0;
     }
-    rc = encode_wgt_map(ctx, &tmB, g.wgt, g.taps * (g.c0 + g.c1), g.n_rows_w, block_n);
+    rc = encode_wgt_map(ctx, &tmB, g.wgt, g.taps * (g.c0 + g.c1), g.n_rows_w, block_n, ctx->f16);
     if (rc) return rc;
 
     const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
@@ -491,7 +495,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     return 0;
 }
 
-extern "C" int mb_gemm_bf16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w,
+extern "C" int mb_gemm16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w,
                             int M, int N, int K, const float* bias_dev, int act, const void* residual_dev,
                             long long res_ld, void* out_dev, long long out_ld, int out_mode, void* stream) {
     if (!ctx) return MB_ERR_ARG;
@@ -506,7 +510,7 @@ extern "C" int mb_gemm_bf16(mb_ctx* ctx, const void* a_dev, long long lda, const
     return mb_tap_gemm(ctx, g, (cudaStream_t)stream);
 }
 
-extern "C" int mb_conv_bf16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, const void* a1_dev, int c1,
+extern "C" int mb_conv16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, const void* a1_dev, int c1,
                             int a1_ld, int n, int h, int w, int taps, int dil, const void* w_dev,
                             int n_rows_w, int n_out, const float* bias_dev, int act, void* out_dev,
                             long long out_ld, int out_mode, long long out_plane, void* stream) {

@@ -37,7 +37,7 @@ __global__ void lin_coef_kernel(LinCoef* __restrict__ tab, int ssize, int dsize)
 
 __global__ void page_preprocess_kernel(const uint8_t* __restrict__ pages, long long page_stride, int sh, int sw,
                                        const LinCoef* __restrict__ xtab, const LinCoef* __restrict__ ytab, int th,
-                                       int tw, int oh, int ow, bf16* __restrict__ out) {
+                                       int tw, int oh, int ow, bf16* __restrict__ out, int f16) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((float)i - 127.5f) / 127.5f;
     __syncthreads();
@@ -64,8 +64,8 @@ __global__ void page_preprocess_kernel(const uint8_t* __restrict__ pages, long l
         v0 = lut[res[0]]; v1 = lut[res[1]]; v2 = lut[res[2]];
     }
     uint2 o;
-    o.x = pack_bf16x2(v0, v1);
-    o.y = pack_bf16x2(v2, 0.f);
+    o.x = pack2(v0, v1, f16);
+    o.y = pack2(v2, 0.f, f16);
     reinterpret_cast<uint2*>(out)[((long long)page * oh + oy) * ow + ox] = o;
 }
 
@@ -124,7 +124,8 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 // grid = (OUT / TILE_ROWS, n_crops).  layout 0: [N,3,384,384] (RGB planes); layout 1: patch rows
 // [N*576, 768] with k = c*256 + py*16 + px (the A operand of the ViT patch-embedding GEMM).
 __global__ void __launch_bounds__(K9_THREADS)
-crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, int layout, int* __restrict__ err) {
+crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, int layout, int* __restrict__ err,
+                   int f16) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ float lut[256];
     __shared__ int s_r0, s_r1;
@@ -204,15 +205,15 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
         const long long n_img = blockIdx.y;
         if (layout == 0) {
             bf16* o = out + n_img * 3 * OUT * OUT + (long long)yy * OUT + xx;
-            o[0] = __float2bfloat16_rn(r);
-            o[OUT * OUT] = __float2bfloat16_rn(g);
-            o[2 * OUT * OUT] = __float2bfloat16_rn(b);
+            store16(o, r, f16);
+            store16(o + OUT * OUT, g, f16);
+            store16(o + 2 * OUT * OUT, b, f16);
         } else {
             const int patch = (yy >> 4) * 24 + (xx >> 4);
             bf16* o = out + (n_img * 576 + patch) * 768 + (yy & 15) * 16 + (xx & 15);
-            o[0] = __float2bfloat16_rn(r);
-            o[256] = __float2bfloat16_rn(g);
-            o[512] = __float2bfloat16_rn(b);
+            store16(o, r, f16);
+            store16(o + 256, g, f16);
+            store16(o + 512, b, f16);
         }
     }
 }
@@ -254,7 +255,7 @@ int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int
     }
     MB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), stream));
     dim3 grid(OUT / TILE_ROWS, n);
-    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err);
+    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err, ctx->f16);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -289,7 +290,7 @@ extern "C" int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_p
     MB_LAUNCH_CHECK(ctx);
     dim3 grid(mb_cdiv(out_w, 256), out_h, n_pages);
     page_preprocess_kernel<<<grid, 256, 0, stream>>>(pages_dev, (long long)page_h * page_w * 3, page_h, page_w, xtab,
-                                                     ytab, target_h, target_w, out_h, out_w, (bf16*)out_dev);
+                                                     ytab, target_h, target_w, out_h, out_w, (bf16*)out_dev, ctx->f16);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -13,9 +13,11 @@ def _ctx(t):
     return Context.get(t.device.index or 0)
 
 
-def gemm_bf16(a, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16, n_out=None):
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w bf16 row-major; K % 64 == 0."""
-    assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+def gemm16(a, w, bias=None, act=ACT_NONE, residual=None, out_dtype=None, n_out=None):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w 16-bit row-major; K % 64 == 0."""
+    dt = _ctx(a).torch_dtype
+    out_dtype = dt if out_dtype is None else out_dtype
+    assert a.is_cuda and a.dtype == dt and w.dtype == dt, (a.dtype, w.dtype, dt)
     assert a.stride(-1) == 1 and w.is_contiguous()
     M, K = a.shape
     n_rows = w.shape[0]
@@ -24,17 +26,18 @@ def gemm_bf16(a, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.bflo
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= N
     _ctx(a).call(
-        "mb_gemm_bf16", ptr(a), c_ll(a.stride(0)), ptr(w), c_int(n_rows), c_int(M), c_int(N), c_int(K),
+        "mb_gemm16", ptr(a), c_ll(a.stride(0)), ptr(w), c_int(n_rows), c_int(M), c_int(N), c_int(K),
         ptr(bias), c_int(act), ptr(residual), c_ll(residual.stride(0) if residual is not None else 0),
-        ptr(out), c_ll(out.stride(0)), c_int(OUT_BF16 if out_dtype == torch.bfloat16 else OUT_F32),
+        ptr(out), c_ll(out.stride(0)), c_int(OUT_F32 if out_dtype == torch.float32 else OUT_BF16),
         cur_stream())
     return out
 
 
-def conv_bf16(x0, w, bias=None, act=ACT_NONE, x1=None, taps=9, dil=1, n_out=None, out_dtype=torch.bfloat16,
-              planar=False):
-    """NHWC implicit-GEMM convolution. x0/x1: [N,H,W,C] bf16; w: [rows, taps*(C0+C1)] bf16."""
-    assert x0.is_cuda and x0.dtype == torch.bfloat16 and x0.is_contiguous()
+def conv16(x0, w, bias=None, act=ACT_NONE, x1=None, taps=9, dil=1, n_out=None, out_dtype=None, planar=False):
+    """NHWC implicit-GEMM convolution. x0/x1: [N,H,W,C] 16-bit; w: [rows, taps*(C0+C1)] 16-bit."""
+    dt = _ctx(x0).torch_dtype
+    out_dtype = dt if out_dtype is None else out_dtype
+    assert x0.is_cuda and x0.dtype == dt and w.dtype == dt and x0.is_contiguous()
     n, h, wd, c0 = x0.shape
     c1 = 0
     if x1 is not None:
@@ -43,23 +46,22 @@ def conv_bf16(x0, w, bias=None, act=ACT_NONE, x1=None, taps=9, dil=1, n_out=None
     rows = w.shape[0]
     N = rows if n_out is None else n_out
     if planar:
-        out = torch.empty((n, N, h, wd), device=x0.device, dtype=torch.float32)
         out = torch.empty((N, n, h, wd), device=x0.device, dtype=torch.float32)   # channel planes over the batch
         mode, out_ld, plane = OUT_F32_PLANAR, 1, n * h * wd
     else:
         out = torch.empty((n, h, wd, N), device=x0.device, dtype=out_dtype)
-        mode, out_ld, plane = (OUT_BF16 if out_dtype == torch.bfloat16 else OUT_F32), N, 0
+        mode, out_ld, plane = (OUT_F32 if out_dtype == torch.float32 else OUT_BF16), N, 0
     _ctx(x0).call(
-        "mb_conv_bf16", ptr(x0), c_int(c0), c_int(c0), ptr(x1), c_int(c1), c_int(c1), c_int(n), c_int(h),
+        "mb_conv16", ptr(x0), c_int(c0), c_int(c0), ptr(x1), c_int(c1), c_int(c1), c_int(n), c_int(h),
         c_int(wd), c_int(taps), c_int(dil), ptr(w), c_int(rows), c_int(N), ptr(bias), c_int(act), ptr(out),
         c_ll(out_ld), c_int(mode), c_ll(plane), cur_stream())
     return out
 
 
-def pack_conv_weight(w_oihw):
-    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] bf16 (k = (ky*3+kx)*Cin + c), the layout mb_conv_bf16 reads."""
+def pack_conv_weight(w_oihw, dtype=torch.float16):
+    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] 16-bit (k = (ky*3+kx)*Cin + c), the layout mb_conv16 reads."""
     co, ci, kh, kw = w_oihw.shape
-    return w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(torch.bfloat16)
+    return w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(dtype)
 
 
 def craft_post(text, link, text_threshold, link_threshold, low_text, ratios=None, page_hw=None, max_labels=8192,
@@ -109,7 +111,7 @@ def page_preprocess(pages_u8, canvas_size=None, mag_ratio=1.0):
     assert pages_u8.is_cuda and pages_u8.dtype == torch.uint8 and pages_u8.is_contiguous()
     n, ph, pw, _ = pages_u8.shape
     th, tw, oh, ow, ratio = craft_canvas_dims(ph, pw, canvas_size, mag_ratio)
-    out = torch.empty((n, oh, ow, 4), dtype=torch.bfloat16, device=pages_u8.device)
+    out = torch.empty((n, oh, ow, 4), dtype=_ctx(pages_u8).torch_dtype, device=pages_u8.device)
     _ctx(pages_u8).call("mb_page_preprocess", ptr(pages_u8), c_int(n), c_int(ph), c_int(pw), c_int(th), c_int(tw),
                         c_int(oh), c_int(ow), ptr(out), cur_stream())
     return out, ratio
@@ -120,7 +122,7 @@ def pack_crops(pages_u8, rects, page_idx, layout=0):
     n = rects.shape[0]
     _, ph, pw, _ = pages_u8.shape
     shape = (n, 3, 384, 384) if layout == 0 else (n * 576, 768)
-    out = torch.empty(shape, dtype=torch.bfloat16, device=pages_u8.device)
+    out = torch.empty(shape, dtype=_ctx(pages_u8).torch_dtype, device=pages_u8.device)
     _ctx(pages_u8).call("mb_pack_crops", ptr(pages_u8), c_int(ph), c_int(pw), ptr(rects.contiguous()),
                         ptr(page_idx.contiguous()), c_int(n), ptr(out), c_int(layout), cur_stream())
     return out
@@ -142,7 +144,23 @@ def pack_fragments(fragments, device="cuda", layout=0):
     doff = torch.from_numpy(offsets).to(device)
     dhw = torch.from_numpy(hw).to(device)
     shape = (n, 3, 384, 384) if layout == 0 else (n * 576, 768)
-    out = torch.empty(shape, dtype=torch.bfloat16, device=device)
+    out = torch.empty(shape, dtype=_ctx(dbuf).torch_dtype, device=device)
     _ctx(dbuf).call("mb_pack_fragments", ptr(dbuf), ptr(doff), ptr(dhw), c_int(n), ptr(out), c_int(layout),
                     cur_stream())
     return out
+
+
+def load_craft(blob: bytes, device=0):
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    Context.get(device).call("mb_load_craft", buf, ctypes.c_size_t(len(blob)))
+
+
+def craft_forward(x, want_feature=False):
+    """x: [n,h,w,4] 16-bit NHWC (page_preprocess output). Returns scores [2,n,h/2,w/2] fp32 (text, link)
+    and optionally feature [n,h/2,w/2,64]."""
+    assert x.is_cuda and x.dtype == _ctx(x).torch_dtype and x.is_contiguous() and x.shape[3] == 4
+    n, h, w, _ = x.shape
+    scores = torch.empty((2, n, h // 2, w // 2), dtype=torch.float32, device=x.device)
+    feat = torch.empty((n, h // 2, w // 2, 64), dtype=x.dtype, device=x.device) if want_feature else None
+    _ctx(x).call("mb_craft_forward", ptr(x), c_int(n), c_int(h), c_int(w), ptr(scores), ptr(feat), cur_stream())
+    return (scores, feat) if want_feature else scores

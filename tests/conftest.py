@@ -19,3 +19,12 @@ def cuda_ctx():
         pytest.skip("no CUDA device")
     from marie_icr_b200._lib import Context
     return Context.get(0)
+
+
+@pytest.fixture(params=["fp16", "bf16"])
+def dtype16(request, cuda_ctx):
+    """Runs the test once per 16-bit element type of the library; restores the fp16 default afterwards."""
+    import torch
+    cuda_ctx.set_dtype(request.param)
+    yield torch.float16 if request.param == "fp16" else torch.bfloat16
+    cuda_ctx.set_dtype("fp16")

@@ -1,4 +1,4 @@
-"""tap-GEMM (tcgen05/TMA) against torch fp32 references on the same bf16 operands.
+"""tap-GEMM (tcgen05/TMA) against torch fp32 references on the same 16-bit operands (fp16 and bf16).
 
 Tolerance: operands are identical bf16 values, accumulation is fp32 on both sides, so the only differences
 are summation order and the final bf16 rounding of the output: |err| <= 2^-8 * |ref| + 1e-3*scale.
@@ -21,62 +21,62 @@ def _close(out, ref, name):
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 128), (577 * 3, 768, 768), (1000, 2304, 768),
                                    (37, 1024, 4096), (4096, 50265, 1024), (130, 96, 192)])
-def test_gemm_plain(cuda_ctx, M, N, K):
+def test_gemm_plain(cuda_ctx, dtype16, M, N, K):
     from marie_icr_b200 import ops
     torch.manual_seed(M + N + K)
-    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
-    out = ops.gemm_bf16(a, w)
+    a = torch.randn(M, K, device="cuda").to(dtype16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(dtype16)
+    out = ops.gemm16(a, w)
     ref = a.float() @ w.float().t()
     _close(out, ref, f"gemm {M}x{N}x{K}")
 
 
-def test_gemm_epilogues(cuda_ctx):
+def test_gemm_epilogues(cuda_ctx, dtype16):
     from marie_icr_b200 import ops
     torch.manual_seed(1)
     M, N, K = 700, 768, 256
-    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    a = torch.randn(M, K, device="cuda").to(dtype16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(dtype16)
     bias = torch.randn(N, device="cuda")
-    res = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    res = torch.randn(M, N, device="cuda").to(dtype16)
     base = a.float() @ w.float().t() + bias
-    _close(ops.gemm_bf16(a, w, bias=bias), base, "bias")
-    _close(ops.gemm_bf16(a, w, bias=bias, act=ops.ACT_RELU), base.relu(), "relu")
-    _close(ops.gemm_bf16(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(base), "gelu")
-    _close(ops.gemm_bf16(a, w, bias=bias, residual=res), base + res.float(), "residual")
-    out32 = ops.gemm_bf16(a, w, bias=bias, out_dtype=torch.float32)
+    _close(ops.gemm16(a, w, bias=bias), base, "bias")
+    _close(ops.gemm16(a, w, bias=bias, act=ops.ACT_RELU), base.relu(), "relu")
+    _close(ops.gemm16(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(base), "gelu")
+    _close(ops.gemm16(a, w, bias=bias, residual=res), base + res.float(), "residual")
+    out32 = ops.gemm16(a, w, bias=bias, out_dtype=torch.float32)
     assert out32.dtype == torch.float32
     assert (out32 - base).abs().max().item() < 2e-3 * base.abs().max().item()
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,dil", [(1, 16, 128, 64, 64, 1), (2, 24, 200, 128, 256, 1),
                                                (1, 20, 124, 512, 1024, 6), (1, 33, 70, 64, 32, 1)])
-def test_conv3x3(cuda_ctx, n, h, w, cin, cout, dil):
+def test_conv3x3(cuda_ctx, dtype16, n, h, w, cin, cout, dil):
     from marie_icr_b200 import ops
     torch.manual_seed(cin + cout + w)
-    x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
-    wt = (torch.randn(cout, cin, 3, 3, device="cuda") * (9 * cin) ** -0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, cin, device="cuda").to(dtype16)
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda") * (9 * cin) ** -0.5).to(dtype16)
     bias = torch.randn(cout, device="cuda") * 0.1
-    out = ops.conv_bf16(x, ops.pack_conv_weight(wt), bias=bias, act=ops.ACT_RELU, taps=9, dil=dil)
+    out = ops.conv16(x, ops.pack_conv_weight(wt, dtype16), bias=bias, act=ops.ACT_RELU, taps=9, dil=dil)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=dil, dilation=dil).relu()
     _close(out, ref.permute(0, 2, 3, 1), f"conv3x3 {cin}->{cout} d{dil}")
 
 
-def test_conv1x1_concat_and_planar(cuda_ctx):
+def test_conv1x1_concat_and_planar(cuda_ctx, dtype16):
     from marie_icr_b200 import ops
     torch.manual_seed(5)
     n, h, w = 1, 31, 150
-    x0 = torch.randn(n, h, w, 128, device="cuda").to(torch.bfloat16)
-    x1 = torch.randn(n, h, w, 64, device="cuda").to(torch.bfloat16)
-    wt = (torch.randn(64, 192, 1, 1, device="cuda") * 192 ** -0.5).to(torch.bfloat16)
-    out = ops.conv_bf16(x0, ops.pack_conv_weight(wt), x1=x1, taps=1)
+    x0 = torch.randn(n, h, w, 128, device="cuda").to(dtype16)
+    x1 = torch.randn(n, h, w, 64, device="cuda").to(dtype16)
+    wt = (torch.randn(64, 192, 1, 1, device="cuda") * 192 ** -0.5).to(dtype16)
+    out = ops.conv16(x0, ops.pack_conv_weight(wt, dtype16), x1=x1, taps=1)
     ref = F.conv2d(torch.cat([x0, x1], 3).float().permute(0, 3, 1, 2), wt.float())
     _close(out, ref.permute(0, 2, 3, 1), "conv1x1 concat")
     # small-N head layer written as fp32 planes (rows padded to 16 in the weight matrix)
     w2 = torch.zeros(16, 64, device="cuda")
     w2[:2] = torch.randn(2, 64, device="cuda") * 0.1
     b2 = torch.tensor([0.3, -0.2], device="cuda")
-    planes = ops.conv_bf16(x1, w2.to(torch.bfloat16), bias=b2, taps=1, n_out=2, planar=True)
-    ref2 = F.conv2d(x1.float().permute(0, 3, 1, 2), w2[:2].to(torch.bfloat16).float()[:, :, None, None], b2)
+    planes = ops.conv16(x1, w2.to(dtype16), bias=b2, taps=1, n_out=2, planar=True)
+    ref2 = F.conv2d(x1.float().permute(0, 3, 1, 2), w2[:2].to(dtype16).float()[:, :, None, None], b2)
     assert planes.shape == (2, 1, h, w)
     assert (planes[:, 0] - ref2[0]).abs().max().item() < 2e-3 * ref2.abs().max().item() + 1e-4

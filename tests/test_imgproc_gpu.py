@@ -6,12 +6,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _bf16(x):
-    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16)
+def _q(x, dt):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dt)
 
 
 @pytest.mark.parametrize("ph,pw", [(330, 255), (825, 640), (200, 300), (3300, 2550)])
-def test_page_preprocess(cuda_ctx, ph, pw):
+def test_page_preprocess(cuda_ctx, dtype16, ph, pw):
     from marie_icr_b200 import ops
     from oracle import resample
     rng = np.random.default_rng(ph)
@@ -23,11 +23,11 @@ def test_page_preprocess(cuda_ctx, ph, pw):
         assert r == ratio
         got = out[i].cpu()
         assert got.shape[:2] == ref.shape[:2]
-        assert torch.equal(got[..., :3], _bf16(ref)), "preprocessed page differs from cv2 fixed-point resize"
+        assert torch.equal(got[..., :3], _q(ref, dtype16)), "preprocessed page differs from cv2 fixed-point resize"
         assert torch.all(got[..., 3] == 0)
 
 
-def test_pack_fragments_exact(cuda_ctx):
+def test_pack_fragments_exact(cuda_ctx, dtype16):
     from marie_icr_b200 import ops
     from oracle import resample
     rng = np.random.default_rng(3)
@@ -38,14 +38,14 @@ def test_pack_fragments_exact(cuda_ctx):
     torch.cuda.synchronize()
     for i, f in enumerate(frags):
         ref = resample.fragment_to_input(f)
-        assert torch.equal(out[i].cpu(), _bf16(ref)), f"fragment {shapes[i]} differs from PIL bicubic"
+        assert torch.equal(out[i].cpu(), _q(ref, dtype16)), f"fragment {shapes[i]} differs from PIL bicubic"
     # patch layout carries the same values
     outp = ops.pack_fragments(frags[:3], layout=1).reshape(3, 24, 24, 3, 16, 16)
     chw = outp.permute(0, 3, 1, 4, 2, 5).reshape(3, 3, 384, 384)
     assert torch.equal(chw, out[:3])
 
 
-def test_pack_crops_from_page(cuda_ctx):
+def test_pack_crops_from_page(cuda_ctx, dtype16):
     from marie_icr_b200 import ops
     from oracle import resample, craft_post
     rng = np.random.default_rng(4)
@@ -56,4 +56,4 @@ def test_pack_crops_from_page(cuda_ctx):
     torch.cuda.synchronize()
     for i in range(len(rects)):
         frag = craft_post.crop_rect(pages[pidx[i]], rects[i])
-        assert torch.equal(out[i].cpu(), _bf16(resample.fragment_to_input(frag))), f"crop {i}"
+        assert torch.equal(out[i].cpu(), _q(resample.fragment_to_input(frag), dtype16)), f"crop {i}"
