@@ -1,0 +1,352 @@
+"""CPU restatement of the TrOCR recogniser in plain PyTorch fp32 (TEST INFRASTRUCTURE — see oracle/__init__.py).
+
+PARITY UNPINNED against the reference itself: the arithmetic of this half lives in fairseq (unpinned git HEAD) and
+timm==0.6.12, neither vendored under /root/reference nor installed here, and the reference holds no golden vectors
+for it.  What pins this file instead: (i) the reference's own call sites and configuration —
+  encoder   AdaptedVisionTransformer.forward_features   marie/models/unilm/trocr/deit.py:105-146
+            beit_base/large_patch16_384 (qkv_bias=False, LN eps 1e-6)        deit.py:323-337
+            TrOCREncoder.forward (T x B x C, zero padding mask)               trocr_models.py:508-524
+  decoder   fairseq TransformerDecoder built at trocr_models.py:142-147 with the arch defaults of :423-447
+            (dim 1024, ffn 4096, 16 heads, 12 layers, post-LN, ReLU, sinusoidal positions, embed scale sqrt(d),
+            untied bias-free output projection, cross-attention kdim = encoder dim)
+  search    TextRecognitionGenerator._generate                               generator.py:11-374
+            (fairseq BeamSearch.step / finalize_hypos / EnsembleModel.forward_decoder semantics; bos = eos = 2,
+            pad 1, unk 3, min_len 1, max_len = min(max_len_b, 1023), len-normalised scores, 2*beam candidates)
+  text      get_text                                                          marie/document/trocr_ocr_processor.py:142-180
+(ii) an independent cross-check against HuggingFace transformers' port of the same checkpoints
+(tests/test_oracle_trocr.py: ViTModel / TrOCRForCausalLM on identical weights).
+
+State-dict keys are fairseq's (`encoder.deit.*`, `decoder.*`), so a real TrOCR checkpoint's `model` dict can be
+passed to the same functions and to marie-icr_b200/weights.py:pack_trocr.
+"""
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+BOS, PAD, EOS, UNK = 0, 1, 2, 3
+
+
+@dataclass
+class TrocrConfig:
+    enc_dim: int = 768
+    enc_layers: int = 12
+    enc_heads: int = 12
+    enc_ffn: int = 3072
+    dec_dim: int = 1024
+    dec_layers: int = 12
+    dec_heads: int = 16
+    dec_ffn: int = 4096
+    vocab: int = 50265
+    img: int = 384
+    patch: int = 16
+    max_positions: int = 1024
+
+    @property
+    def tokens(self):
+        return (self.img // self.patch) ** 2 + 1
+
+
+def trocr_base():
+    return TrocrConfig()
+
+
+def trocr_large():
+    return TrocrConfig(enc_dim=1024, enc_layers=24, enc_heads=16, enc_ffn=4096)
+
+
+def trocr_tiny(vocab=1000):
+    """Same structure (head dim 64, 577 tokens) at toy widths — for fast CPU/GPU parity tests."""
+    return TrocrConfig(enc_dim=128, enc_layers=2, enc_heads=2, enc_ffn=256, dec_dim=128, dec_layers=2, dec_heads=2,
+                       dec_ffn=256, vocab=vocab)
+
+
+# ------------------------------------------------------------------------------------------------- weights
+def synth_trocr_state(cfg, seed=0, round_to=torch.float16, out_scale=0.25):
+    """Random-init weights following timm's / fairseq's initialisers (trunc-normal 0.02 ViT linears, xavier-uniform
+    decoder linears, N(0, d^-0.5) embeddings), rounded once to `round_to` so the oracle and the device share the
+    exact same values.  The decoder's residual-writing projections (out_proj, fc2) are scaled by `out_scale` so the
+    residual stream keeps the position signal that calibrate_eos() relies on."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def rnd(t):
+        return t.to(round_to).float() if round_to is not None else t
+
+    def tn(*shape, std=0.02):
+        return rnd(torch.empty(*shape).normal_(0, std, generator=g).clamp_(-2 * std, 2 * std))
+
+    def xavier(out_f, in_f, gain=1.0):
+        b = gain * math.sqrt(6.0 / (in_f + out_f))
+        return rnd(torch.empty(out_f, in_f).uniform_(-b, b, generator=g))
+
+    def ln(key, d):
+        sd[key + ".weight"] = rnd(1.0 + 0.1 * torch.empty(d).normal_(0, 1, generator=g))
+        sd[key + ".bias"] = rnd(0.05 * torch.empty(d).normal_(0, 1, generator=g))
+
+    def bias(d, std=0.02):
+        return rnd(torch.empty(d).normal_(0, std, generator=g))
+
+    D = cfg.enc_dim
+    e = "encoder.deit."
+    sd[e + "patch_embed.proj.weight"] = tn(D, 3, cfg.patch, cfg.patch)
+    sd[e + "patch_embed.proj.bias"] = bias(D)
+    sd[e + "cls_token"] = tn(1, 1, D)
+    sd[e + "pos_embed"] = tn(1, cfg.tokens, D)
+    for i in range(cfg.enc_layers):
+        b = f"{e}blocks.{i}."
+        ln(b + "norm1", D)
+        sd[b + "attn.qkv.weight"] = tn(3 * D, D, std=0.05)
+        sd[b + "attn.proj.weight"] = tn(D, D)
+        sd[b + "attn.proj.bias"] = bias(D)
+        ln(b + "norm2", D)
+        sd[b + "mlp.fc1.weight"] = tn(cfg.enc_ffn, D)
+        sd[b + "mlp.fc1.bias"] = bias(cfg.enc_ffn)
+        sd[b + "mlp.fc2.weight"] = tn(D, cfg.enc_ffn)
+        sd[b + "mlp.fc2.bias"] = bias(D)
+    ln(e + "norm", D)
+
+    H = cfg.dec_dim
+    emb = torch.empty(cfg.vocab, H).normal_(0, H ** -0.5, generator=g)
+    emb[PAD] = 0
+    sd["decoder.embed_tokens.weight"] = rnd(emb)
+    for i in range(cfg.dec_layers):
+        b = f"decoder.layers.{i}."
+        for name, kdim in (("self_attn", H), ("encoder_attn", D)):
+            sd[b + name + ".q_proj.weight"] = xavier(H, H, 2 ** -0.5)
+            sd[b + name + ".k_proj.weight"] = xavier(H, kdim, 2 ** -0.5)
+            sd[b + name + ".v_proj.weight"] = xavier(H, kdim, 2 ** -0.5)
+            sd[b + name + ".out_proj.weight"] = xavier(H, H, out_scale)
+            for p in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                sd[b + name + f".{p}.bias"] = bias(H)
+        ln(b + "self_attn_layer_norm", H)
+        ln(b + "encoder_attn_layer_norm", H)
+        sd[b + "fc1.weight"] = xavier(cfg.dec_ffn, H)
+        sd[b + "fc1.bias"] = bias(cfg.dec_ffn)
+        sd[b + "fc2.weight"] = xavier(H, cfg.dec_ffn, out_scale)
+        sd[b + "fc2.bias"] = bias(H)
+        ln(b + "final_layer_norm", H)
+    wout = torch.empty(cfg.vocab, H).normal_(0, H ** -0.5, generator=g)
+    sd["decoder.output_projection.weight"] = rnd(wout)
+    return sd
+
+
+def calibrate_eos(sd, cfg, eos_step=6, samples=6, seed=0, margin=1.0, round_to=torch.float16):
+    """A random-init decoder never emits EOS (1 chance in V per step), so every hypothesis would run to max_len=200.
+    Like the CRAFT 'calibrated head'  the EOS row of the output projection is set, in place, to the
+    direction that separates the decoder's hidden state at steps >= eos_step from earlier steps (measured on a few
+    greedy roll-outs over random encoder states), scaled so EOS wins the arg-max around step `eos_step`.  The same
+    weights go to the oracle and the device, so parity is unaffected.  Returns the scale used."""
+    g = torch.Generator().manual_seed(seed + 77)
+    enc = torch.randn(samples, cfg.tokens, cfg.enc_dim, generator=g)
+    W = sd["decoder.output_projection.weight"]
+    W[EOS] = 0
+    st = DecoderState(sd, cfg, enc)
+    tok = torch.full((samples,), EOS, dtype=torch.long)
+    hs = []
+    with torch.no_grad():
+        for t in range(eos_step + 3):
+            logits, h = st.step(tok, t, return_hidden=True)
+            hs.append(h)
+            logits[:, PAD] = -math.inf
+            logits[:, EOS] = -math.inf
+            tok = logits.argmax(-1)
+        hs = torch.stack(hs)                                   # [T, S, H]
+        m = hs.mean(1)
+        v = m[eos_step:].mean(0) - m[:eos_step].mean(0)
+        v = v / v.norm()
+        other = (hs[eos_step] @ W.t()).max(-1).values.mean()
+        alpha = float((other + margin) / (hs[eos_step] @ v).mean())
+        W[EOS] = (alpha * v).to(round_to).float() if round_to is not None else alpha * v
+    return alpha
+
+
+# ------------------------------------------------------------------------------------------------- encoder
+def _ln(x, sd, key, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], eps)
+
+
+def encoder_forward(sd, cfg, imgs):
+    """imgs [B,3,384,384] f32 -> [B, 577, D]  (deit.py:105-146 with timm 0.6.12 Block/Attention/Mlp semantics)."""
+    e = "encoder.deit."
+    x = F.conv2d(imgs, sd[e + "patch_embed.proj.weight"], sd[e + "patch_embed.proj.bias"], stride=cfg.patch)
+    x = x.flatten(2).transpose(1, 2)                                   # B, 576, D (row-major patches)
+    x = torch.cat([sd[e + "cls_token"].expand(x.shape[0], -1, -1), x], 1) + sd[e + "pos_embed"]
+    B, T, D = x.shape
+    h, dh = cfg.enc_heads, D // cfg.enc_heads
+    for i in range(cfg.enc_layers):
+        b = f"{e}blocks.{i}."
+        y = _ln(x, sd, b + "norm1", 1e-6)
+        qkv = F.linear(y, sd[b + "attn.qkv.weight"]).reshape(B, T, 3, h, dh).permute(2, 0, 3, 1, 4)
+        att = (qkv[0] @ qkv[1].transpose(-2, -1)) * dh ** -0.5
+        y = (att.softmax(-1) @ qkv[2]).transpose(1, 2).reshape(B, T, D)
+        x = x + F.linear(y, sd[b + "attn.proj.weight"], sd[b + "attn.proj.bias"])
+        y = _ln(x, sd, b + "norm2", 1e-6)
+        y = F.gelu(F.linear(y, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"]))
+        x = x + F.linear(y, sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"])
+    return _ln(x, sd, e + "norm", 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- decoder
+def sinusoidal_table(n, dim, padding_idx=PAD):
+    """fairseq SinusoidalPositionalEmbedding.get_embedding: [sin | cos] halves, zero row at padding_idx."""
+    half = dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float) * -(math.log(10000) / (half - 1)))
+    ang = torch.arange(n, dtype=torch.float)[:, None] * freq[None]
+    t = torch.cat([ang.sin(), ang.cos()], 1)
+    t[padding_idx] = 0
+    return t
+
+
+class DecoderState:
+    """Incremental state: per layer self-attention K/V [rows, heads, t, dh] and static cross-attention K/V."""
+
+    def __init__(self, sd, cfg, enc_out):
+        self.sd, self.cfg = sd, cfg
+        H, h = cfg.dec_dim, cfg.dec_heads
+        self.dh = H // h
+        B, T, _ = enc_out.shape
+        self.cross = []
+        for i in range(cfg.dec_layers):
+            b = f"decoder.layers.{i}.encoder_attn."
+            k = F.linear(enc_out, sd[b + "k_proj.weight"], sd[b + "k_proj.bias"]).view(B, T, h, self.dh).transpose(1, 2)
+            v = F.linear(enc_out, sd[b + "v_proj.weight"], sd[b + "v_proj.bias"]).view(B, T, h, self.dh).transpose(1, 2)
+            self.cross.append((k, v))
+        self.self_kv = [None] * cfg.dec_layers
+        self.pe = sinusoidal_table(cfg.max_positions + 2, H)
+
+    def reorder(self, idx):
+        self.self_kv = [(k[idx], v[idx]) for k, v in self.self_kv]
+        self.cross = [(k[idx], v[idx]) for k, v in self.cross]
+
+    def step(self, tokens_last, t, return_hidden=False):
+        """tokens_last [rows] (token at position t, 0-based) -> logits [rows, V] (fp32)."""
+        sd, cfg = self.sd, self.cfg
+        H, h, dh = cfg.dec_dim, cfg.dec_heads, self.dh
+        x = math.sqrt(H) * sd["decoder.embed_tokens.weight"][tokens_last] + self.pe[PAD + 1 + t]
+        R = x.shape[0]
+        for i in range(cfg.dec_layers):
+            b = f"decoder.layers.{i}."
+            q = F.linear(x, sd[b + "self_attn.q_proj.weight"], sd[b + "self_attn.q_proj.bias"]) * dh ** -0.5
+            k = F.linear(x, sd[b + "self_attn.k_proj.weight"], sd[b + "self_attn.k_proj.bias"]).view(R, h, 1, dh)
+            v = F.linear(x, sd[b + "self_attn.v_proj.weight"], sd[b + "self_attn.v_proj.bias"]).view(R, h, 1, dh)
+            if self.self_kv[i] is not None:
+                k = torch.cat([self.self_kv[i][0], k], 2)
+                v = torch.cat([self.self_kv[i][1], v], 2)
+            self.self_kv[i] = (k, v)
+            a = (q.view(R, h, 1, dh) @ k.transpose(-2, -1)).softmax(-1) @ v
+            x = _ln(x + F.linear(a.reshape(R, H), sd[b + "self_attn.out_proj.weight"], sd[b + "self_attn.out_proj.bias"]),
+                    sd, b + "self_attn_layer_norm", 1e-5)
+            q = F.linear(x, sd[b + "encoder_attn.q_proj.weight"], sd[b + "encoder_attn.q_proj.bias"]) * dh ** -0.5
+            ck, cv = self.cross[i]
+            a = (q.view(R, h, 1, dh) @ ck.transpose(-2, -1)).softmax(-1) @ cv
+            x = _ln(x + F.linear(a.reshape(R, H), sd[b + "encoder_attn.out_proj.weight"],
+                                 sd[b + "encoder_attn.out_proj.bias"]), sd, b + "encoder_attn_layer_norm", 1e-5)
+            y = F.linear(F.relu(F.linear(x, sd[b + "fc1.weight"], sd[b + "fc1.bias"])), sd[b + "fc2.weight"], sd[b + "fc2.bias"])
+            x = _ln(x + y, sd, b + "final_layer_norm", 1e-5)
+        logits = F.linear(x, sd["decoder.output_projection.weight"])
+        return (logits, x) if return_hidden else logits
+
+
+# ------------------------------------------------------------------------------------------------- search
+def generate(sd, cfg, enc_out, beam=1, max_len_b=200, min_len=1, forced=None, trace=None):
+    """fairseq sequence generation as configured by the reference (generator.py:11-374; task.py:165-276):
+    returns, per input row, the list of finalised hypotheses sorted by score (desc), each a dict
+    {tokens: LongTensor (ends with EOS), score: float (sum log-prob / length), positional_scores}.
+
+    Sentences are independent in fairseq's search, so finished sentences are simply frozen here instead of being
+    removed from the batch (generator.py:262-297 only compacts the tensors).
+    `forced`: optional [bsz, L] token matrix — teacher forcing for parity checks: the search is replaced by taking
+    forced[:, step] (beam must be 1) while `trace` collects (step, lprobs) for margin analysis."""
+    bsz = enc_out.shape[0]
+    V = cfg.vocab
+    max_len = min(int(max_len_b), cfg.max_positions - 1)
+    rows = bsz * beam
+    st = DecoderState(sd, cfg, enc_out.repeat_interleave(beam, 0))
+    tokens = torch.full((rows, max_len + 2), PAD, dtype=torch.long)
+    tokens[:, 0] = EOS
+    scores = torch.zeros(rows, max_len + 1)
+    ignore = torch.zeros(bsz, beam, dtype=torch.bool)
+    finalized = [[] for _ in range(bsz)]
+    finished = [False] * bsz
+    cand = 2 * beam
+    for step in range(max_len + 1):
+        logits = st.step(tokens[:, step], step)
+        lprobs = F.log_softmax(logits.float(), -1)
+        lprobs[lprobs != lprobs] = -math.inf
+        lprobs[:, PAD] = -math.inf
+        if step >= max_len:
+            lprobs[:, :EOS] = -math.inf
+            lprobs[:, EOS + 1:] = -math.inf
+        elif step < min_len:
+            lprobs[:, EOS] = -math.inf
+        if trace is not None:
+            trace.append((step, lprobs.clone()))
+        lp = lprobs.view(bsz, beam, V)
+        if forced is not None:
+            assert beam == 1
+            if step >= forced.shape[1]:
+                break
+            tok = forced[:, step]
+            tokens[:, step + 1] = tok
+            scores[:, step] = (scores[:, step - 1] if step else 0) + lp[torch.arange(bsz), 0, tok]
+            continue
+        if step == 0:
+            lp = lp[:, :1, :]
+        else:
+            lp = lp + scores.view(bsz, beam, -1)[:, :, step - 1].unsqueeze(-1)
+        flat = lp.reshape(bsz, -1)
+        c_scores, c_idx = torch.topk(flat, k=min(cand, flat.shape[1] - 1))
+        c_beam, c_tok = c_idx // V, c_idx % V
+        new_tokens, new_scores, reorder = tokens.clone(), scores.clone(), torch.arange(rows)
+        for s in range(bsz):
+            if finished[s]:
+                continue
+            eos_mask = (c_tok[s] == EOS) & (c_scores[s] != -math.inf)
+            eos_mask[:beam] &= ~ignore[s]
+            for c in range(beam):                          # only EOS among the top `beam` candidates finalises
+                if eos_mask[c] and len(finalized[s]) < beam:
+                    src = s * beam + int(c_beam[s, c])
+                    toks = torch.cat([tokens[src, 1:step + 1], torch.tensor([EOS])])
+                    pos = torch.cat([scores[src, :step], c_scores[s, c:c + 1]])
+                    pos[1:] = pos[1:] - pos[:-1].clone()
+                    finalized[s].append(dict(tokens=toks, score=float(c_scores[s, c]) / (step + 1),
+                                             positional_scores=pos))
+            if len(finalized[s]) == beam or step == max_len:
+                finished[s] = True
+                continue
+            eos_mask[:beam] |= ignore[s]
+            active = eos_mask.long() * cand + torch.arange(len(eos_mask))
+            vals, hyp = torch.topk(active, k=beam, largest=False)
+            ignore[s] = vals >= cand
+            for j in range(beam):
+                c = int(hyp[j])
+                src = s * beam + int(c_beam[s, c])
+                dst = s * beam + j
+                new_tokens[dst, :step + 1] = tokens[src, :step + 1]
+                new_tokens[dst, step + 1] = c_tok[s, c]
+                new_scores[dst, :step] = scores[src, :step]
+                new_scores[dst, step] = c_scores[s, c]
+                reorder[dst] = src
+        tokens, scores = new_tokens, new_scores
+        if all(finished):
+            break
+        st.reorder(reorder)
+    if forced is not None:
+        return tokens, scores
+    for s in range(bsz):
+        order = sorted(range(len(finalized[s])), key=lambda i: -finalized[s][i]["score"])
+        finalized[s] = [finalized[s][i] for i in order]
+    return finalized
+
+
+def recognize(sd, cfg, imgs, beam=1, max_len_b=200):
+    """imgs [B,3,384,384] f32 -> list of (token ids without EOS, confidence = exp(score)) like get_text
+    (trocr_ocr_processor.py:142-180) before detokenisation."""
+    enc = encoder_forward(sd, cfg, imgs)
+    out = []
+    for hyps in generate(sd, cfg, enc, beam=beam, max_len_b=max_len_b):
+        top = hyps[0]
+        out.append((top["tokens"][:-1].tolist(), math.exp(top["score"])))
+    return out
