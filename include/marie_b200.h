@@ -51,6 +51,11 @@ const char* mb_last_error(const mb_ctx* ctx);
 enum { MB_DTYPE_BF16 = 0, MB_DTYPE_F16 = 1 };
 int mb_set_dtype(mb_ctx* ctx, int dtype);
 int mb_get_dtype(const mb_ctx* ctx);
+/* Live CUDA-event timing of the tensor-core GEMM launches on their launch stream (bench.py roofline):
+ * mb_profile_enable(ctx, 1) resets and starts, mb_profile_read drains: out3 = {sum of launch durations in ms,
+ * sum of algorithmic FLOPs, number of launches}. */
+int mb_profile_enable(mb_ctx* ctx, int enable);
+int mb_profile_read(mb_ctx* ctx, double* out3_host);
 /* Number of kernels this context has launched so far (bench.py "gpu_launches"). */
 unsigned long long mb_launch_count(const mb_ctx* ctx);
 
@@ -127,6 +132,36 @@ int mb_pack_fragments(mb_ctx* ctx, const uint8_t* buf_dev, const long long* offs
 int mb_load_craft(mb_ctx* ctx, const void* blob_host, size_t nbytes);
 int mb_craft_forward(mb_ctx* ctx, const void* x_dev, int n, int h, int w, float* scores_dev, void* feature_dev,
                      void* stream);
+
+/* ---- K8: line grouping (host side: a few thousand boxes, O(n^2) integer work) -----------------------------------
+ * mb_line_merge replaces line_merge / __line_merge (marie/boxes/line_processor.py:48-171): boxes [n,4] i32 (x,y,w,h) ->
+ * lines [<= n, 4] i32 sorted by y.  mb_find_line_numbers replaces find_line_number (:15-45): 1-based line id per box,
+ * -1 when there are no lines.  Both over find_overlap_vertical (marie/utils/overlap.py:42-103).  Host pointers. */
+int mb_line_merge(mb_ctx* ctx, const int32_t* boxes_host, int n, int32_t* lines_out_host, int* n_lines);
+int mb_find_line_numbers(mb_ctx* ctx, const int32_t* lines_host, int n_lines, const int32_t* boxes_host, int n_boxes,
+                         int32_t* ids_out_host);
+
+/* ---- K10-K12: TrOCR recogniser ----------------------------------------------------------------------
+ * mb_load_trocr: flat blob from marie-icr_b200/weights.py:pack_trocr built from the fairseq state dict
+ * (`encoder.deit.*`, `decoder.*`) — replaces checkpoint_utils.load_model_ensemble_and_task + .half().to(device) in
+ * init() (marie/document/trocr_ocr_processor.py:36-113).  mb_trocr_dims: {enc_dim, dec_dim, vocab, tokens}.
+ * mb_trocr_encode: replaces TrOCREncoder.forward / forward_features (marie/models/unilm/trocr/trocr_models.py:508-524,
+ * deit.py:105-146).  patches: [n*576, 768] 16-bit patch rows (mb_pack_* layout 1); enc_out: [n*577, enc_dim] 16-bit.
+ * mb_trocr_decode: replaces TextRecognitionGenerator._generate (marie/models/unilm/trocr/generator.py:11-374) for
+ * beam in 1..8 (1 = greedy): tokens_out [n, out_ld] i32 = best hypothesis including its final EOS (id 2), padded with
+ * 1; lengths [n]; scores [n] = sum of log-probs / length.  max_len_b as in task.py:266 (200).  steps_run (host,
+ * optional) receives the number of decoder steps executed.  Synchronises `stream`.
+ * mb_trocr_forced_logits: parity hook — teacher-forced decoder, logits_out [L, n, vocab] fp32.
+ * mb_trocr_recognize: encode + decode over n crops in chunks (0 = default 512 crops per chunk). */
+int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes);
+int mb_trocr_dims(mb_ctx* ctx, int* dims4_host);
+int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void* enc_out_dev, void* stream);
+int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int beam, int max_len_b, int32_t* tokens_out_dev,
+                    int out_ld, int32_t* lengths_dev, float* scores_dev, int* steps_run, void* stream);
+int mb_trocr_forced_logits(mb_ctx* ctx, const void* enc_out_dev, int n, const int32_t* forced_dev, int L,
+                           float* logits_out_dev, void* stream);
+int mb_trocr_recognize(mb_ctx* ctx, const void* patches_dev, int n, int beam, int max_len_b, int chunk,
+                       int32_t* tokens_out_dev, int out_ld, int32_t* lengths_dev, float* scores_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,14 @@ class Context:
         code = 1 if str(dtype) in ("torch.float16", "fp16", "f16", "float16") else 0
         self.call("mb_set_dtype", c_int(code))
 
+    def profile(self, enable):
+        self.call("mb_profile_enable", c_int(1 if enable else 0))
+
+    def profile_read(self):
+        out = (ctypes.c_double * 3)()
+        self.call("mb_profile_read", out)
+        return dict(ms=out[0], flops=out[1], launches=int(out[2]))
+
     @property
     def launches(self):
         return int(self.lib.mb_launch_count(self.handle))

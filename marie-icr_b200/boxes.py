@@ -1,0 +1,90 @@
+"""BoxProcessorCraftB200 — drop-in for BoxProcessorCraft (marie/boxes/craft_box_processor.py:244-562): same
+constructor, PSM dispatch, thresholds, return tuple and error behaviour; detection runs on the B200 path
+(K1 -> K2-K4 -> K5-K7).  The reference's unconditional debug writes (crop JPEGs, overlay PNG/JPEG, score-map PNGs;
+:100,533-550 and craft_utils.py:40-43) are not reproduced.
+"""
+import copy
+import os
+
+import numpy as np
+import torch
+
+from . import weights as _weights
+from .pipeline import PSM_PRESETS, PagePipeline
+from .plugin_api import BoxProcessor, PSMode
+
+
+class BoxProcessorCraftB200(BoxProcessor):
+    def __init__(self, work_dir="/tmp/boxes", models_dir="./model_zoo", cuda=True, config=None, *, state_dict=None,
+                 pipeline=None, device=0):
+        """state_dict: CRAFT weights (keys of marie/models/craft/craft.py); when omitted the reference's checkpoint
+        `<models_dir>/craft/craft_mlt_25k.pth` is loaded (craft_box_processor.py:260-277)."""
+        super().__init__(work_dir, models_dir, cuda, config or {})
+        if not cuda:
+            raise RuntimeError("BoxProcessorCraftB200 has no CPU path: cuda=True and a B200 are required")
+        self.pipeline = pipeline or PagePipeline(device=device)
+        if state_dict is None and not self.pipeline.has_craft:
+            path = os.path.join(models_dir, "craft", "craft_mlt_25k.pth")
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"CRAFT checkpoint not found: {path}")
+            state_dict = torch.load(path, map_location="cpu")
+        if state_dict is not None:
+            self.pipeline.load_craft(_weights.pack_craft(state_dict, self.pipeline.dtype))
+        self.device = f"cuda:{self.pipeline.device}"
+
+    def unload(self):
+        from ._lib import Context
+        Context.get(self.pipeline.device).close()
+
+    # ------------------------------------------------------------------ PSM presets (get_prediction, :76-146)
+    def _predict(self, image, mode):
+        pages = torch.from_numpy(np.ascontiguousarray(image[None])).to(self.device)
+        det = self.pipeline.detect(pages, PSM_PRESETS[mode])
+        bboxes = det["boxes"].cpu().numpy()
+        polys = [b for b in bboxes]                      # poly=False: polys[k] = boxes[k] (:133-135)
+        self._last_rects = det["rects"].cpu().numpy()
+        return bboxes, polys, None, []
+
+    def psm_word(self, image):
+        return self._predict(image, "word")
+
+    def psm_sparse(self, image):
+        return self._predict(image, "sparse")
+
+    def psm_line(self, image):
+        return self._predict(image, "line")
+
+    def psm_raw_line(self, image):
+        return self._predict(image, "raw_line")
+
+    def psm_multiline(self, image):
+        return self._predict(image, "multiline")
+
+    # ------------------------------------------------------------------ extract_bounding_boxes (:431-562)
+    def extract_bounding_boxes(self, _id, key, img, psm=PSMode.SPARSE):
+        if img is None:
+            raise Exception("Input image can't be empty")
+        image = img
+        lines_bboxes = []
+        if psm == PSMode.SPARSE:
+            bboxes, polys, score_text, lines_bboxes = self.psm_sparse(image)
+        elif psm == PSMode.LINE:
+            bboxes, polys, score_text, lines_bboxes = self.psm_line(image)
+        elif psm == PSMode.MULTI_LINE:
+            bboxes, polys, score_text, lines_bboxes = self.psm_multiline(image)
+        elif psm == PSMode.RAW_LINE or psm == PSMode.WORD:
+            h, w = image.shape[0], image.shape[1]
+            return [[0, 0, w, h]], [copy.deepcopy(image)], [0], dict(), lines_bboxes
+        else:
+            raise Exception(f"PSM mode not supported : {psm}")
+        prediction_result = {"bboxes": bboxes, "polys": polys, "heatmap": score_text}
+        rects = self._last_rects
+        rect_from_poly, fragments, line_numbers = [], [], []
+        if len(lines_bboxes):
+            from . import lines as _lines
+            ids = _lines.find_line_numbers(lines_bboxes, rects)
+        for i, (x, y, w, h) in enumerate(rects.tolist()):
+            rect_from_poly.append([x, y, w, h])
+            fragments.append(image[y:y + h + 1, x:x + w + 1].copy())      # crop_poly_low on the expanded rect (:42-73,524)
+            line_numbers.append(int(ids[i]) if len(lines_bboxes) else -1)
+        return rect_from_poly, fragments, line_numbers, prediction_result, lines_bboxes

@@ -74,6 +74,23 @@ extern "C" int mb_set_dtype(mb_ctx* ctx, int dtype) {
 }
 extern "C" int mb_get_dtype(const mb_ctx* ctx) { return ctx && ctx->f16 ? MB_DTYPE_F16 : MB_DTYPE_BF16; }
 
+// Live timing of the tensor-core GEMM launches (bench.py roofline).  enable != 0 starts (and resets) the collection;
+// mb_profile_read drains it: out3 = {sum of launch durations [ms], sum of algorithmic FLOPs, launches}.
+extern "C" int mb_profile_enable(mb_ctx* ctx, int enable) {
+    if (!ctx) return MB_ERR_ARG;
+    mb_profile_drain(ctx);
+    ctx->profile = enable != 0;
+    ctx->prof_ms_total = ctx->prof_flops_total = 0;
+    ctx->prof_launches = 0;
+    return MB_OK;
+}
+extern "C" int mb_profile_read(mb_ctx* ctx, double* out3) {
+    if (!ctx || !out3) return MB_ERR_ARG;
+    mb_profile_drain(ctx);
+    out3[0] = ctx->prof_ms_total; out3[1] = ctx->prof_flops_total; out3[2] = (double)ctx->prof_launches;
+    return MB_OK;
+}
+
 extern "C" const char* mb_last_error(const mb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
 extern "C" unsigned long long mb_launch_count(const mb_ctx* ctx) { return ctx ? ctx->launches : 0; }

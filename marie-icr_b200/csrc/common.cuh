@@ -31,6 +31,12 @@ struct mb_ctx {
     unsigned int* dev_diag = nullptr;
     // 16-bit element type of activations / weights: 0 = bf16, 1 = fp16 (default; mb_set_dtype)
     int f16 = 1;
+    // optional live timing of the tap-GEMM launches (bench.py roofline): CUDA event pairs on the launch stream
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+    std::vector<double> prof_flops;
+    double prof_ms_total = 0, prof_flops_total = 0;
+    unsigned long long prof_launches = 0;
     // kernel launch counter (bench.py "gpu_launches")
     unsigned long long launches = 0;
 };
@@ -90,6 +96,7 @@ struct TapGemm {
     long long out_plane = 0;      // MB_OUT_F32_PLANAR: elements between channel planes
 };
 int mb_tap_gemm(mb_ctx* ctx, const TapGemm& p, cudaStream_t stream);
+void mb_profile_drain(mb_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers

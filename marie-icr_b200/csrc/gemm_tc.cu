@@ -425,6 +425,24 @@ int encode_wgt_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int ktot, int 
 
 }  // namespace
 
+void mb_profile_drain(mb_ctx* ctx) {
+    if (ctx->prof_events.empty()) return;
+    cudaEventSynchronize(ctx->prof_events.back());
+    for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]) == cudaSuccess) {
+            ctx->prof_ms_total += ms;
+            ctx->prof_flops_total += ctx->prof_flops[i / 2];
+            ctx->prof_launches++;
+        }
+        cudaEventDestroy(ctx->prof_events[i]);
+        cudaEventDestroy(ctx->prof_events[i + 1]);
+    }
+    ctx->prof_events.clear();
+    ctx->prof_flops.clear();
+    cudaGetLastError();
+}
+
 int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     MB_REQUIRE(ctx, g.a0 && g.wgt && g.out, "tap_gemm: null pointer");
     MB_REQUIRE(ctx, g.c0 > 0 && g.c0 % BLOCK_K == 0 && g.c1 >= 0 && g.c1 % BLOCK_K == 0,
@@ -490,7 +508,21 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     }
     const long long total = (long long)p.m_tiles * p.n_tiles;
     const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profile) {
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, stream);
+    }
     tap_gemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
+    if (ctx->profile) {
+        cudaEventRecord(ev1, stream);
+        ctx->prof_events.push_back(ev0);
+        ctx->prof_events.push_back(ev1);
+        // algorithmic work: 2 * pixels * n_out * K (padding rows / zero-filled halo not counted)
+        ctx->prof_flops.push_back(2.0 * (double)g.n * g.h * g.w * (double)g.n_out * (double)g.taps * (g.c0 + g.c1));
+        if (ctx->prof_events.size() >= 8192) mb_profile_drain(ctx);
+    }
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }

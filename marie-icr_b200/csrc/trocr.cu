@@ -1,3 +1,1025 @@
-// placeholder: TrOCR encoder/decoder (filled in next)
+// K10-K12: TrOCR recogniser — ViT encoder, transformer decoder with a device-resident KV cache, and fairseq's
+// beam / greedy search run entirely on the device.
+//
+// Reference (paths relative to the reference repo):
+//   encoder  AdaptedVisionTransformer.forward_features  marie/models/unilm/trocr/deit.py:105-146 (timm 0.6.12 blocks:
+//            pre-LN, qkv without bias, softmax(QK^T d^-0.5)V, erf-GELU MLP, LN eps 1e-6), TrOCREncoder.forward
+//            marie/models/unilm/trocr/trocr_models.py:508-524
+//   decoder  fairseq TransformerDecoder built at trocr_models.py:142-147 with the arch table :423-447 (post-LN, ReLU,
+//            sinusoidal positions, embed scale sqrt(d), bias-free output projection, cross-attn kdim = encoder dim)
+//   search   TextRecognitionGenerator._generate  marie/models/unilm/trocr/generator.py:11-374 (fairseq BeamSearch.step,
+//            finalize_hypos): log-softmax in fp32, pad/min-len/max-len masking, top 2*beam candidates, EOS finalisation,
+//            length-normalised scores, beam reorder of the incremental state
+//
+// All dense layers run on the tcgen05 tap-GEMM (gemm_tc.cu) with fused bias / GELU / ReLU / residual epilogues.  The
+// kernels in this file are the glue that is not a GEMM: LayerNorm, token assembly, the 577-token encoder attention,
+// the decode-step attentions over the KV caches, the fused log-softmax + top-k and the search bookkeeping.  The beam
+// reorder never moves KV data: an ancestor table (step x row) redirects each hypothesis to the rows that hold its
+// history (generator.py:139 reorder_incremental_state copies the whole cache instead).
 #include "common.cuh"
-void mb_free_trocr(mb_ctx* ctx) { (void)ctx; }
+#include "blob.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int DH = 64;            // head dim of every TrOCR variant (768/12, 1024/16)
+constexpr int MAX_BEAM = 8;
+constexpr int TOK_PAD = 1, TOK_EOS = 2;
+
+struct EncLayer {
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *proj_b, *fc1_b, *fc2_b;
+    const bf16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+};
+struct DecLayer {
+    const bf16 *sqkv_w, *sout_w, *cq_w, *ckv_w, *cout_w, *fc1_w, *fc2_w;
+    const float *sqkv_b, *sout_b, *cq_b, *ckv_b, *cout_b, *fc1_b, *fc2_b;
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+};
+
+}  // namespace
+
+struct TrocrModel {
+    WeightBlob blob;
+    int enc_dim = 0, enc_layers = 0, enc_heads = 0, enc_ffn = 0;
+    int dec_dim = 0, dec_layers = 0, dec_heads = 0, dec_ffn = 0;
+    int vocab = 0, tokens = 0, max_pos = 0;
+    const bf16* patch_w = nullptr; const float* patch_b = nullptr; const float* cls_pos = nullptr;
+    const float *norm_w = nullptr, *norm_b = nullptr;
+    std::vector<EncLayer> enc;
+    std::vector<DecLayer> dec;
+    const bf16* embed = nullptr; const float* pe = nullptr; const bf16* out_w = nullptr;
+    void* arena = nullptr; size_t arena_bytes = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; D % 8 == 0, D <= 2048.  in/out 16-bit (may alias), gamma/beta fp32, statistics in fp32
+// (two-pass: mean, then centred variance — the order torch's CPU kernel uses up to summation order).
+constexpr int LN_MAXV = 8;
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long long rows, int D, float eps, int f16) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nv = D >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(in + row * D);
+    float v[LN_MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            const uint4 u = src[vi];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2(w[k], f16);
+                v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        if (lane + 32 * i < nv) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; sq += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+    uint4* dst = reinterpret_cast<uint4*>(out + row * D);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+            uint4 o;
+            o.x = pack2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y, f16);
+            o.y = pack2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w, f16);
+            o.z = pack2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y, f16);
+            o.w = pack2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w, f16);
+            dst[vi] = o;
+        }
+    }
+}
+
+// x[n, 0] = cls + pos[0];  x[n, 1+p] = patch_out[n, p] + pos[1+p]   (deit.py:121-143; cls folded into cls_pos[0])
+__global__ void assemble_tokens_kernel(const bf16* __restrict__ patch_out, const float* __restrict__ cls_pos,
+                                       bf16* __restrict__ x, long long total8, int T, int D, int f16) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int d8 = D >> 3;
+    for (; i < total8; i += stride) {
+        const int c = (int)(i % d8);
+        const long long r = i / d8;
+        const int t = (int)(r % T);
+        const long long n = r / T;
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (t > 0) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(patch_out + ((n * (T - 1) + t - 1) * D)) + c);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 p = unpack2(w[k], f16); f[2 * k] = p.x; f[2 * k + 1] = p.y; }
+        }
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(cls_pos + (long long)t * D) + 2 * c);
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(cls_pos + (long long)t * D) + 2 * c + 1);
+        uint4 o;
+        o.x = pack2(f[0] + p0.x, f[1] + p0.y, f16); o.y = pack2(f[2] + p0.z, f[3] + p0.w, f16);
+        o.z = pack2(f[4] + p1.x, f[5] + p1.y, f16); o.w = pack2(f[6] + p1.z, f[7] + p1.w, f16);
+        reinterpret_cast<uint4*>(x + r * D)[c] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ encoder attention
+// softmax(Q K^T / sqrt(64)) V for T tokens per image, flash-style (online softmax), one CTA = 64 query rows of one
+// (image, head); 4 warps x 16 rows; K/V streamed in 64-key tiles through double-buffered cp.async.  Tensor math is
+// mma.sync m16n8k16 (legacy HMMA path) — 11% of the encoder FLOPs; the tcgen05 version is future work.
+// qkv: [n*T, 3*D] (q | k | v, head h at columns h*64); out: [n*T, D].
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+template <bool F16>
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    if (F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// tile [64 rows][64 x 16-bit] with the 16-byte chunk index XOR-swizzled by (row & 7)
+__device__ __forceinline__ int swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+template <bool F16>
+__global__ void __launch_bounds__(128) enc_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T,
+                                                            int D, float scale_log2e) {
+    __shared__ __align__(128) unsigned char sQ[64 * 128];
+    __shared__ __align__(128) unsigned char sK[2][64 * 128];
+    __shared__ __align__(128) unsigned char sV[2][64 * 128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * 64, head = blockIdx.y;
+    const long long img = blockIdx.z;
+    const long long ld = 3LL * D;
+    const bf16* base = qkv + img * T * ld + head * DH;
+    const int n_tiles = (T + 63) >> 6;
+
+    auto load_tile = [&](unsigned char* dst, const bf16* src, int row0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 128 * i;            // 512 chunks of 16 B
+            const int r = idx >> 3, c = idx & 7;
+            const bool ok = row0 + r < T;
+            cp_async16(smem_addr(dst + swz(r, c)), src + (long long)(ok ? row0 + r : 0) * ld + c * 8, ok);
+        }
+    };
+    load_tile(sQ, base, q0);
+    load_tile(sK[0], base + D, 0);
+    load_tile(sV[0], base + 2 * D, 0);
+    cp_async_commit();
+
+    uint32_t aq[4][4];
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < n_tiles) {
+            load_tile(sK[buf ^ 1], base + D, (j + 1) * 64);
+            load_tile(sV[buf ^ 1], base + 2 * D, (j + 1) * 64);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (j == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = ks * 2 + (lane >> 4);
+                ldsm_x4(smem_addr(sQ + swz(r, c)), aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
+            }
+        }
+        // S = Q K^T  (16 x 64 per warp)
+        float s[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {          // two k-steps per ldmatrix.x4
+                uint32_t b0, b1, b2, b3;
+                const int r = nb * 8 + (lane & 7);
+                const int c = kp * 4 + (lane >> 3);
+                ldsm_x4(smem_addr(sK[buf] + swz(r, c)), b0, b1, b2, b3);
+                mma16816<F16>(s[nb], aq[kp * 2], b0, b1);
+                mma16816<F16>(s[nb], aq[kp * 2 + 1], b2, b3);
+            }
+        }
+        // online softmax (rows g and g+8 of this warp's 16)
+        const int key0 = j * 64 + (lane & 3) * 2;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int k = key0 + nb * 8;
+            s[nb][0] = (k < T) ? s[nb][0] * scale_log2e : -INFINITY;
+            s[nb][1] = (k + 1 < T) ? s[nb][1] * scale_log2e : -INFINITY;
+            s[nb][2] = (k < T) ? s[nb][2] * scale_log2e : -INFINITY;
+            s[nb][3] = (k + 1 < T) ? s[nb][3] * scale_log2e : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has at least one valid key
+        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        l0 *= c0; l1 *= c1;
+        uint32_t ap[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const float p0 = exp2f(s[nb][0] - mn0), p1 = exp2f(s[nb][1] - mn0);
+            const float p2 = exp2f(s[nb][2] - mn1), p3 = exp2f(s[nb][3] - mn1);
+            l0 += p0 + p1; l1 += p2 + p3;
+            ap[nb >> 1][(nb & 1) * 2] = pack2(p0, p1, F16);
+            ap[nb >> 1][(nb & 1) * 2 + 1] = pack2(p2, p3, F16);
+            o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
+        }
+        // O += P V
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {          // two 8-wide dh blocks per ldmatrix.x4.trans
+                uint32_t b0, b1, b2, b3;
+                const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = dp * 2 + (lane >> 4);
+                ldsm_x4_t(smem_addr(sV[buf] + swz(r, c)), b0, b1, b2, b3);
+                mma16816<F16>(o[dp * 2], ap[kk], b0, b1);
+                mma16816<F16>(o[dp * 2 + 1], ap[kk], b2, b3);
+            }
+        }
+        __syncthreads();   // all warps done with sK/sV[buf] before the next prefetch overwrites it
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // stage the 64x64 output tile in sQ (each warp only touches its own 16 rows), then coalesced 16 B stores
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        const int r0 = warp * 16 + g, r1 = r0 + 8;
+        *reinterpret_cast<uint32_t*>(sQ + swz(r0, nb) + tg * 4) = pack2(o[nb][0] * i0, o[nb][1] * i0, F16);
+        *reinterpret_cast<uint32_t*>(sQ + swz(r1, nb) + tg * 4) = pack2(o[nb][2] * i1, o[nb][3] * i1, F16);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i;                // 128 chunks per warp (16 rows x 8)
+        const int r = warp * 16 + (idx >> 3), c = idx & 7;
+        if (q0 + r < T)
+            *reinterpret_cast<uint4*>(out + (img * T + q0 + r) * D + head * DH + c * 8) =
+                *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decoder glue
+// x[r] = sqrt(H) * E[tok[r]] + PE[pos]   (fairseq: embed_scale * embed_tokens + sinusoidal positions)
+__global__ void dec_embed_kernel(const int* __restrict__ tokens, int tok_ld, int step, const bf16* __restrict__ embed,
+                                 const float* __restrict__ pe, bf16* __restrict__ x, int rows, int H, float scale,
+                                 int f16) {
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    const int tok = tokens[(long long)r * tok_ld + step];
+    const float* p = pe + (long long)(TOK_PAD + 1 + step) * H;
+    for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
+        const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(embed + (long long)tok * H + c), f16);
+        *reinterpret_cast<uint32_t*>(x + (long long)r * H + c) = pack2(scale * e.x + p[c], scale * e.y + p[c + 1], f16);
+    }
+}
+
+// Self-attention of one new token over the cached history.  qkv: [R, 3H] (q pre-scaled | k | v) of this step.
+// Appends k, v to the caches at (step, row) and attends over steps 0..step through the ancestor table.
+// grid (heads, R), one warp (2 dims of the head per lane).
+__global__ void __launch_bounds__(32) dec_self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kcache,
+                                                           bf16* __restrict__ vcache, const int* __restrict__ anc,
+                                                           bf16* __restrict__ out, int R, int H, int step, int f16) {
+    const int head = blockIdx.x, r = blockIdx.y, lane = threadIdx.x;
+    const long long col = head * DH + lane * 2;
+    const uint32_t qraw = *reinterpret_cast<const uint32_t*>(qkv + (long long)r * 3 * H + col);
+    const uint32_t kraw = *reinterpret_cast<const uint32_t*>(qkv + (long long)r * 3 * H + H + col);
+    const uint32_t vraw = *reinterpret_cast<const uint32_t*>(qkv + (long long)r * 3 * H + 2 * H + col);
+    *reinterpret_cast<uint32_t*>(kcache + ((long long)step * R + r) * H + col) = kraw;
+    *reinterpret_cast<uint32_t*>(vcache + ((long long)step * R + r) * H + col) = vraw;
+    const float2 q = unpack2(qraw, f16);
+    float m = -INFINITY, l = 0.f, ox = 0.f, oy = 0.f;
+    for (int t = 0; t <= step; ++t) {
+        uint32_t kr, vr;
+        if (t == step) { kr = kraw; vr = vraw; }
+        else {
+            const long long src = ((long long)t * R + anc[(long long)t * R + r]) * H + col;
+            kr = *reinterpret_cast<const uint32_t*>(kcache + src);
+            vr = *reinterpret_cast<const uint32_t*>(vcache + src);
+        }
+        const float2 k = unpack2(kr, f16), v = unpack2(vr, f16);
+        const float s = warp_sum(q.x * k.x + q.y * k.y);
+        const float mn = fmaxf(m, s);
+        const float c = __expf(m - mn), p = __expf(s - mn);
+        l = l * c + p;
+        ox = ox * c + p * v.x;
+        oy = oy * c + p * v.y;
+        m = mn;
+    }
+    *reinterpret_cast<uint32_t*>(out + (long long)r * H + col) = pack2(ox / l, oy / l, f16);
+}
+
+// Cross-attention of the new token of every beam of one crop over the crop's T encoder states.
+// q: [R, H] (pre-scaled); kv: [n*T, 2H] (k | v) of this layer; out [R, H].  grid (heads, n_crops), 128 threads:
+// scores for all keys and beams in shared memory, softmax per beam, then P.V with lanes across the head dim.
+constexpr int XA_THREADS = 128;
+__global__ void __launch_bounds__(XA_THREADS) dec_cross_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
+                                                                    bf16* __restrict__ out, int T, int H, int beam,
+                                                                    int f16) {
+    extern __shared__ float sp[];                   // [beam][T] scores, then [4 warps][beam][64] partial outputs
+    __shared__ float sq[MAX_BEAM][DH];
+    __shared__ float smax[MAX_BEAM], ssum[MAX_BEAM];
+    const int head = blockIdx.x, crop = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long ld = 2LL * H;
+    const bf16* kbase = kv + (long long)crop * T * ld + head * DH;
+    const bf16* vbase = kbase + H;
+    for (int i = tid; i < beam * DH; i += XA_THREADS) {
+        const int b = i / DH, d = i % DH;
+        sq[b][d] = load16(q + ((long long)crop * beam + b) * H + head * DH + d, f16);
+    }
+    __syncthreads();
+    // scores: one key per thread iteration, 8 x 16 B loads of the key row
+    for (int t = tid; t < T; t += XA_THREADS) {
+        float acc[MAX_BEAM];
+#pragma unroll
+        for (int b = 0; b < MAX_BEAM; ++b) acc[b] = 0.f;
+        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)t * ld);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldg(kr + c);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2(w[k], f16);
+#pragma unroll
+                for (int b = 0; b < MAX_BEAM; ++b)
+                    if (b < beam) acc[b] += sq[b][c * 8 + 2 * k] * f.x + sq[b][c * 8 + 2 * k + 1] * f.y;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < MAX_BEAM; ++b)
+            if (b < beam) sp[b * T + t] = acc[b];
+    }
+    __syncthreads();
+    // softmax statistics: warp w handles beams w, w+4
+    for (int b = warp; b < beam; b += 4) {
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sp[b * T + t]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int t = lane; t < T; t += 32) {
+            const float p = __expf(sp[b * T + t] - mx);
+            sp[b * T + t] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) { smax[b] = mx; ssum[b] = sum; }
+    }
+    __syncthreads();
+    // P.V: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
+    float ax[MAX_BEAM], ay[MAX_BEAM];
+#pragma unroll
+    for (int b = 0; b < MAX_BEAM; ++b) ax[b] = ay[b] = 0.f;
+    for (int t = warp; t < T; t += 4) {
+        const float2 v = unpack2(__ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)t * ld) + lane), f16);
+#pragma unroll
+        for (int b = 0; b < MAX_BEAM; ++b)
+            if (b < beam) { const float p = sp[b * T + t]; ax[b] += p * v.x; ay[b] += p * v.y; }
+    }
+    __syncthreads();
+    float* part = sp;                                // reuse: [4][beam][64]
+#pragma unroll
+    for (int b = 0; b < MAX_BEAM; ++b)
+        if (b < beam) {
+            part[(warp * beam + b) * DH + lane * 2] = ax[b];
+            part[(warp * beam + b) * DH + lane * 2 + 1] = ay[b];
+        }
+    __syncthreads();
+    for (int i = tid; i < beam * DH; i += XA_THREADS) {
+        const int b = i / DH, d = i % DH;
+        const float s = part[(0 * beam + b) * DH + d] + part[(1 * beam + b) * DH + d] + part[(2 * beam + b) * DH + d] +
+                        part[(3 * beam + b) * DH + d];
+        store16(out + ((long long)crop * beam + b) * H + head * DH + d, s / ssum[b], f16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ search
+// Per row: log-softmax statistics of the fp32 logits and the top `cand` (= 2*beam) masked log-probs
+// (generator.py:153-177: pad never, EOS banned below min_len, only EOS at max_len; NaN -> -inf).
+// Ties resolve to the lower token id.
+constexpr int TOPK_THREADS = 256;
+constexpr int MAX_CAND = 2 * MAX_BEAM;
+__device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__global__ void __launch_bounds__(TOPK_THREADS) logits_topk_kernel(const float* __restrict__ logits, int V, int ld,
+                                                                   int cand, int eos_banned, int only_eos,
+                                                                   float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+    __shared__ float red[TOPK_THREADS / 32];
+    __shared__ float s_stat[2];
+    __shared__ float sv[TOPK_THREADS / 32][MAX_CAND];
+    __shared__ int si[TOPK_THREADS / 32][MAX_CAND];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* x = logits + (long long)r * ld;
+    // pass 1: max (for the softmax) — every vocabulary entry takes part in the normaliser, masked or not
+    float mx = -INFINITY;
+    for (int i = tid; i < V; i += TOPK_THREADS) { const float v = x[i]; if (v == v) mx = fmaxf(mx, v); }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int w = 1; w < TOPK_THREADS / 32; ++w) m = fmaxf(m, red[w]); s_stat[0] = m; }
+    __syncthreads();
+    mx = s_stat[0];
+    // pass 2: sum exp, and per-thread top list of the unmasked logits
+    float tv[MAX_CAND];
+    int ti[MAX_CAND];
+#pragma unroll
+    for (int k = 0; k < MAX_CAND; ++k) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
+    float sum = 0.f;
+    for (int i = tid; i < V; i += TOPK_THREADS) {
+        float v = x[i];
+        if (v == v) sum += __expf(v - mx); else v = -INFINITY;
+        if (i == TOK_PAD || (eos_banned && i == TOK_EOS) || (only_eos && i != TOK_EOS)) v = -INFINITY;
+        if (cand_better(v, i, tv[cand - 1], ti[cand - 1])) {
+            int k = cand - 1;
+            while (k > 0 && cand_better(v, i, tv[k - 1], ti[k - 1])) { tv[k] = tv[k - 1]; ti[k] = ti[k - 1]; --k; }
+            tv[k] = v; ti[k] = i;
+        }
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) { float s = 0.f; for (int w = 0; w < TOPK_THREADS / 32; ++w) s += red[w]; s_stat[1] = logf(s); }
+    // warp-level merge: repeatedly take the best head among the 32 sorted lists
+    int head = 0;
+    for (int k = 0; k < cand; ++k) {
+        float bv = head < cand ? tv[head] : -INFINITY;
+        int bi = head < cand ? ti[head] : 0x7fffffff;
+        float wv = bv; int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (cand_better(ov, oi, wv, wi)) { wv = ov; wi = oi; }
+        }
+        if (wi == bi && wv == bv && head < cand) ++head;      // token ids are unique: exactly one lane advances
+        if (lane == 0) { sv[warp][k] = wv; si[warp][k] = wi; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // merge the 8 warp lists (lane w < 8 owns list w)
+        int h = 0;
+        const float lse = s_stat[0] + s_stat[1];
+        for (int k = 0; k < cand; ++k) {
+            float bv = (lane < TOPK_THREADS / 32 && h < cand) ? sv[lane][h] : -INFINITY;
+            int bi = (lane < TOPK_THREADS / 32 && h < cand) ? si[lane][h] : 0x7fffffff;
+            float wv = bv; int wi = bi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (cand_better(ov, oi, wv, wi)) { wv = ov; wi = oi; }
+            }
+            if (wi == bi && wv == bv && lane < TOPK_THREADS / 32 && h < cand) ++h;
+            if (lane == 0) {
+                cand_val[(long long)r * cand + k] = (wv == -INFINITY) ? -INFINITY : wv - lse;
+                cand_idx[(long long)r * cand + k] = wi;
+            }
+        }
+    }
+}
+
+struct SearchState {
+    int* tokens;        // [R, max_len + 2]
+    float* scores;      // [R, max_len + 1] cumulative log-probs
+    int* anc;           // [max_len + 1, R] ancestor table for the self-attention caches
+    int* tokens_tmp; float* scores_tmp; int* anc_tmp;
+    unsigned char* ignore;   // [n, beam]
+    int* fin_count;     // [n]
+    int* fin_tokens;    // [n, beam, max_len + 1]
+    int* fin_len;       // [n, beam]
+    float* fin_score;   // [n, beam]
+    unsigned char* finished;   // [n]
+    int* n_unfinished;  // [1]
+};
+
+// One thread per sentence: fairseq BeamSearch.step over the per-row candidate lists + generator.py:196-362.
+__global__ void search_step_kernel(SearchState st, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                                   int n, int beam, int step, int max_len) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int R = n * beam, cand = 2 * beam, tl = max_len + 2, sl = max_len + 1;
+    // rows keep their history unless a live sentence reorders them
+    if (st.finished[s]) {
+        for (int b = 0; b < beam; ++b) st.anc[(long long)step * R + s * beam + b] = s * beam + b;
+        return;
+    }
+    // candidates: step 0 uses beam 0 only; later steps add the beam's cumulative score
+    float cv[MAX_CAND]; int cb[MAX_CAND], ct[MAX_CAND];
+    int heads[MAX_BEAM];
+    for (int b = 0; b < beam; ++b) heads[b] = 0;
+    const int nb = step == 0 ? 1 : beam;
+    for (int k = 0; k < cand; ++k) {
+        float bv = -INFINITY; int bb = -1, bt = 0x7fffffff;
+        for (int b = 0; b < nb; ++b) {
+            if (heads[b] >= cand) continue;
+            const long long row = (long long)(s * beam + b);
+            float v = cand_val[row * cand + heads[b]];
+            const int t = cand_idx[row * cand + heads[b]];
+            if (step > 0) v += st.scores[row * sl + step - 1];
+            // torch.topk over the flattened [beam * V] row: ties by flat index (beam-major)
+            if (bb < 0 || v > bv) { bv = v; bb = b; bt = t; }
+        }
+        cv[k] = bv; cb[k] = bb; ct[k] = bt;
+        heads[bb]++;
+    }
+    // finalise EOS hypotheses among the top `beam` candidates
+    bool eos[MAX_CAND];
+    for (int k = 0; k < cand; ++k) eos[k] = (ct[k] == TOK_EOS) && (cv[k] != -INFINITY);
+    for (int k = 0; k < beam; ++k) eos[k] = eos[k] && !st.ignore[s * beam + k];
+    int fc = st.fin_count[s];
+    for (int k = 0; k < beam; ++k) {
+        if (!eos[k] || fc >= beam) continue;
+        const long long src = (long long)(s * beam + cb[k]);
+        int* ft = st.fin_tokens + ((long long)s * beam + fc) * sl;
+        for (int t = 0; t < step; ++t) ft[t] = st.tokens[src * tl + 1 + t];
+        ft[step] = TOK_EOS;
+        st.fin_len[s * beam + fc] = step + 1;
+        st.fin_score[s * beam + fc] = cv[k] / (float)(step + 1);
+        ++fc;
+    }
+    st.fin_count[s] = fc;
+    if (fc == beam || step == max_len) {
+        st.finished[s] = 1;
+        atomicSub(st.n_unfinished, 1);
+        for (int b = 0; b < beam; ++b) st.anc[(long long)step * R + s * beam + b] = s * beam + b;
+        return;
+    }
+    // pick the `beam` best non-EOS candidates (smallest of eos*cand + k, ascending)
+    for (int k = 0; k < beam; ++k) eos[k] = eos[k] || st.ignore[s * beam + k];
+    int hyp[MAX_BEAM]; bool ign[MAX_BEAM];
+    int j = 0;
+    for (int k = 0; k < cand && j < beam; ++k) if (!eos[k]) { hyp[j] = k; ign[j] = false; ++j; }
+    for (int k = 0; k < cand && j < beam; ++k) if (eos[k]) { hyp[j] = k; ign[j] = true; ++j; }
+    for (int b = 0; b < beam; ++b) {
+        const int k = hyp[b];
+        const long long src = (long long)(s * beam + cb[k]), dst = (long long)(s * beam + b);
+        st.ignore[s * beam + b] = ign[b];
+        for (int t = 0; t <= step; ++t) st.tokens_tmp[dst * tl + t] = st.tokens[src * tl + t];
+        st.tokens_tmp[dst * tl + step + 1] = ct[k];
+        for (int t = 0; t < step; ++t) st.scores_tmp[dst * sl + t] = st.scores[src * sl + t];
+        st.scores_tmp[dst * sl + step] = cv[k];
+        for (int t = 0; t < step; ++t) st.anc_tmp[(long long)t * R + dst] = st.anc[(long long)t * R + src];
+        st.anc_tmp[(long long)step * R + dst] = (int)src;
+    }
+}
+// second phase: publish the reordered rows of live sentences (tmp -> main), after every thread has read the old state
+__global__ void search_commit_kernel(SearchState st, int n, int beam, int step, int max_len) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = n * beam, tl = max_len + 2, sl = max_len + 1;
+    if (row >= R) return;
+    if (st.finished[row / beam]) return;
+    for (int t = 0; t <= step + 1; ++t) st.tokens[(long long)row * tl + t] = st.tokens_tmp[(long long)row * tl + t];
+    for (int t = 0; t <= step; ++t) st.scores[(long long)row * sl + t] = st.scores_tmp[(long long)row * sl + t];
+    for (int t = 0; t <= step; ++t) st.anc[(long long)t * R + row] = st.anc_tmp[(long long)t * R + row];
+}
+
+// teacher forcing (parity hook): next token = forced[r, step]; cumulative score of that token
+__global__ void forced_step_kernel(SearchState st, const float* __restrict__ logits, int V, int ld,
+                                   const int* __restrict__ forced, int forced_ld, int R, int step, int max_len) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    st.tokens[(long long)r * (max_len + 2) + step + 1] = forced[(long long)r * forced_ld + step];
+    st.anc[(long long)step * R + r] = r;
+}
+
+__global__ void search_init_kernel(SearchState st, int n, int beam, int max_len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = n * beam;
+    if (i < R) {
+        for (int t = 0; t < max_len + 2; ++t) st.tokens[(long long)i * (max_len + 2) + t] = t == 0 ? TOK_EOS : TOK_PAD;
+        st.ignore[i] = 0;
+        st.fin_len[i] = 0;
+        st.fin_score[i] = -INFINITY;
+    }
+    if (i < n) { st.fin_count[i] = 0; st.finished[i] = 0; }
+    if (i == 0) *st.n_unfinished = n;
+}
+
+// best finalised hypothesis per sentence (generator.py:364-373 sorts by score, get_text takes [0])
+__global__ void search_pick_kernel(SearchState st, int n, int beam, int max_len, int* __restrict__ out_tokens,
+                                   int out_ld, int* __restrict__ out_len, float* __restrict__ out_score) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int best = -1;
+    for (int b = 0; b < st.fin_count[s]; ++b)
+        if (best < 0 || st.fin_score[s * beam + b] > st.fin_score[s * beam + best]) best = b;
+    if (best < 0) { out_len[s] = 0; out_score[s] = -INFINITY; return; }
+    const int len = st.fin_len[s * beam + best];
+    for (int t = 0; t < len && t < out_ld; ++t)
+        out_tokens[(long long)s * out_ld + t] = st.fin_tokens[((long long)s * beam + best) * (max_len + 1) + t];
+    for (int t = len; t < out_ld; ++t) out_tokens[(long long)s * out_ld + t] = TOK_PAD;
+    out_len[s] = len;
+    out_score[s] = st.fin_score[s * beam + best];
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+struct Arena {
+    unsigned char* base; size_t off = 0, cap;
+    template <typename T> T* take(size_t n) {
+        off = mb_align_up(off, 256);
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+int ensure_arena(mb_ctx* ctx, TrocrModel* m, size_t bytes) {
+    if (bytes <= m->arena_bytes) return 0;
+    if (m->arena) cudaFree(m->arena);
+    m->arena = nullptr; m->arena_bytes = 0;
+    if (cudaMalloc(&m->arena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return mb_set_err(ctx, MB_ERR_OOM, "trocr: workspace of %zu bytes failed", bytes);
+    }
+    m->arena_bytes = bytes;
+    return 0;
+}
+
+int gemm(mb_ctx* ctx, const bf16* a, int K, const bf16* w, int rows_w, long long M, int N, const float* bias, int act,
+         const bf16* residual, void* out, int out_mode, cudaStream_t s) {
+    TapGemm g;
+    g.a0 = a; g.c0 = K; g.a0_ld = K;
+    g.n = 1; g.h = 1; g.w = (int)M;
+    g.wgt = w; g.n_rows_w = rows_w; g.n_out = N;
+    g.bias = bias; g.act = act;
+    g.residual = residual; g.res_ld = N;
+    g.out = out; g.out_ld = N; g.out_mode = out_mode;
+    return mb_tap_gemm(ctx, g, s);
+}
+
+int layernorm(mb_ctx* ctx, const bf16* in, bf16* out, const float* g, const float* b, long long rows, int D, float eps,
+              cudaStream_t s) {
+    if (D % 8 != 0 || D > 256 * LN_MAXV) return mb_set_err(ctx, MB_ERR_ARG, "layernorm: unsupported width %d", D);
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(in, out, g, b, rows, D, eps, ctx->f16);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int grid1d(mb_ctx* ctx, long long total, int threads) {
+    long long g = (total + threads - 1) / threads;
+    const long long cap = (long long)ctx->num_sms * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+#define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+// patches [n*576, 768] -> enc_out [n*577, D]; ws must hold x, y [n*577*D] and big [n*577*max(3D, ffn)]
+int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out, bf16* x, bf16* y, bf16* big,
+           cudaStream_t s) {
+    const int D = m->enc_dim, T = m->tokens, F = m->enc_ffn;
+    const long long M = (long long)n * T;
+    // patch embedding (Conv2d k=s=16 == GEMM over patch rows) into `big`, then cls/pos assembly into x
+    RC(gemm(ctx, patches, 768, m->patch_w, D, (long long)n * (T - 1), D, m->patch_b, MB_ACT_NONE, nullptr, big, MB_OUT_BF16, s));
+    {
+        const long long total8 = M * (D / 8);
+        assemble_tokens_kernel<<<grid1d(ctx, total8, 256), 256, 0, s>>>(big, m->cls_pos, x, total8, T, D, ctx->f16);
+        MB_LAUNCH_CHECK(ctx);
+    }
+    const float scale_log2e = 0.125f * 1.4426950408889634f;
+    for (int l = 0; l < m->enc_layers; ++l) {
+        const EncLayer& L = m->enc[l];
+        RC(layernorm(ctx, x, y, L.ln1_w, L.ln1_b, M, D, 1e-6f, s));
+        RC(gemm(ctx, y, D, L.qkv_w, 3 * D, M, 3 * D, nullptr, MB_ACT_NONE, nullptr, big, MB_OUT_BF16, s));
+        {
+            dim3 grid((T + 63) / 64, m->enc_heads, n);
+            if (ctx->f16) enc_attention_kernel<true><<<grid, 128, 0, s>>>(big, y, T, D, scale_log2e);
+            else enc_attention_kernel<false><<<grid, 128, 0, s>>>(big, y, T, D, scale_log2e);
+            MB_LAUNCH_CHECK(ctx);
+        }
+        RC(gemm(ctx, y, D, L.proj_w, D, M, D, L.proj_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
+        RC(layernorm(ctx, x, y, L.ln2_w, L.ln2_b, M, D, 1e-6f, s));
+        RC(gemm(ctx, y, D, L.fc1_w, F, M, F, L.fc1_b, MB_ACT_GELU, nullptr, big, MB_OUT_BF16, s));
+        RC(gemm(ctx, big, F, L.fc2_w, D, M, D, L.fc2_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
+    }
+    RC(layernorm(ctx, x, enc_out, m->norm_w, m->norm_b, M, D, 1e-6f, s));
+    return 0;
+}
+
+struct DecodeWs {
+    bf16 *cross_kv, *kcache, *vcache, *x, *qkv, *att, *tmp, *ffn;
+    float* logits; float* cand_val; int* cand_idx;
+    SearchState st;
+};
+
+size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* base, DecodeWs* w) {
+    Arena a{base, 0, 0};
+    const int H = m->dec_dim, T = m->tokens, L = m->dec_layers, V = m->vocab;
+    const long long R = (long long)n * beam;
+    const int cand = 2 * beam;
+    w->cross_kv = a.take<bf16>((size_t)L * n * T * 2 * H);
+    w->kcache = a.take<bf16>((size_t)L * (max_len + 1) * R * H);
+    w->vcache = a.take<bf16>((size_t)L * (max_len + 1) * R * H);
+    w->x = a.take<bf16>(R * H);
+    w->qkv = a.take<bf16>(R * 3 * H);
+    w->att = a.take<bf16>(R * H);
+    w->tmp = a.take<bf16>(R * H);
+    w->ffn = a.take<bf16>(R * m->dec_ffn);
+    w->logits = a.take<float>(R * V);
+    w->cand_val = a.take<float>(R * cand);
+    w->cand_idx = a.take<int>(R * cand);
+    w->st.tokens = a.take<int>(R * (max_len + 2));
+    w->st.tokens_tmp = a.take<int>(R * (max_len + 2));
+    w->st.scores = a.take<float>(R * (max_len + 1));
+    w->st.scores_tmp = a.take<float>(R * (max_len + 1));
+    w->st.anc = a.take<int>((size_t)(max_len + 1) * R);
+    w->st.anc_tmp = a.take<int>((size_t)(max_len + 1) * R);
+    w->st.ignore = a.take<unsigned char>(R);
+    w->st.fin_count = a.take<int>(n);
+    w->st.fin_tokens = a.take<int>(R * (max_len + 1));
+    w->st.fin_len = a.take<int>(R);
+    w->st.fin_score = a.take<float>(R);
+    w->st.finished = a.take<unsigned char>(n);
+    w->st.n_unfinished = a.take<int>(1);
+    return mb_align_up(a.off, 256);
+}
+
+// one decoder step for all R rows: tokens[:, step] -> logits [R, V]
+int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, int n, int beam, int step, int max_len, cudaStream_t s) {
+    const int H = m->dec_dim, T = m->tokens, F = m->dec_ffn, V = m->vocab;
+    const int R = n * beam;
+    dec_embed_kernel<<<R, 128, 0, s>>>(w.st.tokens, max_len + 2, step, m->embed, m->pe, w.x, R, H, sqrtf((float)H), ctx->f16);
+    MB_LAUNCH_CHECK(ctx);
+    for (int l = 0; l < m->dec_layers; ++l) {
+        const DecLayer& L = m->dec[l];
+        const size_t cache_off = (size_t)l * (max_len + 1) * R * H;
+        RC(gemm(ctx, w.x, H, L.sqkv_w, 3 * H, R, 3 * H, L.sqkv_b, MB_ACT_NONE, nullptr, w.qkv, MB_OUT_BF16, s));
+        dec_self_attn_kernel<<<dim3(m->dec_heads, R), 32, 0, s>>>(w.qkv, w.kcache + cache_off, w.vcache + cache_off, w.st.anc,
+                                                                  w.att, R, H, step, ctx->f16);
+        MB_LAUNCH_CHECK(ctx);
+        RC(gemm(ctx, w.att, H, L.sout_w, H, R, H, L.sout_b, MB_ACT_NONE, w.x, w.tmp, MB_OUT_BF16, s));
+        RC(layernorm(ctx, w.tmp, w.x, L.ln1_w, L.ln1_b, R, H, 1e-5f, s));
+        RC(gemm(ctx, w.x, H, L.cq_w, H, R, H, L.cq_b, MB_ACT_NONE, nullptr, w.qkv, MB_OUT_BF16, s));
+        {
+            const size_t smem = (size_t)beam * (T > 4 * DH ? T : 4 * DH) * sizeof(float);
+            dec_cross_attn_kernel<<<dim3(m->dec_heads, n), XA_THREADS, smem, s>>>(
+                w.qkv, w.cross_kv + (size_t)l * n * T * 2 * H, w.att, T, H, beam, ctx->f16);
+            MB_LAUNCH_CHECK(ctx);
+        }
+        RC(gemm(ctx, w.att, H, L.cout_w, H, R, H, L.cout_b, MB_ACT_NONE, w.x, w.tmp, MB_OUT_BF16, s));
+        RC(layernorm(ctx, w.tmp, w.x, L.ln2_w, L.ln2_b, R, H, 1e-5f, s));
+        RC(gemm(ctx, w.x, H, L.fc1_w, F, R, F, L.fc1_b, MB_ACT_RELU, nullptr, w.ffn, MB_OUT_BF16, s));
+        RC(gemm(ctx, w.ffn, F, L.fc2_w, H, R, H, L.fc2_b, MB_ACT_NONE, w.x, w.tmp, MB_OUT_BF16, s));
+        RC(layernorm(ctx, w.tmp, w.x, L.ln3_w, L.ln3_b, R, H, 1e-5f, s));
+    }
+    RC(gemm(ctx, w.x, H, m->out_w, V, R, V, nullptr, MB_ACT_NONE, nullptr, w.logits, MB_OUT_F32, s));
+    return 0;
+}
+
+int decode_prepare(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const bf16* enc_out, int n, int beam, int max_len,
+                   cudaStream_t s) {
+    const int H = m->dec_dim, T = m->tokens, D = m->enc_dim;
+    // static cross-attention K/V, once per crop (not per beam): [n*T, 2H] per layer
+    for (int l = 0; l < m->dec_layers; ++l)
+        RC(gemm(ctx, enc_out, D, m->dec[l].ckv_w, 2 * H, (long long)n * T, 2 * H, m->dec[l].ckv_b, MB_ACT_NONE, nullptr,
+                w.cross_kv + (size_t)l * n * T * 2 * H, MB_OUT_BF16, s));
+    const int R = n * beam;
+    search_init_kernel<<<mb_cdiv(R, 128), 128, 0, s>>>(w.st, n, beam, max_len);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // namespace
+
+void mb_free_trocr(mb_ctx* ctx) {
+    if (!ctx->trocr) return;
+    ctx->trocr->blob.release();
+    if (ctx->trocr->arena) cudaFree(ctx->trocr->arena);
+    delete ctx->trocr;
+    ctx->trocr = nullptr;
+}
+
+extern "C" int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes) {
+    if (!ctx) return MB_ERR_ARG;
+    mb_free_trocr(ctx);
+    TrocrModel* m = new TrocrModel();
+    ctx->trocr = m;
+    int rc = m->blob.load(ctx, blob_host, nbytes);
+    if (rc) { mb_free_trocr(ctx); return rc; }
+    const int wdt = ctx->f16 ? 3 : 1;
+    bool ok = true;
+    std::string missing;
+    auto W = [&](const std::string& name) -> const bf16* {
+        const BlobTensor* t = m->blob.get(name);
+        if (!t || t->dtype != wdt) { ok = false; missing = name; return nullptr; }
+        return (const bf16*)t->dev;
+    };
+    auto Fp = [&](const std::string& name) -> const float* {
+        const BlobTensor* t = m->blob.get(name);
+        if (!t || t->dtype != 0) { ok = false; missing = name; return nullptr; }
+        return (const float*)t->dev;
+    };
+    const BlobTensor* cfg = m->blob.get("config");
+    if (!cfg || cfg->dtype != 2 || cfg->nbytes < 11 * 4) {
+        mb_free_trocr(ctx);
+        return mb_set_err(ctx, MB_ERR_ARG, "trocr blob: config missing");
+    }
+    int c[11];
+    cudaMemcpy(c, cfg->dev, sizeof(c), cudaMemcpyDeviceToHost);
+    m->enc_dim = c[0]; m->enc_layers = c[1]; m->enc_heads = c[2]; m->enc_ffn = c[3];
+    m->dec_dim = c[4]; m->dec_layers = c[5]; m->dec_heads = c[6]; m->dec_ffn = c[7];
+    m->vocab = c[8]; m->tokens = c[9]; m->max_pos = c[10];
+    if (m->enc_dim != m->enc_heads * DH || m->dec_dim != m->dec_heads * DH || m->enc_dim % 64 || m->dec_dim % 64 ||
+        m->enc_ffn % 64 || m->dec_ffn % 64) {
+        mb_free_trocr(ctx);
+        return mb_set_err(ctx, MB_ERR_ARG, "trocr blob: unsupported geometry (head dim must be 64, widths multiples of 64)");
+    }
+    m->patch_w = W("enc.patch.w"); m->patch_b = Fp("enc.patch.b"); m->cls_pos = Fp("enc.cls_pos");
+    m->norm_w = Fp("enc.norm.w"); m->norm_b = Fp("enc.norm.b");
+    m->enc.resize(m->enc_layers);
+    for (int i = 0; i < m->enc_layers; ++i) {
+        const std::string p = "enc.L" + std::to_string(i) + ".";
+        EncLayer& L = m->enc[i];
+        L.ln1_w = Fp(p + "ln1.w"); L.ln1_b = Fp(p + "ln1.b"); L.ln2_w = Fp(p + "ln2.w"); L.ln2_b = Fp(p + "ln2.b");
+        L.qkv_w = W(p + "qkv.w"); L.proj_w = W(p + "proj.w"); L.proj_b = Fp(p + "proj.b");
+        L.fc1_w = W(p + "fc1.w"); L.fc1_b = Fp(p + "fc1.b"); L.fc2_w = W(p + "fc2.w"); L.fc2_b = Fp(p + "fc2.b");
+    }
+    m->embed = W("dec.embed"); m->pe = Fp("dec.pe"); m->out_w = W("dec.out.w");
+    m->dec.resize(m->dec_layers);
+    for (int i = 0; i < m->dec_layers; ++i) {
+        const std::string p = "dec.L" + std::to_string(i) + ".";
+        DecLayer& L = m->dec[i];
+        L.sqkv_w = W(p + "self.qkv.w"); L.sqkv_b = Fp(p + "self.qkv.b"); L.sout_w = W(p + "self.out.w"); L.sout_b = Fp(p + "self.out.b");
+        L.cq_w = W(p + "cross.q.w"); L.cq_b = Fp(p + "cross.q.b"); L.ckv_w = W(p + "cross.kv.w"); L.ckv_b = Fp(p + "cross.kv.b");
+        L.cout_w = W(p + "cross.out.w"); L.cout_b = Fp(p + "cross.out.b");
+        L.fc1_w = W(p + "fc1.w"); L.fc1_b = Fp(p + "fc1.b"); L.fc2_w = W(p + "fc2.w"); L.fc2_b = Fp(p + "fc2.b");
+        L.ln1_w = Fp(p + "ln1.w"); L.ln1_b = Fp(p + "ln1.b"); L.ln2_w = Fp(p + "ln2.w"); L.ln2_b = Fp(p + "ln2.b");
+        L.ln3_w = Fp(p + "ln3.w"); L.ln3_b = Fp(p + "ln3.b");
+    }
+    if (!ok) {
+        mb_free_trocr(ctx);
+        return mb_set_err(ctx, MB_ERR_ARG, "trocr blob: tensor %s missing or not packed for the context dtype (%s)",
+                          missing.c_str(), ctx->f16 ? "fp16" : "bf16");
+    }
+    return 0;
+}
+
+extern "C" int mb_trocr_dims(mb_ctx* ctx, int* dims) {
+    if (!ctx || !ctx->trocr) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded");
+    TrocrModel* m = ctx->trocr;
+    dims[0] = m->enc_dim; dims[1] = m->dec_dim; dims[2] = m->vocab; dims[3] = m->tokens;
+    return 0;
+}
+
+extern "C" int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void* enc_out_dev, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TrocrModel* m = ctx->trocr;
+    if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
+    MB_REQUIRE(ctx, n > 0, "trocr_encode: empty batch");
+    const int D = m->enc_dim, T = m->tokens;
+    const size_t wide = (size_t)(3 * D > m->enc_ffn ? 3 * D : m->enc_ffn);
+    const size_t M = (size_t)n * T;
+    const size_t bytes = (2 * M * D + M * wide) * 2 + 1024;
+    RC(ensure_arena(ctx, m, bytes));
+    Arena a{(unsigned char*)m->arena, 0, 0};
+    bf16* x = a.take<bf16>(M * D);
+    bf16* y = a.take<bf16>(M * D);
+    bf16* big = a.take<bf16>(M * wide);
+    return encode(ctx, m, (const bf16*)patches_dev, n, (bf16*)enc_out_dev, x, y, big, (cudaStream_t)stream);
+}
+
+// Greedy (beam 1) / beam search over encoder states.  tokens_out [n, out_ld] i32 (hypothesis incl. the final EOS,
+// padded with 1), lengths [n], scores [n] (length-normalised sum of log-probs, generator.py finalize_hypos).
+extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int beam, int max_len_b,
+                               int32_t* tokens_out_dev, int out_ld, int32_t* lengths_dev, float* scores_dev,
+                               int* steps_run, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TrocrModel* m = ctx->trocr;
+    if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
+    MB_REQUIRE(ctx, n > 0 && beam >= 1 && beam <= MAX_BEAM, "trocr_decode: beam must be in 1..%d", MAX_BEAM);
+    MB_REQUIRE(ctx, 2 * beam < m->vocab, "trocr_decode: vocabulary smaller than the candidate list");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int max_len = max_len_b < m->max_pos - 1 ? max_len_b : m->max_pos - 1;   // generator.py:57-61
+    MB_REQUIRE(ctx, max_len >= 1, "trocr_decode: max_len must be >= min_len (1)");
+    DecodeWs w;
+    const size_t bytes = plan_decode(m, n, beam, max_len, nullptr, &w);
+    RC(ensure_arena(ctx, m, bytes));
+    plan_decode(m, n, beam, max_len, (unsigned char*)m->arena, &w);
+    RC(decode_prepare(ctx, m, w, (const bf16*)enc_out_dev, n, beam, max_len, s));
+    const int R = n * beam, cand = 2 * beam;
+    int step = 0;
+    for (; step <= max_len; ++step) {
+        RC(decoder_step(ctx, m, w, n, beam, step, max_len, s));
+        logits_topk_kernel<<<R, TOPK_THREADS, 0, s>>>(w.logits, m->vocab, m->vocab, cand, step < 1, step >= max_len,
+                                                     w.cand_val, w.cand_idx);
+        MB_LAUNCH_CHECK(ctx);
+        search_step_kernel<<<mb_cdiv(n, 64), 64, 0, s>>>(w.st, w.cand_val, w.cand_idx, n, beam, step, max_len);
+        MB_LAUNCH_CHECK(ctx);
+        search_commit_kernel<<<mb_cdiv(R, 128), 128, 0, s>>>(w.st, n, beam, step, max_len);
+        MB_LAUNCH_CHECK(ctx);
+        if ((step & 1) == 1 || step == max_len) {    // poll the "all finished" counter every other step
+            int left = 0;
+            MB_CUDA(ctx, cudaMemcpyAsync(&left, w.st.n_unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
+            MB_CUDA(ctx, cudaStreamSynchronize(s));
+            if (left == 0) { ++step; break; }
+        }
+    }
+    if (steps_run) *steps_run = step;
+    search_pick_kernel<<<mb_cdiv(n, 64), 64, 0, s>>>(w.st, n, beam, max_len, tokens_out_dev, out_ld, lengths_dev, scores_dev);
+    MB_LAUNCH_CHECK(ctx);
+    MB_CUDA(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Parity hook: teacher-forced decoding (beam 1).  forced [n, L] i32 = the tokens chosen at steps 0..L-1;
+// logits_out [L, n, V] fp32 receives the raw decoder outputs of every step (before log-softmax / masking).
+extern "C" int mb_trocr_forced_logits(mb_ctx* ctx, const void* enc_out_dev, int n, const int32_t* forced_dev, int L,
+                                      float* logits_out_dev, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TrocrModel* m = ctx->trocr;
+    if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
+    MB_REQUIRE(ctx, n > 0 && L >= 1 && L < m->max_pos, "trocr_forced_logits: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    DecodeWs w;
+    const size_t bytes = plan_decode(m, n, 1, L, nullptr, &w);
+    RC(ensure_arena(ctx, m, bytes));
+    plan_decode(m, n, 1, L, (unsigned char*)m->arena, &w);
+    RC(decode_prepare(ctx, m, w, (const bf16*)enc_out_dev, n, 1, L, s));
+    for (int step = 0; step < L; ++step) {
+        RC(decoder_step(ctx, m, w, n, 1, step, L, s));
+        MB_CUDA(ctx, cudaMemcpyAsync(logits_out_dev + (size_t)step * n * m->vocab, w.logits, (size_t)n * m->vocab * 4,
+                                     cudaMemcpyDeviceToDevice, s));
+        forced_step_kernel<<<mb_cdiv(n, 128), 128, 0, s>>>(w.st, w.logits, m->vocab, m->vocab, forced_dev, L, n, step, L);
+        MB_LAUNCH_CHECK(ctx);
+    }
+    MB_CUDA(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Full recogniser on packed patch rows (mb_pack_crops / mb_pack_fragments layout 1): encoder + search, processed in
+// chunks of `chunk` crops (0 = pick from free memory).  Replaces task.inference_step(generator, ...) inside get_text
+// (marie/document/trocr_ocr_processor.py:142-149).
+extern "C" int mb_trocr_recognize(mb_ctx* ctx, const void* patches_dev, int n, int beam, int max_len_b, int chunk,
+                                  int32_t* tokens_out_dev, int out_ld, int32_t* lengths_dev, float* scores_dev,
+                                  void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TrocrModel* m = ctx->trocr;
+    if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
+    if (n == 0) return 0;
+    MB_REQUIRE(ctx, n > 0 && beam >= 1 && beam <= MAX_BEAM, "trocr_recognize: bad arguments");
+    if (chunk <= 0) chunk = 512;
+    const int D = m->enc_dim, T = m->tokens;
+    void* enc_out = nullptr;
+    const int cmax = n < chunk ? n : chunk;
+    if (cudaMalloc(&enc_out, (size_t)cmax * T * D * 2) != cudaSuccess) {
+        cudaGetLastError();
+        return mb_set_err(ctx, MB_ERR_OOM, "trocr_recognize: encoder output buffer");
+    }
+    int rc = 0;
+    for (int i0 = 0; i0 < n && !rc; i0 += chunk) {
+        const int c = n - i0 < chunk ? n - i0 : chunk;
+        rc = mb_trocr_encode(ctx, (const bf16*)patches_dev + (size_t)i0 * (T - 1) * 768, c, enc_out, stream);
+        if (!rc)
+            rc = mb_trocr_decode(ctx, enc_out, c, beam, max_len_b, tokens_out_dev + (size_t)i0 * out_ld, out_ld,
+                                 lengths_dev + i0, scores_dev + i0, nullptr, stream);
+    }
+    cudaFree(enc_out);
+    return rc;
+}

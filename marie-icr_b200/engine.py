@@ -1,0 +1,100 @@
+"""OcrEngineB200 — the per-page driver of the path: mirror of OcrEngine / DefaultOcrEngine
+(marie/ocr/ocr_engine.py:28-221, marie/ocr/default_ocr_engine.py:15-98) with the processors injected the same way
+(`box_processor=`, `default_ocr_processor=`).  `extract` returns the reference's result records
+({meta, words, lines} per page).
+
+When both processors are the B200 ones and all frames share one size, the pages go through the batched device
+pipeline (detection in micro-batches, crops from all pages pooled into recogniser batches); the records are the same
+as those of the page-by-page loop, which is kept for every other case.
+"""
+import numpy as np
+
+from .boxes import BoxProcessorCraftB200
+from .document import TrOcrProcessorB200
+from .pipeline import PSM_PRESETS, records_to_words
+from .plugin_api import CoordinateFormat, PSMode, assemble_result
+
+
+def copy_frames(frames):
+    """ocr_engine.py:416-433: PIL -> BGR ndarray, deep copy."""
+    out = []
+    for f in frames:
+        if not isinstance(f, np.ndarray):
+            f = np.array(f)[:, :, ::-1]
+        out.append(np.ascontiguousarray(f).copy())
+    return out
+
+
+class OcrEngineB200:
+    def __init__(self, models_dir="./model_zoo", cuda=True, *, box_processor=None, default_ocr_processor=None, **kwargs):
+        if box_processor is None:
+            box_processor = BoxProcessorCraftB200(models_dir=models_dir, cuda=cuda)
+        if default_ocr_processor is None:
+            default_ocr_processor = TrOcrProcessorB200(models_dir=models_dir, cuda=cuda,
+                                                       pipeline=getattr(box_processor, "pipeline", None))
+        self.box_processor = box_processor
+        self.icr_processor = default_ocr_processor
+        self.has_cuda = cuda
+
+    def extract(self, frames, pms_mode=PSMode.SPARSE, coordinate_format=CoordinateFormat.XYWH, regions=None,
+                queue_id=None, **kwargs):
+        queue_id = "0000-0000-0000-0000" if queue_id is None else queue_id
+        regions = [] if regions is None else regions
+        if isinstance(frames, np.ndarray) and frames.ndim == 3:
+            frames = [frames]
+        ro_frames = copy_frames(frames)
+        if len(regions):
+            raise NotImplementedError("region extraction (ocr_engine.py:223-414) is listed as 'next' in SURVEY.md §8f")
+        batched = (isinstance(self.box_processor, BoxProcessorCraftB200) and isinstance(self.icr_processor, TrOcrProcessorB200)
+                   and self.box_processor.pipeline is self.icr_processor.pipeline
+                   and pms_mode in (PSMode.SPARSE, PSMode.LINE, PSMode.MULTI_LINE)
+                   and len({f.shape for f in ro_frames}) == 1 and not kwargs.get("crop_to_content", False))
+        if batched:
+            return self._extract_batched(ro_frames, pms_mode, coordinate_format)
+        return self._extract_pagewise(ro_frames, queue_id, "0", pms_mode, coordinate_format)
+
+    # page-by-page loop of __process_extract_fullpage (ocr_engine.py:154-221)
+    def _extract_pagewise(self, frames, queue_id, checksum, pms_mode, coordinate_format):
+        results = []
+        for i, img in enumerate(frames):
+            boxes, fragments, lines, _, line_bboxes = self.box_processor.extract_bounding_boxes(queue_id, checksum, img, pms_mode)
+            result, _ = self.icr_processor.recognize(queue_id, checksum, img, boxes, fragments, lines)
+            self._finish(result, i, lines, line_bboxes, coordinate_format)
+            results.append(result)
+        return results
+
+    def _extract_batched(self, frames, pms_mode, coordinate_format):
+        import torch
+        pipe = self.box_processor.pipeline
+        pages = torch.from_numpy(np.stack(frames)).pin_memory()
+        icr = self.icr_processor
+        rec, counts = pipe.run_host(pages, preset=PSM_PRESETS[pms_mode.value], beam=icr.beam, max_len_b=icr.max_len_b,
+                                    out_ld=min(icr.max_len_b + 1, 64))
+        words = records_to_words(rec, icr.detok)
+        results, k = [], 0
+        for i, img in enumerate(frames):
+            page_words = words[k:k + counts[i]]
+            k += counts[i]
+            meta = {"imageSize": {"width": img.shape[1], "height": img.shape[0]}, "page": 0, "lang": "en"}
+            if not page_words:
+                result = {"meta": meta, "words": [], "lines": []}
+                lines = []
+            else:
+                boxes = [w["box"] for w in page_words]
+                lines = [w["line"] for w in page_words]
+                res = [{"confidence": w["confidence"], "id": f"img-{j}", "text": w["text"]} for j, w in enumerate(page_words)]
+                result = assemble_result(meta, boxes, lines, res)
+            self._finish(result, i, lines, [], coordinate_format)
+            results.append(result)
+        return results
+
+    @staticmethod
+    def _finish(result, page, lines, line_bboxes, coordinate_format):
+        if coordinate_format == CoordinateFormat.XYXY:
+            for word in result["words"]:
+                x, y, w, h = word["box"]
+                word["box"] = [x, y, x + w, y + h]
+        result["meta"]["page"] = page
+        result["meta"]["lines"] = lines
+        result["meta"]["lines_bboxes"] = line_bboxes
+        result["meta"]["format"] = coordinate_format.name.lower()

@@ -164,3 +164,62 @@ def craft_forward(x, want_feature=False):
     feat = torch.empty((n, h // 2, w // 2, 64), dtype=x.dtype, device=x.device) if want_feature else None
     _ctx(x).call("mb_craft_forward", ptr(x), c_int(n), c_int(h), c_int(w), ptr(scores), ptr(feat), cur_stream())
     return (scores, feat) if want_feature else scores
+
+
+# ------------------------------------------------------------------------------------------------ TrOCR
+def load_trocr(blob: bytes, device=0):
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    Context.get(device).call("mb_load_trocr", buf, ctypes.c_size_t(len(blob)))
+
+
+def trocr_dims(device=0):
+    d = (ctypes.c_int * 4)()
+    Context.get(device).call("mb_trocr_dims", d)
+    return dict(enc_dim=d[0], dec_dim=d[1], vocab=d[2], tokens=d[3])
+
+
+def trocr_encode(patches):
+    """patches [n*576, 768] 16-bit (pack_crops / pack_fragments layout=1) -> enc_out [n, 577, enc_dim]."""
+    ctx = _ctx(patches)
+    dims = trocr_dims(ctx.device)
+    n = patches.shape[0] // (dims["tokens"] - 1)
+    out = torch.empty((n, dims["tokens"], dims["enc_dim"]), dtype=patches.dtype, device=patches.device)
+    ctx.call("mb_trocr_encode", ptr(patches), c_int(n), ptr(out), cur_stream())
+    return out
+
+
+def trocr_decode(enc_out, beam=1, max_len_b=200, out_ld=None):
+    """enc_out [n, 577, D] -> (tokens [n, out_ld] i32 incl. final EOS, lengths [n] i32, scores [n] f32, steps_run)."""
+    ctx = _ctx(enc_out)
+    n = enc_out.shape[0]
+    out_ld = (max_len_b + 1) if out_ld is None else out_ld
+    tokens = torch.empty((n, out_ld), dtype=torch.int32, device=enc_out.device)
+    lengths = torch.empty((n,), dtype=torch.int32, device=enc_out.device)
+    scores = torch.empty((n,), dtype=torch.float32, device=enc_out.device)
+    steps = ctypes.c_int(0)
+    ctx.call("mb_trocr_decode", ptr(enc_out.contiguous()), c_int(n), c_int(beam), c_int(max_len_b), ptr(tokens),
+             c_int(out_ld), ptr(lengths), ptr(scores), ctypes.byref(steps), cur_stream())
+    return tokens, lengths, scores, steps.value
+
+
+def trocr_forced_logits(enc_out, forced):
+    """Teacher-forced decoder logits: forced [n, L] i32 -> [L, n, vocab] fp32."""
+    ctx = _ctx(enc_out)
+    n, L = forced.shape
+    vocab = trocr_dims(ctx.device)["vocab"]
+    out = torch.empty((L, n, vocab), dtype=torch.float32, device=enc_out.device)
+    ctx.call("mb_trocr_forced_logits", ptr(enc_out.contiguous()), c_int(n), ptr(forced.contiguous()), c_int(L), ptr(out),
+             cur_stream())
+    return out
+
+
+def trocr_recognize(patches, beam=1, max_len_b=200, chunk=0, out_ld=None):
+    ctx = _ctx(patches)
+    n = patches.shape[0] // (trocr_dims(ctx.device)["tokens"] - 1)
+    out_ld = (max_len_b + 1) if out_ld is None else out_ld
+    tokens = torch.empty((n, out_ld), dtype=torch.int32, device=patches.device)
+    lengths = torch.empty((n,), dtype=torch.int32, device=patches.device)
+    scores = torch.empty((n,), dtype=torch.float32, device=patches.device)
+    ctx.call("mb_trocr_recognize", ptr(patches), c_int(n), c_int(beam), c_int(max_len_b), c_int(chunk), ptr(tokens),
+             c_int(out_ld), ptr(lengths), ptr(scores), cur_stream())
+    return tokens, lengths, scores

@@ -1,0 +1,211 @@
+"""Batched device pipeline: pages -> CRAFT boxes -> crops -> TrOCR token ids, everything resident in HBM between the
+stages (the reference round-trips through the host after every stage: score maps `.cpu()` at
+marie/boxes/craft_box_processor.py:113-114, one H2D per crop at marie/document/trocr_ocr_processor.py:124, two D2H
+per hypothesis at :160-163).
+
+Stage map: K1 mb_page_preprocess -> K2-K4 mb_craft_forward -> K5-K7 mb_craft_post ->
+K9 mb_pack_crops (patch-row layout) -> K10 mb_trocr_encode -> K11/K12 mb_trocr_decode.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import Context
+
+# (text_threshold, link_threshold, low_text) per page-segmentation mode — the hard-coded presets of
+# marie/boxes/craft_box_processor.py:317-428
+PSM_PRESETS = {
+    "word": (0.6, 0.8, 0.3),
+    "sparse": (0.7, 0.45, 0.3),
+    "line": (0.4, 0.2, 0.3),
+    "raw_line": (0.4, 0.2, 0.5),
+    "multiline": (0.6, 0.3, 0.3),
+}
+
+RECORD_HEAD = 8   # page, x, y, w, h, line, length, score(bits)
+
+
+class _StageTimer:
+    """CUDA-event stage timers on the current stream (bench.py per-stage breakdown); a no-op unless enabled."""
+
+    def __init__(self):
+        self.enabled = False
+        self.pending, self.ms, self.units = [], {}, {}
+
+    def reset(self, enabled):
+        self.enabled = enabled
+        self.pending, self.ms, self.units = [], {}, {}
+
+    def start(self):
+        if not self.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, name, e0, units=0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.pending.append((name, e0, e1, units))
+
+    def collect(self):
+        torch.cuda.synchronize()
+        for name, e0, e1, units in self.pending:
+            self.ms[name] = self.ms.get(name, 0.0) + e0.elapsed_time(e1)
+            self.units[name] = self.units.get(name, 0) + units
+        self.pending = []
+        return dict(ms=dict(self.ms), units=dict(self.units))
+
+
+class PagePipeline:
+    """Owns the per-device context and the loaded models."""
+
+    def __init__(self, device=0, craft_blob=None, trocr_blob=None, micro_batch=8, crop_chunk=1024, max_labels=8192,
+                 max_boxes=4096):
+        self.device = int(device)
+        self.ctx = Context.get(self.device)
+        self.micro_batch = micro_batch
+        self.crop_chunk = crop_chunk
+        self.max_labels, self.max_boxes = max_labels, max_boxes
+        self.has_craft = self.has_trocr = False
+        self.timer = _StageTimer()
+        if craft_blob is not None:
+            self.load_craft(craft_blob)
+        if trocr_blob is not None:
+            self.load_trocr(trocr_blob)
+
+    @property
+    def dtype(self):
+        return self.ctx.torch_dtype
+
+    def load_craft(self, blob):
+        ops.load_craft(blob, self.device)
+        self.has_craft = True
+
+    def load_trocr(self, blob):
+        ops.load_trocr(blob, self.device)
+        self.has_trocr = True
+
+    # ------------------------------------------------------------------------------------------ detection
+    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False):
+        """pages_dev [n,H,W,3] u8 (BGR) on the device -> dict with per-crop `rects` [N,4] i32 (x,y,w,h), `page_idx`
+        [N] i32, `boxes` [N,4,2] f32 (page coordinates, adjustResultCoordinates output), `counts` (host list)."""
+        if not self.has_craft:
+            raise RuntimeError("CRAFT weights are not loaded")
+        n, ph, pw, _ = pages_dev.shape
+        tt, lt, low = preset
+        rects, boxes, pidx, counts, maps = [], [], [], [], []
+        for i0 in range(0, n, self.micro_batch):
+            chunk = pages_dev[i0:i0 + self.micro_batch]
+            m = chunk.shape[0]
+            t = self.timer.start()
+            x, ratio = ops.page_preprocess(chunk)
+            self.timer.stop("k1_preprocess", t, m)
+            t = self.timer.start()
+            scores = ops.craft_forward(x)
+            self.timer.stop("k2_4_craft", t, m)
+            del x
+            r2 = (1.0 / ratio) * 2
+            t = self.timer.start()
+            out = ops.craft_post(scores[0], scores[1], tt, lt, low, ratios=[(r2, r2)] * m, page_hw=[(ph, pw)] * m,
+                                 max_labels=self.max_labels, max_boxes=self.max_boxes)
+            self.timer.stop("k5_7_post", t, m)
+            nb = out["n_boxes"].cpu().tolist()          # mb_craft_post has synchronised the stream already
+            for j in range(m):
+                rects.append(out["rects"][j, :nb[j]])
+                boxes.append(out["adj"][j, :nb[j]])
+                pidx.append(torch.full((nb[j],), i0 + j, dtype=torch.int32, device=pages_dev.device))
+            counts.extend(nb)
+            if keep_maps:
+                maps.append(scores)
+        res = dict(rects=torch.cat(rects).contiguous(), boxes=torch.cat(boxes).contiguous(),
+                   page_idx=torch.cat(pidx).contiguous(), counts=counts)
+        if keep_maps:
+            res["scores"] = torch.cat(maps, 1)
+        return res
+
+    # ------------------------------------------------------------------------------------------ recognition
+    def recognize_crops(self, pages_dev, rects, page_idx, beam=1, max_len_b=200, out_ld=32):
+        """Crops addressed by (page, rect) -> (tokens [N,out_ld] i32, lengths [N] i32, scores [N] f32) on the device."""
+        if not self.has_trocr:
+            raise RuntimeError("TrOCR weights are not loaded")
+        n = rects.shape[0]
+        dev = pages_dev.device
+        tokens = torch.full((n, out_ld), 1, dtype=torch.int32, device=dev)
+        lengths = torch.zeros((n,), dtype=torch.int32, device=dev)
+        scores = torch.zeros((n,), dtype=torch.float32, device=dev)
+        for i0 in range(0, n, self.crop_chunk):
+            r = rects[i0:i0 + self.crop_chunk].contiguous()
+            p = page_idx[i0:i0 + self.crop_chunk].contiguous()
+            e = self.timer.start()
+            patches = ops.pack_crops(pages_dev, r, p, layout=1)
+            self.timer.stop("k9_crops", e, r.shape[0])
+            e = self.timer.start()
+            t, l, s = ops.trocr_recognize(patches, beam=beam, max_len_b=max_len_b, chunk=self.crop_chunk, out_ld=out_ld)
+            self.timer.stop("k10_12_trocr", e, r.shape[0])
+            tokens[i0:i0 + r.shape[0]] = t
+            lengths[i0:i0 + r.shape[0]] = l
+            scores[i0:i0 + r.shape[0]] = s
+        return tokens, lengths, scores
+
+    def recognize_fragments(self, fragments, beam=1, max_len_b=200, out_ld=32):
+        """Host fragments (list of [h,w,3] u8 BGR) -> (tokens, lengths, scores) on the device; one H2D for all."""
+        if not self.has_trocr:
+            raise RuntimeError("TrOCR weights are not loaded")
+        n = len(fragments)
+        dev = f"cuda:{self.device}"
+        tokens = torch.full((n, out_ld), 1, dtype=torch.int32, device=dev)
+        lengths = torch.zeros((n,), dtype=torch.int32, device=dev)
+        scores = torch.zeros((n,), dtype=torch.float32, device=dev)
+        for i0 in range(0, n, self.crop_chunk):
+            part = fragments[i0:i0 + self.crop_chunk]
+            patches = ops.pack_fragments(part, device=dev, layout=1)
+            t, l, s = ops.trocr_recognize(patches, beam=beam, max_len_b=max_len_b, chunk=self.crop_chunk, out_ld=out_ld)
+            tokens[i0:i0 + len(part)] = t
+            lengths[i0:i0 + len(part)] = l
+            scores[i0:i0 + len(part)] = s
+        return tokens, lengths, scores
+
+    # ------------------------------------------------------------------------------------------ whole path
+    def run_device(self, pages_dev, preset=PSM_PRESETS["sparse"], beam=1, max_len_b=200, out_ld=32):
+        """Pages already in HBM -> packed per-word records [N, RECORD_HEAD + out_ld] i32 on the device
+        (page, x, y, w, h, line=-1, length, score bits, tokens...) and the per-page counts (host)."""
+        det = self.detect(pages_dev, preset)
+        n = det["rects"].shape[0]
+        rec = torch.empty((n, RECORD_HEAD + out_ld), dtype=torch.int32, device=pages_dev.device)
+        if n:
+            tokens, lengths, scores = self.recognize_crops(pages_dev, det["rects"], det["page_idx"], beam, max_len_b, out_ld)
+            rec[:, 0] = det["page_idx"]
+            rec[:, 1:5] = det["rects"]
+            rec[:, 5] = -1                       # find_line_number(lines_bboxes=[], box) == -1 (line_processor.py:21-45)
+            rec[:, 6] = lengths
+            rec[:, 7] = scores.view(torch.int32)
+            rec[:, RECORD_HEAD:] = tokens
+        return rec, det["counts"]
+
+    def run_host(self, pages_pinned, **kw):
+        """Host pages ([n,H,W,3] u8, ideally pinned) -> records on the host; H2D and D2H inside."""
+        pages_dev = pages_pinned.to(f"cuda:{self.device}", non_blocking=True)
+        rec, counts = self.run_device(pages_dev, **kw)
+        return rec.cpu(), counts
+
+
+def records_to_words(rec, detok, page=None):
+    """Host records -> list of dicts {page, box [x,y,w,h], line, text, confidence, tokens} in detector order.
+    Text is upper-cased and the confidence is round(round(exp(score), 6), 4) as in
+    marie/document/trocr_ocr_processor.py:159-160,338-341."""
+    import math
+    rec = rec.numpy() if hasattr(rec, "numpy") else np.asarray(rec)
+    out = []
+    for r in rec:
+        if page is not None and int(r[0]) != page:
+            continue
+        ln = int(r[6])
+        toks = [int(t) for t in r[RECORD_HEAD:RECORD_HEAD + ln]]
+        score = float(np.array([r[7]], dtype=np.int32).view(np.float32)[0])
+        conf = round(round(math.exp(score), 6), 4) if ln else 0.0
+        out.append(dict(page=int(r[0]), box=[int(v) for v in r[1:5]], line=int(r[5]), tokens=toks,
+                        text=detok.decode(toks).upper(), confidence=conf))
+    return out

@@ -106,3 +106,58 @@ def pack_craft(state_dict, dtype=torch.float16):
         t[name + ".w"] = _pack_conv(w, rows_, cin_pad, dtype)
         t[name + ".b"] = _pad_bias(b, rows_)
     return build_blob(t)
+
+
+def pack_trocr(state_dict, cfg, dtype=torch.float16):
+    """fairseq TrOCR state dict (`encoder.deit.*`, `decoder.*`) -> blob bytes for mb_load_trocr.
+    cfg: any object with enc_dim, enc_layers, enc_heads, enc_ffn, dec_dim, dec_layers, dec_heads, dec_ffn, vocab,
+    tokens, max_positions.  Layout choices: q/k/v of the decoder self-attention fused into one [3H, H] matrix,
+    cross k/v into [2H, enc_dim]; the fairseq query scaling head_dim^-0.5 = 0.125 (a power of two, exact) is folded
+    into the decoder q weights/biases; cls_token is folded into row 0 of the position table; the sinusoidal position
+    table (fairseq SinusoidalPositionalEmbedding) is precomputed in fp32."""
+    import math
+    sd = {k: v.detach().float().cpu() for k, v in state_dict.items() if torch.is_tensor(v)}
+    t = {}
+    t["config"] = torch.tensor([cfg.enc_dim, cfg.enc_layers, cfg.enc_heads, cfg.enc_ffn, cfg.dec_dim, cfg.dec_layers,
+                                cfg.dec_heads, cfg.dec_ffn, cfg.vocab, cfg.tokens, cfg.max_positions], dtype=torch.int32)
+    e = "encoder.deit."
+    D, H = cfg.enc_dim, cfg.dec_dim
+    assert D // cfg.enc_heads == 64 and H // cfg.dec_heads == 64, "head dim must be 64"
+    t["enc.patch.w"] = sd[e + "patch_embed.proj.weight"].reshape(D, -1).to(dtype)
+    t["enc.patch.b"] = sd[e + "patch_embed.proj.bias"]
+    cls_pos = sd[e + "pos_embed"][0].clone()
+    cls_pos[0] += sd[e + "cls_token"][0, 0]
+    t["enc.cls_pos"] = cls_pos
+    t["enc.norm.w"], t["enc.norm.b"] = sd[e + "norm.weight"], sd[e + "norm.bias"]
+    for i in range(cfg.enc_layers):
+        b, p = f"{e}blocks.{i}.", f"enc.L{i}."
+        t[p + "ln1.w"], t[p + "ln1.b"] = sd[b + "norm1.weight"], sd[b + "norm1.bias"]
+        t[p + "ln2.w"], t[p + "ln2.b"] = sd[b + "norm2.weight"], sd[b + "norm2.bias"]
+        t[p + "qkv.w"] = sd[b + "attn.qkv.weight"].to(dtype)
+        t[p + "proj.w"], t[p + "proj.b"] = sd[b + "attn.proj.weight"].to(dtype), sd[b + "attn.proj.bias"]
+        t[p + "fc1.w"], t[p + "fc1.b"] = sd[b + "mlp.fc1.weight"].to(dtype), sd[b + "mlp.fc1.bias"]
+        t[p + "fc2.w"], t[p + "fc2.b"] = sd[b + "mlp.fc2.weight"].to(dtype), sd[b + "mlp.fc2.bias"]
+    t["dec.embed"] = sd["decoder.embed_tokens.weight"].to(dtype)
+    half = H // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float) * -(math.log(10000) / (half - 1)))
+    ang = torch.arange(cfg.max_positions + 2, dtype=torch.float)[:, None] * freq[None]
+    pe = torch.cat([ang.sin(), ang.cos()], 1)
+    pe[1] = 0                                               # padding_idx
+    t["dec.pe"] = pe.contiguous()
+    t["dec.out.w"] = sd["decoder.output_projection.weight"].to(dtype)
+    sc = 64 ** -0.5
+    for i in range(cfg.dec_layers):
+        b, p = f"decoder.layers.{i}.", f"dec.L{i}."
+        sa, ca = b + "self_attn.", b + "encoder_attn."
+        t[p + "self.qkv.w"] = torch.cat([sd[sa + "q_proj.weight"] * sc, sd[sa + "k_proj.weight"], sd[sa + "v_proj.weight"]], 0).to(dtype)
+        t[p + "self.qkv.b"] = torch.cat([sd[sa + "q_proj.bias"] * sc, sd[sa + "k_proj.bias"], sd[sa + "v_proj.bias"]], 0)
+        t[p + "self.out.w"], t[p + "self.out.b"] = sd[sa + "out_proj.weight"].to(dtype), sd[sa + "out_proj.bias"]
+        t[p + "cross.q.w"], t[p + "cross.q.b"] = (sd[ca + "q_proj.weight"] * sc).to(dtype), sd[ca + "q_proj.bias"] * sc
+        t[p + "cross.kv.w"] = torch.cat([sd[ca + "k_proj.weight"], sd[ca + "v_proj.weight"]], 0).to(dtype)
+        t[p + "cross.kv.b"] = torch.cat([sd[ca + "k_proj.bias"], sd[ca + "v_proj.bias"]], 0)
+        t[p + "cross.out.w"], t[p + "cross.out.b"] = sd[ca + "out_proj.weight"].to(dtype), sd[ca + "out_proj.bias"]
+        t[p + "fc1.w"], t[p + "fc1.b"] = sd[b + "fc1.weight"].to(dtype), sd[b + "fc1.bias"]
+        t[p + "fc2.w"], t[p + "fc2.b"] = sd[b + "fc2.weight"].to(dtype), sd[b + "fc2.bias"]
+        for j, name in enumerate(("self_attn_layer_norm", "encoder_attn_layer_norm", "final_layer_norm"), 1):
+            t[p + f"ln{j}.w"], t[p + f"ln{j}.b"] = sd[b + name + ".weight"], sd[b + name + ".bias"]
+    return build_blob({k: v.contiguous() for k, v in t.items()})

@@ -14,61 +14,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-# (conv index, bn index) pairs per slice of torchvision vgg16_bn.features as cut by vgg16_bn.py:33-40
-_VGG = {
-    "slice1": [(0, 1), (3, 4), (7, 8), (10, 11)],
-    "slice2": [(14, 15), (17, 18)],
-    "slice3": [(20, 21), (24, 25), (27, 28)],
-    "slice4": [(30, 31), (34, 35), (37, 38)],
-}
-_VGG_CH = {0: (3, 64), 3: (64, 64), 7: (64, 128), 10: (128, 128), 14: (128, 256), 17: (256, 256), 20: (256, 256),
-           24: (256, 512), 27: (512, 512), 30: (512, 512), 34: (512, 512), 37: (512, 512)}
-_UP = {"upconv1": (1024, 512, 256), "upconv2": (512, 256, 128), "upconv3": (256, 128, 64), "upconv4": (128, 64, 32)}
-_CLS = {0: (32, 32, 3), 2: (32, 32, 3), 4: (32, 16, 3), 6: (16, 16, 1), 8: (16, 2, 1)}
-
-
-def synth_craft_state(seed=0, random_bn=False, bf16_round=True):
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-
-    def conv(key, cin, cout, k):
-        w = torch.empty(cout, cin, k, k)
-        fan_in, fan_out = cin * k * k, cout * k * k
-        bound = (6.0 / (fan_in + fan_out)) ** 0.5            # xavier_uniform_, gain 1
-        w.uniform_(-bound, bound, generator=g)
-        if bf16_round:
-            w = w.to(torch.bfloat16).float()
-        sd[key + ".weight"] = w
-        sd[key + ".bias"] = torch.zeros(cout)
-
-    def bn(key, c):
-        if random_bn:
-            sd[key + ".weight"] = torch.empty(c).uniform_(0.6, 1.4, generator=g)
-            sd[key + ".bias"] = torch.empty(c).uniform_(-0.2, 0.2, generator=g)
-            sd[key + ".running_mean"] = torch.empty(c).uniform_(-0.2, 0.2, generator=g)
-            sd[key + ".running_var"] = torch.empty(c).uniform_(0.5, 1.5, generator=g)
-        else:
-            sd[key + ".weight"] = torch.ones(c)
-            sd[key + ".bias"] = torch.zeros(c)
-            sd[key + ".running_mean"] = torch.zeros(c)
-            sd[key + ".running_var"] = torch.ones(c)
-        sd[key + ".num_batches_tracked"] = torch.tensor(0)
-
-    for sl, pairs in _VGG.items():
-        for ci, bi in pairs:
-            cin, cout = _VGG_CH[ci]
-            conv(f"basenet.{sl}.{ci}", cin, cout, 3)
-            bn(f"basenet.{sl}.{bi}", cout)
-    conv("basenet.slice5.1", 512, 1024, 3)
-    conv("basenet.slice5.2", 1024, 1024, 1)
-    for name, (i, m, o) in _UP.items():
-        conv(f"{name}.conv.0", i + m, m, 1)
-        bn(f"{name}.conv.1", m)
-        conv(f"{name}.conv.3", m, o, 3)
-        bn(f"{name}.conv.4", o)
-    for idx, (cin, cout, k) in _CLS.items():
-        conv(f"conv_cls.{idx}", cin, cout, k)
-    return sd
+from synthetic.weights import glyph_craft_state, synth_craft_state  # noqa: F401  (generators live outside oracle/)
 
 
 def _cbr(sd, x, ck, bk, relu=True, padding=1, dilation=1):

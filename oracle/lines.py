@@ -51,9 +51,9 @@ def find_line_number(lines, box):
     return line
 
 
-def _merge_pass(boxes, min_iou):
+def _merge_pass(boxes, min_iou, kind=None):
     boxes = np.asarray(boxes, dtype=np.int64).reshape(-1, 4)
-    boxes = boxes[np.argsort(boxes[:, 1])]          # default (quicksort) argsort, like the reference
+    boxes = boxes[np.argsort(boxes[:, 1], kind=kind)]   # kind=None: default (quicksort) argsort, like the reference
     n = len(boxes)
     visited = np.zeros(n, bool)
     out = []
@@ -76,15 +76,17 @@ def _merge_pass(boxes, min_iou):
     return out
 
 
-def line_merge(bboxes):
-    """Seven merge passes at decreasing IoU (early stop after 3 passes without change), containment prune, y-sort."""
+def line_merge(bboxes, kind=None):
+    """Seven merge passes at decreasing IoU (early stop after 3 passes without change), containment prune, y-sort.
+    kind=None reproduces the reference call for call (numpy's default argsort, whose order among equal y is
+    platform-dependent); kind="stable" is the deterministic tie rule the product implements."""
     if len(bboxes) == 0:
         return []
     merged = [list(b) for b in bboxes]
     unchanged = 0
     for thr in (0.8, 0.7, 0.6, 0.5, 0.4, 0.37, 0.35):
         before = len(merged)
-        merged = _merge_pass(merged, thr)
+        merged = _merge_pass(merged, thr, kind)
         if len(merged) == before:
             unchanged += 1
             if unchanged > 2:
@@ -93,7 +95,7 @@ def line_merge(bboxes):
     x0, y0, x1, y1 = m[:, 0], m[:, 1], m[:, 0] + m[:, 2], m[:, 1] + m[:, 3]
     inside = (x0[None] > x0[:, None]) & (x1[None] < x1[:, None]) & (y0[None] > y0[:, None]) & (y1[None] < y1[:, None])
     m = m[~inside.any(0)]
-    return m[np.argsort(m[:, 1])]
+    return m[np.argsort(m[:, 1], kind=kind)]
 
 
 def merge_block(bboxes):

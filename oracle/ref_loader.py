@@ -59,3 +59,40 @@ def load():
     _cache.update(craft=ref_craft, craft_utils=ref_craft_utils, imgproc=ref_imgproc, overlap=overlap,
                   lines=lines)
     return _cache
+
+
+def load_ocr_processor():
+    """The reference's OcrProcessor base class (marie/document/ocr_processor.py:34-267), loaded by path behind stub
+    modules for its logging / font / filesystem helpers.  Its `recognize` is the result-assembly oracle."""
+    if "ocr_processor" in _cache:
+        return _cache["ocr_processor"]
+    load()
+
+    def _load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    _load("marie.registry_base", "marie/registry_base.py")
+    _load("marie.base_handler", "marie/base_handler.py")
+    dt = types.ModuleType("marie.utils.draw_truetype")
+    dt.determine_font_size = lambda h: 10
+    dt.get_default_font = lambda s: None
+    sys.modules["marie.utils.draw_truetype"] = dt
+    ut = types.ModuleType("marie.utils.utils")
+
+    def ensure_exists(d):
+        os.makedirs(d, exist_ok=True)
+        return d
+    ut.ensure_exists = ensure_exists
+    sys.modules["marie.utils.utils"] = ut
+    for pkg in ("marie.document",):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+    mod = _load("ref_ocr_processor", "marie/document/ocr_processor.py")
+    _cache["ocr_processor"] = mod.OcrProcessor
+    return mod.OcrProcessor

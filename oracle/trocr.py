@@ -25,121 +25,21 @@ from dataclasses import dataclass
 import torch
 import torch.nn.functional as F
 
-BOS, PAD, EOS, UNK = 0, 1, 2, 3
+from synthetic.weights import (BOS, EOS, PAD, UNK, TrocrConfig, synth_trocr_state, trocr_base, trocr_large,  # noqa: F401
+                               trocr_tiny)
 
 
-@dataclass
-class TrocrConfig:
-    enc_dim: int = 768
-    enc_layers: int = 12
-    enc_heads: int = 12
-    enc_ffn: int = 3072
-    dec_dim: int = 1024
-    dec_layers: int = 12
-    dec_heads: int = 16
-    dec_ffn: int = 4096
-    vocab: int = 50265
-    img: int = 384
-    patch: int = 16
-    max_positions: int = 1024
-
-    @property
-    def tokens(self):
-        return (self.img // self.patch) ** 2 + 1
-
-
-def trocr_base():
-    return TrocrConfig()
-
-
-def trocr_large():
-    return TrocrConfig(enc_dim=1024, enc_layers=24, enc_heads=16, enc_ffn=4096)
-
-
-def trocr_tiny(vocab=1000):
-    """Same structure (head dim 64, 577 tokens) at toy widths — for fast CPU/GPU parity tests."""
-    return TrocrConfig(enc_dim=128, enc_layers=2, enc_heads=2, enc_ffn=256, dec_dim=128, dec_layers=2, dec_heads=2,
-                       dec_ffn=256, vocab=vocab)
-
-
-# ------------------------------------------------------------------------------------------------- weights
-def synth_trocr_state(cfg, seed=0, round_to=torch.float16, out_scale=0.25):
-    """Random-init weights following timm's / fairseq's initialisers (trunc-normal 0.02 ViT linears, xavier-uniform
-    decoder linears, N(0, d^-0.5) embeddings), rounded once to `round_to` so the oracle and the device share the
-    exact same values.  The decoder's residual-writing projections (out_proj, fc2) are scaled by `out_scale` so the
-    residual stream keeps the position signal that calibrate_eos() relies on."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-
-    def rnd(t):
-        return t.to(round_to).float() if round_to is not None else t
-
-    def tn(*shape, std=0.02):
-        return rnd(torch.empty(*shape).normal_(0, std, generator=g).clamp_(-2 * std, 2 * std))
-
-    def xavier(out_f, in_f, gain=1.0):
-        b = gain * math.sqrt(6.0 / (in_f + out_f))
-        return rnd(torch.empty(out_f, in_f).uniform_(-b, b, generator=g))
-
-    def ln(key, d):
-        sd[key + ".weight"] = rnd(1.0 + 0.1 * torch.empty(d).normal_(0, 1, generator=g))
-        sd[key + ".bias"] = rnd(0.05 * torch.empty(d).normal_(0, 1, generator=g))
-
-    def bias(d, std=0.02):
-        return rnd(torch.empty(d).normal_(0, std, generator=g))
-
-    D = cfg.enc_dim
-    e = "encoder.deit."
-    sd[e + "patch_embed.proj.weight"] = tn(D, 3, cfg.patch, cfg.patch)
-    sd[e + "patch_embed.proj.bias"] = bias(D)
-    sd[e + "cls_token"] = tn(1, 1, D)
-    sd[e + "pos_embed"] = tn(1, cfg.tokens, D)
-    for i in range(cfg.enc_layers):
-        b = f"{e}blocks.{i}."
-        ln(b + "norm1", D)
-        sd[b + "attn.qkv.weight"] = tn(3 * D, D, std=0.05)
-        sd[b + "attn.proj.weight"] = tn(D, D)
-        sd[b + "attn.proj.bias"] = bias(D)
-        ln(b + "norm2", D)
-        sd[b + "mlp.fc1.weight"] = tn(cfg.enc_ffn, D)
-        sd[b + "mlp.fc1.bias"] = bias(cfg.enc_ffn)
-        sd[b + "mlp.fc2.weight"] = tn(D, cfg.enc_ffn)
-        sd[b + "mlp.fc2.bias"] = bias(D)
-    ln(e + "norm", D)
-
-    H = cfg.dec_dim
-    emb = torch.empty(cfg.vocab, H).normal_(0, H ** -0.5, generator=g)
-    emb[PAD] = 0
-    sd["decoder.embed_tokens.weight"] = rnd(emb)
-    for i in range(cfg.dec_layers):
-        b = f"decoder.layers.{i}."
-        for name, kdim in (("self_attn", H), ("encoder_attn", D)):
-            sd[b + name + ".q_proj.weight"] = xavier(H, H, 2 ** -0.5)
-            sd[b + name + ".k_proj.weight"] = xavier(H, kdim, 2 ** -0.5)
-            sd[b + name + ".v_proj.weight"] = xavier(H, kdim, 2 ** -0.5)
-            sd[b + name + ".out_proj.weight"] = xavier(H, H, out_scale)
-            for p in ("q_proj", "k_proj", "v_proj", "out_proj"):
-                sd[b + name + f".{p}.bias"] = bias(H)
-        ln(b + "self_attn_layer_norm", H)
-        ln(b + "encoder_attn_layer_norm", H)
-        sd[b + "fc1.weight"] = xavier(cfg.dec_ffn, H)
-        sd[b + "fc1.bias"] = bias(cfg.dec_ffn)
-        sd[b + "fc2.weight"] = xavier(H, cfg.dec_ffn, out_scale)
-        sd[b + "fc2.bias"] = bias(H)
-        ln(b + "final_layer_norm", H)
-    wout = torch.empty(cfg.vocab, H).normal_(0, H ** -0.5, generator=g)
-    sd["decoder.output_projection.weight"] = rnd(wout)
-    return sd
-
-
-def calibrate_eos(sd, cfg, eos_step=6, samples=6, seed=0, margin=1.0, round_to=torch.float16):
+def calibrate_eos(sd, cfg, eos_step=6, samples=6, seed=0, margin=1.0, round_to=torch.float16, enc=None):
     """A random-init decoder never emits EOS (1 chance in V per step), so every hypothesis would run to max_len=200.
     Like the CRAFT 'calibrated head'  the EOS row of the output projection is set, in place, to the
     direction that separates the decoder's hidden state at steps >= eos_step from earlier steps (measured on a few
-    greedy roll-outs over random encoder states), scaled so EOS wins the arg-max around step `eos_step`.  The same
+    greedy roll-outs over the encoder states `enc` — pass real encoder outputs of a few sample crops; random
+    states are only a fallback), scaled so EOS wins the arg-max around step `eos_step`.  The same
     weights go to the oracle and the device, so parity is unaffected.  Returns the scale used."""
     g = torch.Generator().manual_seed(seed + 77)
-    enc = torch.randn(samples, cfg.tokens, cfg.enc_dim, generator=g)
+    if enc is None:
+        enc = torch.randn(samples, cfg.tokens, cfg.enc_dim, generator=g)
+    samples = enc.shape[0]
     W = sd["decoder.output_projection.weight"]
     W[EOS] = 0
     st = DecoderState(sd, cfg, enc)

@@ -1,0 +1,109 @@
+"""The drop-in boundary end to end on the GPU: BoxProcessorCraftB200 + TrOcrProcessorB200 behind OcrEngineB200, the
+batched pipeline against the page-by-page plugin loop, and every stage against the oracle fed with the same
+intermediate data (score maps -> boxes -> crops -> token ids -> text)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(cuda_ctx):
+    from marie_icr_b200.boxes import BoxProcessorCraftB200
+    from marie_icr_b200.document import TrOcrProcessorB200
+    from marie_icr_b200.engine import OcrEngineB200
+    from oracle import craft_net, resample, synth, trocr
+    cuda_ctx.set_dtype("fp16")
+    pages = [synth.synth_page(i, height=660, width=510, scale=0.8, line_pitch=48, gap=24, margin=30)[0] for i in range(3)]
+    sd = craft_net.glyph_craft_state(0)
+    cfg = trocr.trocr_tiny()
+    tsd = trocr.synth_trocr_state(cfg, 2)
+    box = BoxProcessorCraftB200(state_dict=sd)
+    frag0 = box.extract_bounding_boxes("t", "k", pages[0])[1][:3]
+    cal = torch.stack([torch.from_numpy(resample.fragment_to_input(f)) for f in frag0])
+    with torch.no_grad():
+        trocr.calibrate_eos(tsd, cfg, eos_step=4, enc=trocr.encoder_forward(tsd, cfg, cal))
+    icr = TrOcrProcessorB200(state_dict=tsd, config=cfg, beam=1, max_len_b=16, pipeline=box.pipeline)
+    eng = OcrEngineB200(box_processor=box, default_ocr_processor=icr)
+    return eng, pages, sd, tsd, cfg
+
+
+def _plain(results):
+    out = []
+    for r in results:
+        out.append(dict(meta={k: (np.asarray(v).tolist() if not isinstance(v, (str, int, dict)) else v) for k, v in r["meta"].items()},
+                        words=[{k: (np.asarray(v).tolist() if not isinstance(v, (str, int, float)) else v) for k, v in w.items()} for w in r["words"]],
+                        lines=[{k: (np.asarray(v).tolist() if not isinstance(v, (str, int, float)) else v) for k, v in l.items()} for l in r["lines"]]))
+    return out
+
+
+def test_box_processor_contract_and_oracle(engine):
+    from marie_icr_b200 import ops
+    from marie_icr_b200.plugin_api import PSMode
+    from oracle import craft_post
+    eng, pages, sd, _, _ = engine
+    box = eng.box_processor
+    page = pages[1]
+    rects, frags, line_ids, pred, lines_bboxes = box.extract_bounding_boxes("id", "key", page, PSMode.SPARSE)
+    assert len(rects) == len(frags) == len(line_ids) > 10 and lines_bboxes == []
+    assert all(l == -1 for l in line_ids) and isinstance(frags, list)
+    # oracle post-processing on the device's own score maps
+    dev = torch.from_numpy(page[None]).cuda()
+    x, ratio = ops.page_preprocess(dev)
+    scores = ops.craft_forward(x)
+    det, _, _ = craft_post.det_boxes_cv(scores[0, 0].cpu().numpy(), scores[1, 0].cpu().numpy(), 0.7, 0.45, 0.3)
+    adj = craft_post.adjust_result_coordinates([b.copy() for b in det], 1 / ratio, 1 / ratio)
+    want = craft_post.boxes_to_rects(adj, page.shape[0], page.shape[1])
+    same = [np.array_equal(a, b) for a, b in zip(np.asarray(det), (pred["bboxes"] / np.float32(2 / ratio)))]
+    assert len(want) == len(rects)
+    mism = sum(r != w for r, w in zip(rects, want))
+    assert mism <= max(1, len(want) // 100), f"{mism}/{len(want)} rects differ from the oracle"
+    for r, f in zip(rects, frags):
+        assert np.array_equal(f, craft_post.crop_rect(page, r))
+    # WORD / RAW_LINE: no detection, the whole image is one box (craft_box_processor.py:453-476)
+    r2, f2, l2, p2, _ = box.extract_bounding_boxes("id", "key", page[:40, :200], PSMode.WORD)
+    assert r2 == [[0, 0, 200, 40]] and l2 == [0] and p2 == {} and np.array_equal(f2[0], page[:40, :200])
+    with pytest.raises(Exception, match="can't be empty"):
+        box.extract_bounding_boxes("id", "key", None)
+    with pytest.raises(Exception, match="not supported"):
+        box.extract_bounding_boxes("id", "key", page, "bogus")
+
+
+def test_icr_processor_matches_oracle(engine):
+    import math
+    from marie_icr_b200.bpe import SyntheticDetokenizer
+    from oracle import resample, trocr
+    eng, pages, _, tsd, cfg = engine
+    _, frags, _, _, _ = eng.box_processor.extract_bounding_boxes("id", "key", pages[2])
+    frags = frags[:24]
+    res = eng.icr_processor.recognize_from_fragments(frags)
+    assert [r["id"] for r in res] == [f"img-{k}" for k in range(len(frags))]
+    chw = torch.stack([torch.from_numpy(resample.fragment_to_input(f)) for f in frags]).half().float()
+    with torch.no_grad():
+        ref = trocr.recognize(tsd, cfg, chw, beam=1, max_len_b=16)
+    detok = SyntheticDetokenizer()
+    exact = 0
+    for r, (toks, conf) in zip(res, ref):
+        if r["text"] == detok.decode(toks).upper():
+            exact += 1
+            assert abs(r["confidence"] - round(round(conf, 6), 4)) <= 2e-3
+    assert exact >= len(frags) - 1, f"only {exact}/{len(frags)} texts identical to the oracle"
+    assert eng.icr_processor.recognize_from_fragments([]) == []
+
+
+def test_engine_batched_equals_pagewise(engine):
+    from marie_icr_b200.plugin_api import CoordinateFormat, PSMode
+    eng, pages, _, _, _ = engine
+    a = _plain(eng.extract(pages, PSMode.SPARSE, CoordinateFormat.XYXY))
+    b = _plain(eng._extract_pagewise([p.copy() for p in pages], "q", "0", PSMode.SPARSE, CoordinateFormat.XYXY))
+    assert len(a) == len(b) == 3
+    for i, (ra, rb) in enumerate(zip(a, b)):
+        assert ra["meta"] == rb["meta"] and ra["meta"]["page"] == i and ra["meta"]["format"] == "xyxy"
+        assert len(ra["words"]) > 10
+        assert ra["words"] == rb["words"]
+        assert ra["lines"] == rb["lines"]
+    # a blank page yields an empty record, not an error (ocr_processor.py:147-154)
+    blank = np.full_like(pages[0], 255)
+    r = eng.extract([blank, pages[0]])
+    assert r[0]["words"] == [] and len(r[1]["words"]) == len(a[0]["words"])

@@ -1,0 +1,103 @@
+"""Host-side product logic that needs no GPU: the C++ line grouping behind the C ABI (csrc/lines.cu), the result
+assembly mirror, the PSM presets, the detokenizers and the record codec."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__
+    __graft_entry__.build()
+
+
+def test_line_merge_matches_golden_and_oracle():
+    from marie_icr_b200 import lines as prod
+    from oracle import lines as ora
+    with open(os.path.join(GOLD, "lines.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        ys = [b[1] for b in c["boxes"]]
+        got = np.asarray(prod.line_merge(c["boxes"])).reshape(-1, 4)
+        if len(set(ys)) == len(ys):                       # tie-free: identical to the reference's own output
+            assert got.tolist() == c["lines"]
+        assert got.tolist() == np.asarray(ora.line_merge(c["boxes"], kind="stable")).reshape(-1, 4).tolist()
+        assert prod.find_line_numbers(c["lines"], c["boxes"]).tolist() == c["line_ids"]
+    rng = np.random.default_rng(5)
+    for n in (1, 17, 64, 333):
+        ys = rng.permutation(4000)[:n]
+        boxes = np.stack([rng.integers(0, 2000, n), ys, rng.integers(5, 300, n), rng.integers(0, 60, n)], 1)
+        a = np.asarray(ora.line_merge(boxes.tolist())).reshape(-1, 4)            # reference-order oracle
+        assert np.array_equal(np.asarray(prod.line_merge(boxes)).reshape(-1, 4), a)
+    assert prod.find_line_number([], [1, 2, 3, 4]) == -1
+    assert len(prod.line_merge([])) == 0
+
+
+def test_result_assembly_matches_reference_golden():
+    from marie_icr_b200.plugin_api import OcrProcessor
+    with open(os.path.join(GOLD, "ocr_result.json")) as f:
+        g = json.load(f)
+
+    class P(OcrProcessor):
+        def is_available(self):
+            return True
+
+        def recognize_from_fragments(self, frags, **kw):
+            return g["canned"]
+
+    img = np.zeros((600, 1000, 3), np.uint8)
+    res, overlay = P().recognize("golden", "key", img, g["boxes"], [img[:2, :2]] * len(g["boxes"]), g["lines"])
+    assert overlay is None
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "tools"))
+    from make_golden import jsonable
+    assert json.loads(json.dumps(jsonable(res))) == g["result"]
+    empty, ov = P().recognize("golden", "key", img, [], [], [])
+    assert empty["words"] == [] and empty["lines"] == [] and ov.shape == img.shape
+    with pytest.raises(Exception, match="can't be empty"):
+        P().recognize("golden", "key", None, [], [], [])
+    with pytest.raises(AssertionError):
+        P().recognize("golden", "key", img, g["boxes"], [], g["lines"])
+
+
+def test_presets_and_enums():
+    from marie_icr_b200.pipeline import PSM_PRESETS
+    from marie_icr_b200.plugin_api import CoordinateFormat, PSMode
+    assert PSM_PRESETS["sparse"] == (0.7, 0.45, 0.3) and PSM_PRESETS["line"] == (0.4, 0.2, 0.3)
+    assert PSM_PRESETS["multiline"] == (0.6, 0.3, 0.3) and PSM_PRESETS["raw_line"] == (0.4, 0.2, 0.5)
+    assert PSMode.from_value(None) == PSMode.SPARSE and PSMode.from_value("LINE") == PSMode.LINE
+    assert CoordinateFormat.convert([1, 2, 3, 4], CoordinateFormat.XYWH, CoordinateFormat.XYXY) == [1, 2, 4, 6]
+    assert CoordinateFormat.convert((1, 2, 4, 6), CoordinateFormat.XYXY, CoordinateFormat.XYWH) == (1, 2, 3, 4)
+
+
+def test_records_and_detokenizer():
+    import math
+    import torch
+    from marie_icr_b200.bpe import SyntheticDetokenizer
+    from marie_icr_b200.pipeline import RECORD_HEAD, records_to_words
+    rec = torch.zeros((2, RECORD_HEAD + 6), dtype=torch.int32)
+    rec[0, :7] = torch.tensor([3, 10, 20, 30, 40, -1, 3])
+    rec[0, 7] = torch.tensor([-0.25]).view(torch.int32)[0]
+    rec[0, RECORD_HEAD:RECORD_HEAD + 3] = torch.tensor([100, 207, 2])
+    rec[1, 0] = 4
+    words = records_to_words(rec, SyntheticDetokenizer())
+    assert words[0]["page"] == 3 and words[0]["box"] == [10, 20, 30, 40] and words[0]["line"] == -1
+    assert words[0]["tokens"] == [100, 207, 2] and words[0]["text"].isupper()
+    assert words[0]["confidence"] == round(round(math.exp(-0.25), 6), 4)
+    assert words[1]["text"] == "" and words[1]["confidence"] == 0.0
+    assert [w["page"] for w in records_to_words(rec, SyntheticDetokenizer(), page=4)] == [4]
+
+
+def test_processors_refuse_cpu():
+    import torch
+    from marie_icr_b200.boxes import BoxProcessorCraftB200
+    from marie_icr_b200.document import TrOcrProcessorB200
+    with pytest.raises(RuntimeError):
+        BoxProcessorCraftB200(cuda=False)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no cuda devices"):
+            TrOcrProcessorB200(cuda=True)

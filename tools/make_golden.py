@@ -74,3 +74,42 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_result_golden():
+    """OcrProcessor.recognize result assembly (marie/document/ocr_processor.py:87-267) with canned recogniser output."""
+    Ref = ref_loader.load_ocr_processor()
+    rng = np.random.default_rng(41)
+    n = 31
+    boxes = np.stack([rng.integers(0, 900, n), rng.integers(0, 500, n), rng.integers(5, 100, n),
+                      rng.integers(5, 40, n)], 1).tolist()
+    lines = rng.integers(-1, 6, n).tolist()
+    canned = [{"confidence": float(rng.random()), "id": f"img-{k}", "text": f"W{k}"} for k in range(n)]
+
+    class P(Ref):
+        def __init__(self):
+            pass
+
+        def is_available(self):
+            return True
+
+        def recognize_from_fragments(self, frags, **kw):
+            return canned
+
+    img = np.zeros((600, 1000, 3), np.uint8)
+    res, _ = P().recognize("golden", "key", img, boxes, [img[:2, :2]] * n, lines)
+    with open(os.path.join(OUT, "ocr_result.json"), "w") as f:
+        json.dump(dict(boxes=boxes, lines=lines, canned=canned, result=jsonable(res)), f)
+
+
+def jsonable(r):
+    def cv(v):
+        if isinstance(v, (str, int, float)):
+            return v
+        return np.asarray(v).tolist()
+    return {"meta": r["meta"], "words": [{k: cv(v) for k, v in w.items()} for w in r["words"]],
+            "lines": [{k: cv(v) for k, v in l.items()} for l in r["lines"]]}
+
+
+if __name__ == "__main__":
+    make_result_golden()
