@@ -226,6 +226,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
+    from marie_icr_b200 import ops as _ops
+    st0 = _ops.trocr_stats(local_rank)
     ctx.profile(True)
     pipe.timer.reset(True)
     ms, (rec, counts) = timed(step_device, args.steps)
@@ -234,6 +236,8 @@ def run_ours(args, rank, world, local_rank):
     prof = ctx.profile_read()
     ctx.profile(False)
     launches = ctx.launches - launches0
+    st1 = _ops.trocr_stats(local_rank)
+    dec_steps = (st1["decode_steps"] - st0["decode_steps"]) / max(1, st1["decode_calls"] - st0["decode_calls"])
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, (rec_h, _) = timed(step_host, max(1, min(args.steps, 2)))
     e2e_steps = max(1, min(args.steps, 2))
@@ -275,7 +279,7 @@ def run_ours(args, rank, world, local_rank):
                    "pages_per_step": pages_step, "page": "2550x3300x3 u8", "crops_per_step": crops_step, "beam": args.beam,
                    "max_len_b": MAX_LEN_B, "trocr": "base (ViT 768/12 + decoder 1024/12, vocab 50265)",
                    "weights": "seeded synthetic (glyph-path CRAFT, EOS-calibrated TrOCR)", "parallelism": f"dp{world}",
-                   "l2": "inputs larger than L2 (1.6 GB of pages per step)"},
+                   "l2": "inputs larger than L2 (1.6 GB of pages per step)", "decoder_steps_per_chunk": dec_steps},
         "crops_per_s": crops_step / sec_step,
         "e2e": {"value": pages_step / sec_e2e, "unit": "pages/s", "h2d_bytes_per_step": int(pages_host.numel()),
                 "d2h_bytes_per_step": int(rec_h.numel() * 4 / max(world, 1)), "crops_per_s": crops_step / sec_e2e},

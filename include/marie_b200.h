@@ -155,6 +155,8 @@ int mb_find_line_numbers(mb_ctx* ctx, const int32_t* lines_host, int n_lines, co
  * mb_trocr_recognize: encode + decode over n crops in chunks (0 = default 512 crops per chunk). */
 int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes);
 int mb_trocr_dims(mb_ctx* ctx, int* dims4_host);
+/* cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded} */
+int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3_host);
 int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void* enc_out_dev, void* stream);
 int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int beam, int max_len_b, int32_t* tokens_out_dev,
                     int out_ld, int32_t* lengths_dev, float* scores_dev, int* steps_run, void* stream);

@@ -24,11 +24,14 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;          // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int STAGE_TILE_BYTES = 32 * 32 * 4;   // per epilogue warp: 32 rows x 32 fp32 columns
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = (2 * 8 + 4) * 8 + 32;   // mbarriers + TMEM pointer, keeps the staging tiles 16 B aligned
 
 struct KParams {
     int n, h, w;
@@ -146,11 +149,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
+// exact-erf GELU (timm nn.GELU) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit
+// output rounding): one MUFU.RCP + one MUFU.EX2 + a 5-term Horner instead of erff's long branchy path, which made the
+// fc1 epilogue slower than the tile's MMAs.
 __device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 // ---------------------------------------------------------------- kernel
+template <bool F16> __device__ __forceinline__ float2 unpack2t(uint32_t v) { return unpack2(v, F16 ? 1 : 0); }
+template <bool F16> __device__ __forceinline__ uint32_t pack2t(float a, float b) { return pack2(a, b, F16 ? 1 : 0); }
+
+template <int ACT, int OUT, bool RES, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const KParams p) {
@@ -169,6 +186,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;
     uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    uint8_t* smem_stage = reinterpret_cast<uint8_t*>(bars) + BAR_BYTES;      // epilogue staging tiles (16 B aligned)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -182,7 +200,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[i]), 4);   // one arrival per epilogue warp
+            mbar_init(smem_u32(&tmem_empty_bar[i]), EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -270,8 +288,20 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------ epilogue (4 warps, 128 rows)
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------ epilogue (8 warps)
+        // Warp e = warp-4 owns TMEM lane quarter (warp & 3) — the 32 tile rows it may read — and every second
+        // 32-column chunk.  A chunk goes TMEM -> registers (row per lane) -> bias/activation -> fp32 staging tile in
+        // shared memory (XOR-swizzled, conflict-free) -> read back with lanes running along the row, so the
+        // residual loads and the output stores are coalesced row segments instead of 32 scattered rows.
+        // The kernel is specialised on (ACT, OUT, RES, F16): a runtime-generic epilogue unrolled to ~280 KB of SASS
+        // and ran out of the instruction cache (ncu: stall_no_inst on every epilogue instruction).
+        const int ew = warp - 4;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        float* stage = reinterpret_cast<float*>(smem_stage + ew * STAGE_TILE_BYTES);
+        const int rr = lane >> 3, kk = lane & 7;  // read-back role: row offset within a group of 4, 16-byte chunk
+        const bool vec_out = (p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+        const bool vec_res = !RES || ((p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 7) == 0);
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -281,77 +311,90 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int rest = mt / p.w_tiles;
             const int hh = rest % p.h;
             const int nn = rest / p.h;
-            const int wcol = wt * BLOCK_M + q * 32 + lane;
-            const bool valid = wcol < p.w;
-            const long long pix = ((long long)nn * p.h + hh) * p.w + wcol;
+            const int row0 = wt * BLOCK_M + q * 32;                 // first tile row (pixel) of this warp
+            const long long pix0 = ((long long)nn * p.h + hh) * p.w + row0;
+            const int rows_valid = min(32, p.w - row0);             // may be <= 0 for a ragged last tile
 
             mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-            for (int c = 0; c < p.block_n; c += 32) {
+            const int n_chunks = (p.block_n + 31) >> 5;
+#pragma unroll 1
+            for (int ci = half; ci < n_chunks; ci += 2) {
+                const int c = ci * 32;
+                const int n0 = nt * p.block_n + c;
+                if (n0 >= p.n_out || rows_valid <= 0) continue;      // warp-uniform
+                const int ncols = min(32, p.n_out - n0);
+                const bool fast = ncols == 32 && rows_valid == 32 && vec_out && vec_res;   // warp-uniform
+                uint2 rres[8];
+                if (RES && fast) {   // residual prefetch in the read-back layout (4 x 16-bit per lane and row group)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        rres[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + (pix0 + i * 4 + rr) * p.res_ld + n0 + kk * 4));
+                }
                 uint32_t v[32];
-                __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the masked stores
                 tmem_ld32(taddr + (uint32_t)c, v);
                 tmem_wait_ld();
-                const int n0 = nt * p.block_n + c;
-                if (!valid || n0 >= p.n_out) continue;
-                const int ncols = min(32, p.n_out - n0);
                 float f[32];
+                if (p.bias != nullptr) {
+                    const float bl = (lane < ncols) ? __ldg(p.bias + n0 + lane) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (p.bias != nullptr && j < ncols) x += __ldg(p.bias + n0 + j);
-                    if (p.act == MB_ACT_RELU) x = fmaxf(x, 0.0f);
-                    else if (p.act == MB_ACT_GELU) x = gelu_erf(x);
-                    f[j] = x;
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 }
-                if (p.residual != nullptr) {
-                    const bf16* r = p.residual + pix * p.res_ld + n0;
-                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+                if (ACT == MB_ACT_RELU) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + j4);
-                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                } else if (ACT == MB_ACT_GELU) {
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 rr = unpack2(rw[t], p.f16);
-                                f[j4 * 8 + 2 * t] += rr.x;
-                                f[j4 * 8 + 2 * t + 1] += rr.y;
-                            }
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                }
+                if (OUT == MB_OUT_F32_PLANAR) {   // channel planes, pixel-contiguous: already coalesced across lanes
+                    if (lane < rows_valid) {
+                        float* o = reinterpret_cast<float*>(p.out) + pix0 + lane;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) o[(long long)(n0 + j) * p.out_plane] = f[j];
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    *reinterpret_cast<float4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+                        make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                __syncwarp();
+                if (fast) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + rr;
+                        float4 x = *reinterpret_cast<const float4*>(stage + r * 32 + ((kk ^ (r & 7)) << 2));
+                        if (RES) {
+                            const float2 r0 = unpack2t<F16>(rres[i].x), r1 = unpack2t<F16>(rres[i].y);
+                            x.x += r0.x; x.y += r0.y; x.z += r1.x; x.w += r1.y;
                         }
-                    } else {
-                        for (int j = 0; j < ncols; ++j) f[j] += load16(r + j, p.f16);
+                        if (OUT == MB_OUT_BF16)
+                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) =
+                                make_uint2(pack2t<F16>(x.x, x.y), pack2t<F16>(x.z, x.w));
+                        else
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) = x;
                     }
-                }
-                if (p.out_mode == MB_OUT_BF16) {
-                    bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.out_ld + n0;
-                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint4 ov;
-                            ov.x = pack2(f[j4 * 8 + 0], f[j4 * 8 + 1], p.f16);
-                            ov.y = pack2(f[j4 * 8 + 2], f[j4 * 8 + 3], p.f16);
-                            ov.z = pack2(f[j4 * 8 + 4], f[j4 * 8 + 5], p.f16);
-                            ov.w = pack2(f[j4 * 8 + 6], f[j4 * 8 + 7], p.f16);
-                            reinterpret_cast<uint4*>(o)[j4] = ov;
+                } else {
+                    // ragged chunk (last rows / last columns / unaligned pitch): one element per lane and row
+#pragma unroll 1
+                    for (int r = 0; r < rows_valid; ++r) {
+                        if (lane < ncols) {
+                            float x = stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+                            if (RES) x += load16(p.residual + (pix0 + r) * p.res_ld + n0 + lane, F16);
+                            if (OUT == MB_OUT_BF16)
+                                store16(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + lane, x, F16);
+                            else
+                                reinterpret_cast<float*>(p.out)[(pix0 + r) * p.out_ld + n0 + lane] = x;
                         }
-                    } else {
-                        for (int j = 0; j < ncols; ++j) store16(o + j, f[j], p.f16);
                     }
-                } else if (p.out_mode == MB_OUT_F32) {
-                    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n0;
-                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)
-                            reinterpret_cast<float4*>(o)[j4] =
-                                make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-                    } else {
-                        for (int j = 0; j < ncols; ++j) o[j] = f[j];
-                    }
-                } else {   // MB_OUT_F32_PLANAR: channel planes, pixel-contiguous (coalesced across lanes)
-                    float* o = reinterpret_cast<float*>(p.out) + pix;
-                    for (int j = 0; j < ncols; ++j) o[(long long)(n0 + j) * p.out_plane] = f[j];
                 }
+                __syncwarp();
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -464,6 +507,11 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         else if (g.n_out > 16) block_n = 32;
         else block_n = 16;
     }
+    if (g.block_n == 0) {
+        // small problems (decoder steps): shrink the N tile until the grid covers the SMs
+        const long long m_tiles = (long long)g.n * g.h * mb_cdiv(g.w, BLOCK_M);
+        while (block_n > 64 && m_tiles * mb_cdiv(g.n_out, block_n) < ctx->num_sms) block_n >>= 1;
+    }
     MB_REQUIRE(ctx, block_n % 16 == 0 && block_n >= 16 && block_n <= 256, "tap_gemm: bad block_n %d", block_n);
 
     KParams p;
@@ -476,7 +524,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.block_n = block_n;
     p.n_out = g.n_out;
     const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
-    const int bar_bytes = (2 * MAX_STAGES + 4) * 8 + 16;
+    const int bar_bytes = BAR_BYTES + EPI_WARPS * STAGE_TILE_BYTES;
     int stages = (SMEM_LIMIT - 1024 - bar_bytes) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     p.stages = stages;
@@ -500,12 +548,23 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     if (rc) return rc;
 
     const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MB_CUDA(ctx, cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          SMEM_LIMIT));
-        attr_set = true;
-    }
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
+    KernelFn fn = nullptr;
+    const bool res = g.residual != nullptr;
+    const bool h = ctx->f16 != 0;
+#define MB_PICK(A, O, R)                                                                               \
+    if (g.act == (A) && g.out_mode == (O) && res == (R))                                               \
+        fn = h ? (KernelFn)tap_gemm_kernel<A, O, R, true> : (KernelFn)tap_gemm_kernel<A, O, R, false>;
+    MB_PICK(MB_ACT_NONE, MB_OUT_BF16, false) MB_PICK(MB_ACT_NONE, MB_OUT_BF16, true)
+    MB_PICK(MB_ACT_RELU, MB_OUT_BF16, false) MB_PICK(MB_ACT_RELU, MB_OUT_BF16, true)
+    MB_PICK(MB_ACT_GELU, MB_OUT_BF16, false) MB_PICK(MB_ACT_GELU, MB_OUT_BF16, true)
+    MB_PICK(MB_ACT_NONE, MB_OUT_F32, false) MB_PICK(MB_ACT_RELU, MB_OUT_F32, false)
+    MB_PICK(MB_ACT_NONE, MB_OUT_F32_PLANAR, false) MB_PICK(MB_ACT_RELU, MB_OUT_F32_PLANAR, false)
+#undef MB_PICK
+    if (!fn)
+        return mb_set_err(ctx, MB_ERR_ARG, "tap_gemm: unsupported epilogue (act %d, out_mode %d, residual %d)", g.act,
+                          g.out_mode, (int)res);
+    MB_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     const long long total = (long long)p.m_tiles * p.n_tiles;
     const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -514,7 +573,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         cudaEventCreate(&ev1);
         cudaEventRecord(ev0, stream);
     }
-    tap_gemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
+    fn<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
     if (ctx->profile) {
         cudaEventRecord(ev1, stream);
         ctx->prof_events.push_back(ev0);

@@ -49,6 +49,7 @@ struct TrocrModel {
     std::vector<DecLayer> dec;
     const bf16* embed = nullptr; const float* pe = nullptr; const bf16* out_w = nullptr;
     void* arena = nullptr; size_t arena_bytes = 0;
+    unsigned long long decode_calls = 0, decode_steps = 0, decode_rows = 0;
 };
 
 namespace {
@@ -908,6 +909,13 @@ extern "C" int mb_trocr_dims(mb_ctx* ctx, int* dims) {
     return 0;
 }
 
+// cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded}
+extern "C" int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3) {
+    if (!ctx || !ctx->trocr || !out3) return MB_ERR_STATE;
+    out3[0] = ctx->trocr->decode_calls; out3[1] = ctx->trocr->decode_steps; out3[2] = ctx->trocr->decode_rows;
+    return 0;
+}
+
 extern "C" int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void* enc_out_dev, void* stream) {
     if (!ctx) return MB_ERR_ARG;
     TrocrModel* m = ctx->trocr;
@@ -962,6 +970,7 @@ extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int 
         }
     }
     if (steps_run) *steps_run = step;
+    m->decode_calls++; m->decode_steps += step; m->decode_rows += (unsigned long long)n * beam;
     search_pick_kernel<<<mb_cdiv(n, 64), 64, 0, s>>>(w.st, n, beam, max_len, tokens_out_dev, out_ld, lengths_dev, scores_dev);
     MB_LAUNCH_CHECK(ctx);
     MB_CUDA(ctx, cudaStreamSynchronize(s));

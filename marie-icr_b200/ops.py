@@ -178,6 +178,12 @@ def trocr_dims(device=0):
     return dict(enc_dim=d[0], dec_dim=d[1], vocab=d[2], tokens=d[3])
 
 
+def trocr_stats(device=0):
+    d = (ctypes.c_ulonglong * 3)()
+    Context.get(device).call("mb_trocr_stats", d)
+    return dict(decode_calls=int(d[0]), decode_steps=int(d[1]), decode_rows=int(d[2]))
+
+
 def trocr_encode(patches):
     """patches [n*576, 768] 16-bit (pack_crops / pack_fragments layout=1) -> enc_out [n, 577, enc_dim]."""
     ctx = _ctx(patches)

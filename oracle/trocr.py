@@ -29,12 +29,14 @@ from synthetic.weights import (BOS, EOS, PAD, UNK, TrocrConfig, synth_trocr_stat
                                trocr_tiny)
 
 
-def calibrate_eos(sd, cfg, eos_step=6, samples=6, seed=0, margin=1.0, round_to=torch.float16, enc=None):
+def calibrate_eos(sd, cfg, eos_step=6, samples=6, seed=0, margin=2.0, round_to=torch.float16, enc=None, horizon=32):
     """A random-init decoder never emits EOS (1 chance in V per step), so every hypothesis would run to max_len=200.
-    Like the CRAFT 'calibrated head'  the EOS row of the output projection is set, in place, to the
-    direction that separates the decoder's hidden state at steps >= eos_step from earlier steps (measured on a few
+    Like the CRAFT 'calibrated head'  the EOS row of the output projection is fitted, in place, so that
+    its logit ramps through the level of the best competing logit at step eos_step (ridge regression on a few
     greedy roll-outs over the encoder states `enc` — pass real encoder outputs of a few sample crops; random
-    states are only a fallback), scaled so EOS wins the arg-max around step `eos_step`.  The same
+    states are only a fallback), scaled so EOS wins the arg-max around step `eos_step`.  The roll-out runs `horizon` steps past eos_step so the
+    direction is dominated by the slowly varying position components and EOS keeps winning at every later step
+    (no straggler hypotheses that run to max_len).  The same
     weights go to the oracle and the device, so parity is unaffected.  Returns the scale used."""
     g = torch.Generator().manual_seed(seed + 77)
     if enc is None:
@@ -46,19 +48,25 @@ def calibrate_eos(sd, cfg, eos_step=6, samples=6, seed=0, margin=1.0, round_to=t
     tok = torch.full((samples,), EOS, dtype=torch.long)
     hs = []
     with torch.no_grad():
-        for t in range(eos_step + 3):
+        for t in range(eos_step + horizon):
             logits, h = st.step(tok, t, return_hidden=True)
             hs.append(h)
             logits[:, PAD] = -math.inf
             logits[:, EOS] = -math.inf
             tok = logits.argmax(-1)
         hs = torch.stack(hs)                                   # [T, S, H]
-        m = hs.mean(1)
-        v = m[eos_step:].mean(0) - m[:eos_step].mean(0)
-        v = v / v.norm()
-        other = (hs[eos_step] @ W.t()).max(-1).values.mean()
-        alpha = float((other + margin) / (hs[eos_step] @ v).mean())
-        W[EOS] = (alpha * v).to(round_to).float() if round_to is not None else alpha * v
+        T, S, H = hs.shape
+        other = (hs @ W.t()).max(-1).values                    # [T, S] best competing logit
+        # ridge regression of an EOS logit that ramps through the competitors' level at step eos_step:
+        # target = other + clip(slope * (t - eos_step + 0.5), -6, 6)
+        ramp = (margin * (torch.arange(T, dtype=torch.float) - eos_step + 0.5)).clamp(-6, 6)
+        y = (other + ramp[:, None]).reshape(-1).double()
+        Hm = hs.reshape(T * S, H).double()
+        G = Hm @ Hm.t()
+        lam = 1e-2 * float(G.diagonal().mean())
+        w = Hm.t() @ torch.linalg.solve(G + lam * torch.eye(T * S, dtype=torch.double), y)
+        W[EOS] = w.float().to(round_to).float() if round_to is not None else w.float()
+        alpha = float(w.norm())
     return alpha
 
 

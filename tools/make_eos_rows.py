@@ -13,8 +13,18 @@ from oracle import resample, trocr  # noqa: E402
 from synthetic import pages, weights  # noqa: E402
 
 
-def calib_fragments(page, k=4):
-    return [page[145 + 70 * j:205 + 70 * j, 150:370].copy() for j in range(k)]
+def calib_fragments(page, k=8):
+    return [page[145 + 70 * j:205 + 70 * j, 150 + 90 * (j % 3):370 + 140 * (j % 4)].copy() for j in range(k)]
+
+
+def test_fragments(page, k=12):
+    """Other crops (different words / sizes) to check that every hypothesis terminates early."""
+    rng = np.random.default_rng(0)
+    out = []
+    for _ in range(k):
+        y, x = int(rng.integers(150, 2900)), int(rng.integers(150, 2000))
+        out.append(page[y:y + int(rng.integers(40, 80)), x:x + int(rng.integers(80, 320))].copy())
+    return out
 
 
 def main():
@@ -25,11 +35,12 @@ def main():
         sd = weights.synth_trocr_state(cfg, seed, round_to=None)
         with torch.no_grad():
             enc = trocr.encoder_forward(sd, cfg, cal)
-            alpha = trocr.calibrate_eos(sd, cfg, eos_step=step, round_to=None, enc=enc)
-            hyps = trocr.generate(sd, cfg, enc, beam=1, max_len_b=40)
+            alpha = trocr.calibrate_eos(sd, cfg, eos_step=step, round_to=None, enc=enc, margin=1.0)
+            more = torch.stack([torch.from_numpy(resample.fragment_to_input(f)) for f in test_fragments(page)])
+            hyps = trocr.generate(sd, cfg, trocr.encoder_forward(sd, cfg, more), beam=1, max_len_b=200)
         row = sd["decoder.output_projection.weight"][weights.EOS].numpy().astype(np.float32)
         np.save(os.path.join(ROOT, "synthetic", f"eos_row_{name}.npy"), row)
-        print(name, "alpha", alpha, "greedy lengths on the calibration crops:", [len(h[0]["tokens"]) for h in hyps])
+        print(name, "alpha", alpha, "greedy lengths on 12 other crops:", [len(h[0]["tokens"]) for h in hyps])
 
 
 if __name__ == "__main__":
