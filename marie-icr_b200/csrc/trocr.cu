@@ -139,7 +139,7 @@ __global__ void assemble_tokens_kernel(const bf16* __restrict__ patch_out, const
 }
 
 // ------------------------------------------------------------------------------------------------ encoder attention
-// softmax(Q K^T / sqrt(64)) V for T tokens per image, flash-style (online softmax), one CTA = 64 query rows of one
+// softmax(Q K^T * scale) V, flash-style (online softmax), one CTA = 64 query rows of one
 // (image, head); 4 warps x 16 rows; K/V streamed in 64-key tiles through double-buffered cp.async.  Tensor math is
 // mma.sync m16n8k16 (legacy HMMA path) — 11% of the encoder FLOPs; the tcgen05 version is future work.
 // qkv: [n*T, 3*D] (q | k | v, head h at columns h*64); out: [n*T, D].
@@ -172,32 +172,48 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
 // tile [64 rows][64 x 16-bit] with the 16-byte chunk index XOR-swizzled by (row & 7)
 __device__ __forceinline__ int swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+// Generic form: batch item b has Tq query rows (q + (b*Tq + t)*q_ld + head*64) and Tk key/value rows
+// (k|v + (b*Tk + t)*kv_ld + head*64); out + (b*Tq + t)*o_ld + head*64.  The encoder uses it with q/k/v inside one
+// qkv buffer (Tq = Tk = 577); the decoder's cross-attention uses Tq = beam (<= 8) query rows per crop against the
+// crop's 577 cached encoder keys/values, which turns the step into a streaming read of the K/V cache with cp.async
+// keeping ~32 KB in flight per CTA (HBM-bound: 2.36 MB per crop and layer).
+constexpr int ATT_STAGES = 3;                       // K/V tiles in flight per CTA (cp.async groups)
+constexpr int ATT_SMEM = (1 + 2 * ATT_STAGES) * 64 * 128;   // Q tile + STAGES x (K tile + V tile) = 56 KB
 template <bool F16>
-__global__ void __launch_bounds__(128) enc_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T,
-                                                            int D, float scale_log2e) {
-    __shared__ __align__(128) unsigned char sQ[64 * 128];
-    __shared__ __align__(128) unsigned char sK[2][64 * 128];
-    __shared__ __align__(128) unsigned char sV[2][64 * 128];
+__global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restrict__ qptr, long long q_ld,
+                                                        const bf16* __restrict__ kptr, const bf16* __restrict__ vptr,
+                                                        long long kv_ld, bf16* __restrict__ out, long long o_ld, int Tq,
+                                                        int T, float scale_log2e) {
+    extern __shared__ __align__(128) unsigned char att_smem[];
+    unsigned char* sQ = att_smem;
+    unsigned char* sKbase = att_smem + 64 * 128;
+    unsigned char* sVbase = sKbase + ATT_STAGES * 64 * 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * 64, head = blockIdx.y;
     const long long img = blockIdx.z;
-    const long long ld = 3LL * D;
-    const bf16* base = qkv + img * T * ld + head * DH;
+    const bf16* qbase = qptr + img * Tq * q_ld + head * DH;
+    const bf16* kbase = kptr + img * T * kv_ld + head * DH;
+    const bf16* vbase = vptr + img * T * kv_ld + head * DH;
     const int n_tiles = (T + 63) >> 6;
 
-    auto load_tile = [&](unsigned char* dst, const bf16* src, int row0) {
+    auto load_tile = [&](unsigned char* dst, const bf16* src, long long ld, int row0, int limit) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int idx = tid + 128 * i;            // 512 chunks of 16 B
             const int r = idx >> 3, c = idx & 7;
-            const bool ok = row0 + r < T;
+            const bool ok = row0 + r < limit;
             cp_async16(smem_addr(dst + swz(r, c)), src + (long long)(ok ? row0 + r : 0) * ld + c * 8, ok);
         }
     };
-    load_tile(sQ, base, q0);
-    load_tile(sK[0], base + D, 0);
-    load_tile(sV[0], base + 2 * D, 0);
-    cp_async_commit();
+    load_tile(sQ, qbase, q_ld, q0, Tq);
+#pragma unroll
+    for (int st = 0; st < ATT_STAGES - 1; ++st) {     // prologue: tiles 0 .. STAGES-2 (one commit group per tile)
+        if (st < n_tiles) {
+            load_tile(sKbase + st * 64 * 128, kbase, kv_ld, st * 64, T);
+            load_tile(sVbase + st * 64 * 128, vbase, kv_ld, st * 64, T);
+        }
+        cp_async_commit();
+    }
 
     uint32_t aq[4][4];
     float o[8][4];
@@ -206,15 +222,19 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const bf16* __restri
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
     for (int j = 0; j < n_tiles; ++j) {
-        const int buf = j & 1;
-        if (j + 1 < n_tiles) {
-            load_tile(sK[buf ^ 1], base + D, (j + 1) * 64);
-            load_tile(sV[buf ^ 1], base + 2 * D, (j + 1) * 64);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        const int buf = j % ATT_STAGES;
+        unsigned char* sKb = sKbase + buf * 64 * 128;
+        unsigned char* sVb = sVbase + buf * 64 * 128;
+        {   // prefetch tile j + STAGES-1 into the buffer freed by tile j-1 (all warps passed the trailing barrier)
+            const int jn = j + ATT_STAGES - 1;
+            if (jn < n_tiles) {
+                const int bn = jn % ATT_STAGES;
+                load_tile(sKbase + bn * 64 * 128, kbase, kv_ld, jn * 64, T);
+                load_tile(sVbase + bn * 64 * 128, vbase, kv_ld, jn * 64, T);
+            }
+            cp_async_commit();                         // always commit: keeps the group count uniform
         }
+        cp_async_wait<ATT_STAGES - 1>();               // tile j (and Q) have landed
         __syncthreads();
         if (j == 0) {
 #pragma unroll
@@ -234,7 +254,7 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const bf16* __restri
                 uint32_t b0, b1, b2, b3;
                 const int r = nb * 8 + (lane & 7);
                 const int c = kp * 4 + (lane >> 3);
-                ldsm_x4(smem_addr(sK[buf] + swz(r, c)), b0, b1, b2, b3);
+                ldsm_x4(smem_addr(sKb + swz(r, c)), b0, b1, b2, b3);
                 mma16816<F16>(s[nb], aq[kp * 2], b0, b1);
                 mma16816<F16>(s[nb], aq[kp * 2 + 1], b2, b3);
             }
@@ -278,12 +298,12 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const bf16* __restri
                 uint32_t b0, b1, b2, b3;
                 const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = dp * 2 + (lane >> 4);
-                ldsm_x4_t(smem_addr(sV[buf] + swz(r, c)), b0, b1, b2, b3);
+                ldsm_x4_t(smem_addr(sVb + swz(r, c)), b0, b1, b2, b3);
                 mma16816<F16>(o[dp * 2], ap[kk], b0, b1);
                 mma16816<F16>(o[dp * 2 + 1], ap[kk], b2, b3);
             }
         }
-        __syncthreads();   // all warps done with sK/sV[buf] before the next prefetch overwrites it
+        __syncthreads();   // all warps done with this K/V buffer before a later prefetch overwrites it
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -301,8 +321,8 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const bf16* __restri
     for (int i = 0; i < 4; ++i) {
         const int idx = lane + 32 * i;                // 128 chunks per warp (16 rows x 8)
         const int r = warp * 16 + (idx >> 3), c = idx & 7;
-        if (q0 + r < T)
-            *reinterpret_cast<uint4*>(out + (img * T + q0 + r) * D + head * DH + c * 8) =
+        if (q0 + r < Tq)
+            *reinterpret_cast<uint4*>(out + (img * Tq + q0 + r) * o_ld + head * DH + c * 8) =
                 *reinterpret_cast<const uint4*>(sQ + swz(r, c));
     }
 }
@@ -355,90 +375,6 @@ __global__ void __launch_bounds__(32) dec_self_attn_kernel(const bf16* __restric
         m = mn;
     }
     *reinterpret_cast<uint32_t*>(out + (long long)r * H + col) = pack2(ox / l, oy / l, f16);
-}
-
-// Cross-attention of the new token of every beam of one crop over the crop's T encoder states.
-// q: [R, H] (pre-scaled); kv: [n*T, 2H] (k | v) of this layer; out [R, H].  grid (heads, n_crops), 128 threads:
-// scores for all keys and beams in shared memory, softmax per beam, then P.V with lanes across the head dim.
-constexpr int XA_THREADS = 128;
-__global__ void __launch_bounds__(XA_THREADS) dec_cross_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
-                                                                    bf16* __restrict__ out, int T, int H, int beam,
-                                                                    int f16) {
-    extern __shared__ float sp[];                   // [beam][T] scores, then [4 warps][beam][64] partial outputs
-    __shared__ float sq[MAX_BEAM][DH];
-    __shared__ float smax[MAX_BEAM], ssum[MAX_BEAM];
-    const int head = blockIdx.x, crop = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long ld = 2LL * H;
-    const bf16* kbase = kv + (long long)crop * T * ld + head * DH;
-    const bf16* vbase = kbase + H;
-    for (int i = tid; i < beam * DH; i += XA_THREADS) {
-        const int b = i / DH, d = i % DH;
-        sq[b][d] = load16(q + ((long long)crop * beam + b) * H + head * DH + d, f16);
-    }
-    __syncthreads();
-    // scores: one key per thread iteration, 8 x 16 B loads of the key row
-    for (int t = tid; t < T; t += XA_THREADS) {
-        float acc[MAX_BEAM];
-#pragma unroll
-        for (int b = 0; b < MAX_BEAM; ++b) acc[b] = 0.f;
-        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)t * ld);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldg(kr + c);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = unpack2(w[k], f16);
-#pragma unroll
-                for (int b = 0; b < MAX_BEAM; ++b)
-                    if (b < beam) acc[b] += sq[b][c * 8 + 2 * k] * f.x + sq[b][c * 8 + 2 * k + 1] * f.y;
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < MAX_BEAM; ++b)
-            if (b < beam) sp[b * T + t] = acc[b];
-    }
-    __syncthreads();
-    // softmax statistics: warp w handles beams w, w+4
-    for (int b = warp; b < beam; b += 4) {
-        float mx = -INFINITY;
-        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sp[b * T + t]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int t = lane; t < T; t += 32) {
-            const float p = __expf(sp[b * T + t] - mx);
-            sp[b * T + t] = p;
-            sum += p;
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) { smax[b] = mx; ssum[b] = sum; }
-    }
-    __syncthreads();
-    // P.V: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
-    float ax[MAX_BEAM], ay[MAX_BEAM];
-#pragma unroll
-    for (int b = 0; b < MAX_BEAM; ++b) ax[b] = ay[b] = 0.f;
-    for (int t = warp; t < T; t += 4) {
-        const float2 v = unpack2(__ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)t * ld) + lane), f16);
-#pragma unroll
-        for (int b = 0; b < MAX_BEAM; ++b)
-            if (b < beam) { const float p = sp[b * T + t]; ax[b] += p * v.x; ay[b] += p * v.y; }
-    }
-    __syncthreads();
-    float* part = sp;                                // reuse: [4][beam][64]
-#pragma unroll
-    for (int b = 0; b < MAX_BEAM; ++b)
-        if (b < beam) {
-            part[(warp * beam + b) * DH + lane * 2] = ax[b];
-            part[(warp * beam + b) * DH + lane * 2 + 1] = ay[b];
-        }
-    __syncthreads();
-    for (int i = tid; i < beam * DH; i += XA_THREADS) {
-        const int b = i / DH, d = i % DH;
-        const float s = part[(0 * beam + b) * DH + d] + part[(1 * beam + b) * DH + d] + part[(2 * beam + b) * DH + d] +
-                        part[(3 * beam + b) * DH + d];
-        store16(out + ((long long)crop * beam + b) * H + head * DH + d, s / ssum[b], f16);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ search
@@ -684,6 +620,17 @@ int ensure_arena(mb_ctx* ctx, TrocrModel* m, size_t bytes) {
     return 0;
 }
 
+int attention_setup(mb_ctx* ctx) {
+    static bool done = false;
+    if (done) return 0;
+    MB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    MB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    MB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    done = true;
+    return 0;
+}
+
 int gemm(mb_ctx* ctx, const bf16* a, int K, const bf16* w, int rows_w, long long M, int N, const float* bias, int act,
          const bf16* residual, void* out, int out_mode, cudaStream_t s) {
     TapGemm g;
@@ -731,8 +678,9 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
         RC(gemm(ctx, y, D, L.qkv_w, 3 * D, M, 3 * D, nullptr, MB_ACT_NONE, nullptr, big, MB_OUT_BF16, s));
         {
             dim3 grid((T + 63) / 64, m->enc_heads, n);
-            if (ctx->f16) enc_attention_kernel<true><<<grid, 128, 0, s>>>(big, y, T, D, scale_log2e);
-            else enc_attention_kernel<false><<<grid, 128, 0, s>>>(big, y, T, D, scale_log2e);
+            RC(attention_setup(ctx));
+            if (ctx->f16) attention_kernel<true><<<grid, 128, ATT_SMEM, s>>>(big, 3LL * D, big + D, big + 2 * D, 3LL * D, y, D, T, T, scale_log2e);
+            else attention_kernel<false><<<grid, 128, ATT_SMEM, s>>>(big, 3LL * D, big + D, big + 2 * D, 3LL * D, y, D, T, T, scale_log2e);
             MB_LAUNCH_CHECK(ctx);
         }
         RC(gemm(ctx, y, D, L.proj_w, D, M, D, L.proj_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
@@ -799,9 +747,12 @@ int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, int n, int beam, int s
         RC(layernorm(ctx, w.tmp, w.x, L.ln1_w, L.ln1_b, R, H, 1e-5f, s));
         RC(gemm(ctx, w.x, H, L.cq_w, H, R, H, L.cq_b, MB_ACT_NONE, nullptr, w.qkv, MB_OUT_BF16, s));
         {
-            const size_t smem = (size_t)beam * (T > 4 * DH ? T : 4 * DH) * sizeof(float);
-            dec_cross_attn_kernel<<<dim3(m->dec_heads, n), XA_THREADS, smem, s>>>(
-                w.qkv, w.cross_kv + (size_t)l * n * T * 2 * H, w.att, T, H, beam, ctx->f16);
+            // all beams of a crop share one pass over the crop's cached K/V (q is pre-scaled: weights carry d^-0.5)
+            const bf16* kvl = w.cross_kv + (size_t)l * n * T * 2 * H;
+            dim3 grid(1, m->dec_heads, n);
+            RC(attention_setup(ctx));
+            if (ctx->f16) attention_kernel<true><<<grid, 128, ATT_SMEM, s>>>(w.qkv, H, kvl, kvl + H, 2LL * H, w.att, H, beam, T, 1.4426950408889634f);
+            else attention_kernel<false><<<grid, 128, ATT_SMEM, s>>>(w.qkv, H, kvl, kvl + H, 2LL * H, w.att, H, beam, T, 1.4426950408889634f);
             MB_LAUNCH_CHECK(ctx);
         }
         RC(gemm(ctx, w.att, H, L.cout_w, H, R, H, L.cout_b, MB_ACT_NONE, w.x, w.tmp, MB_OUT_BF16, s));
