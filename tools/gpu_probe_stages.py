@@ -59,10 +59,15 @@ def main():
         print(f"encoder n={nn}: {t / nn * 1e3:.1f} us/crop ({111e9 * nn / (t * 1e-3) / 1e12:.0f} TFLOP/s)")
     enc = ops.trocr_encode(patches[: min(n, 512) * 576])
     for beam in (1, 5):
-        torch.cuda.synchronize(); t0 = time.time()
-        toks, lens, sc, steps = ops.trocr_decode(enc, beam=beam, max_len_b=8)
-        torch.cuda.synchronize(); dtm = (time.time() - t0) * 1e3
-        print(f"decode beam={beam} n={enc.shape[0]}: {dtm:.1f} ms for {steps} steps = {dtm / steps:.2f} ms/step")
+        ops.trocr_decode(enc, beam=beam, max_len_b=8)          # warm-up: workspace allocation
+        res = {}
+        for ml in (2, 8):
+            torch.cuda.synchronize(); t0 = time.time()
+            toks, lens, sc, steps = ops.trocr_decode(enc, beam=beam, max_len_b=ml)
+            torch.cuda.synchronize(); res[ml] = ((time.time() - t0) * 1e3, steps)
+        per_step = (res[8][0] - res[2][0]) / (res[8][1] - res[2][1])
+        print(f"decode beam={beam} n={enc.shape[0]}: {res[8][0]:.1f} ms for {res[8][1]} steps; {per_step:.2f} ms/step, "
+              f"prepare (cross K/V) {res[2][0] - per_step * res[2][1]:.1f} ms")
     print("launches", ctx.launches)
 
 
