@@ -115,15 +115,18 @@ struct BoxSmem {
 __global__ void __launch_bounds__(128)
 box_extract_kernel(const int* __restrict__ labels, const float* __restrict__ text, const BoxPlan* __restrict__ plans,
                    const int* __restrict__ n_boxes, float* __restrict__ det, float* __restrict__ adj,
-                   int* __restrict__ rects, int* __restrict__ overflow, int max_boxes, int img_h, int img_w,
-                   float low_text, const double* __restrict__ ratios, const int* __restrict__ page_hw) {
+                   int* __restrict__ rects, int* __restrict__ overflow, int n_img, int max_boxes, int img_h,
+                   int img_w, float low_text, const double* __restrict__ ratios, const int* __restrict__ page_hw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BoxSmem* sm = reinterpret_cast<BoxSmem*>(smem_raw);
-    const int img = blockIdx.y;
-    const int b = blockIdx.x;
-    if (b >= n_boxes[img]) return;
-    const BoxPlan p = plans[(long long)img * max_boxes + b];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // persistent CTAs stride over the (image, slot) pairs; empty slots cost one compare
+    for (int id = blockIdx.x; id < n_img * max_boxes; id += gridDim.x) {
+    const int img = id / max_boxes;
+    const int b = id - img * max_boxes;
+    if (b >= n_boxes[img]) continue;
+    __syncthreads();                 // the previous box's single-thread phase is done with the shared rows
+    const BoxPlan p = plans[(long long)img * max_boxes + b];
     const int* lab = labels + (long long)img * img_h * img_w;
     const float* txt = text + (long long)img * img_h * img_w;
     for (int r = wid; r < p.h; r += nw) {
@@ -156,6 +159,7 @@ box_extract_kernel(const int* __restrict__ labels, const float* __restrict__ tex
         mb_adjust_and_rect(box, rw, rh, pw, ph, a, rect);
         for (int i = 0; i < 8; ++i) { det[o * 8 + i] = box[i]; adj[o * 8 + i] = a[i]; }
         for (int i = 0; i < 4; ++i) rects[o * 4 + i] = rect[i];
+    }
     }
 }
 
@@ -204,10 +208,11 @@ extern "C" int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* li
                                           (int)sizeof(BoxSmem)));
         attr_set = true;
     }
-    dim3 grid(max_boxes, n_img);
+    const long long slots = (long long)n_img * max_boxes;
+    const int grid = (int)(slots < (long long)ctx->num_sms * 8 ? slots : (long long)ctx->num_sms * 8);
     box_extract_kernel<<<grid, 128, sizeof(BoxSmem), stream>>>(labels_dev, text_dev, plans, n_boxes_dev, det_dev,
-                                                               adj_dev, rects_dev, ovf, max_boxes, h, w, low_text,
-                                                               ratios_dev, page_hw_dev);
+                                                               adj_dev, rects_dev, ovf, n_img, max_boxes, h, w,
+                                                               low_text, ratios_dev, page_hw_dev);
     MB_LAUNCH_CHECK(ctx);
     int host_ovf = 0;
     MB_CUDA(ctx, cudaMemcpyAsync(&host_ovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, stream));

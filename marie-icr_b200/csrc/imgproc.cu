@@ -74,9 +74,13 @@ constexpr int OUT = 384;
 constexpr int PREC_BITS = 32 - 8 - 2;
 constexpr int TILE_ROWS = 16;           // output rows per CTA (= one row of 16x16 patches)
 constexpr int K9_THREADS = 384;
-constexpr int K9_SMEM_BYTES = 200 * 1024;
+constexpr int K9_SMEM_BYTES = 200 * 1024;   // large-crop launch (1 CTA / SM)
+constexpr int K9_SMEM_SMALL = 44 * 1024;    // common case: 5 CTAs / SM
 
 struct CropDesc { const uint8_t* base; int pitch; int w; int h; };
+
+// worst-case dynamic shared memory a crop needs in crop_resize_kernel (tables + the widest band of source rows)
+__host__ __device__ inline size_t k9_smem_need(int w, int h);
 
 __device__ __forceinline__ double bicubic(double x) {
     const double a = -0.5;
@@ -125,7 +129,7 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 // [N*576, 768] with k = c*256 + py*16 + px (the A operand of the ViT patch-embedding GEMM).
 __global__ void __launch_bounds__(K9_THREADS)
 crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, int layout, int* __restrict__ err,
-                   int f16) {
+                   int f16, int smem_limit, int small_only) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ float lut[256];
     __shared__ int s_r0, s_r1;
@@ -133,11 +137,15 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
     const int tile = blockIdx.x;
     const int w = cd.w, h = cd.h;
     if (w <= 0 || h <= 0) return;
+    // two launches share this kernel: the common one with a small shared-memory budget (5 CTAs/SM) takes the crops
+    // that fit it, the second one (200 KB, 1 CTA/SM) takes only the large ones
+    const bool fits_small = k9_smem_need(w, h) <= (size_t)K9_SMEM_SMALL;
+    if (small_only != (int)fits_small) return;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (((float)i / 255.0f) - 0.5f) / 0.5f;
 
     const int ks_v = pil_ksize(h), ks_h = pil_ksize(w);
     const size_t table_bytes = (size_t)(TILE_ROWS * 2 + TILE_ROWS * ks_v + OUT * 2 + OUT * ks_h) * 4;
-    if (table_bytes + (size_t)(ks_v + 2) * OUT * 3 > K9_SMEM_BYTES) {   // uniform across the CTA
+    if (table_bytes + (size_t)(ks_v + 2) * OUT * 3 > (size_t)smem_limit) {   // uniform across the CTA
         if (threadIdx.x == 0) atomicExch(err, 1);
         return;
     }
@@ -165,7 +173,7 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
     }
     __syncthreads();
     const int r0 = s_r0, nrows = s_r1 - s_r0;
-    if (table_bytes + (size_t)nrows * OUT * 3 > K9_SMEM_BYTES) {
+    if (table_bytes + (size_t)nrows * OUT * 3 > (size_t)smem_limit) {
         if (threadIdx.x == 0) atomicExch(err, 1);
         return;
     }
@@ -187,35 +195,58 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
         t[0] = clip8(a0); t[1] = clip8(a1); t[2] = clip8(a2);
     }
     __syncthreads();
-    // vertical pass + BGR->RGB + normalise + pack
-    for (int idx = threadIdx.x; idx < TILE_ROWS * OUT; idx += blockDim.x) {
-        const int ty = idx / OUT, xx = idx - ty * OUT;
+    // vertical pass + BGR->RGB + normalise + pack: 8 consecutive output pixels per thread (24 B of the u8 band per
+    // tap, three 16-byte stores)
+    for (int item = threadIdx.x; item < TILE_ROWS * (OUT / 8); item += blockDim.x) {
+        const int ty = item / (OUT / 8), xx0 = (item - ty * (OUT / 8)) * 8;
         const int yy = tile * TILE_ROWS + ty;
         const int ymin = vb[ty * 2] - r0, n = vb[ty * 2 + 1];
         const int* k = vk + ty * ks_v;
-        int a0 = 1 << (PREC_BITS - 1), a1 = a0, a2 = a0;
+        int acc[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) acc[j] = 1 << (PREC_BITS - 1);
         for (int y = 0; y < n; ++y) {
-            const uint8_t* t = tmp + ((size_t)(ymin + y) * OUT + xx) * 3;
+            const uint2* t = reinterpret_cast<const uint2*>(tmp + ((size_t)(ymin + y) * OUT + xx0) * 3);
+            const uint2 q0 = t[0], q1 = t[1], q2 = t[2];
+            const uint32_t wds[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
             const int kv = k[y];
-            a0 += t[0] * kv;
-            a1 += t[1] * kv;
-            a2 += t[2] * kv;
+#pragma unroll
+            for (int j = 0; j < 24; ++j) acc[j] += (int)((wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu) * kv;
         }
-        const float b = lut[clip8(a0)], g = lut[clip8(a1)], r = lut[clip8(a2)];
+        float pr[8], pg[8], pb[8];
+#pragma unroll
+        for (int px = 0; px < 8; ++px) {
+            pb[px] = lut[clip8(acc[3 * px])];
+            pg[px] = lut[clip8(acc[3 * px + 1])];
+            pr[px] = lut[clip8(acc[3 * px + 2])];
+        }
         const long long n_img = blockIdx.y;
+        bf16* o;
+        long long plane;
         if (layout == 0) {
-            bf16* o = out + n_img * 3 * OUT * OUT + (long long)yy * OUT + xx;
-            store16(o, r, f16);
-            store16(o + OUT * OUT, g, f16);
-            store16(o + 2 * OUT * OUT, b, f16);
+            o = out + n_img * 3 * OUT * OUT + (long long)yy * OUT + xx0;
+            plane = (long long)OUT * OUT;
         } else {
-            const int patch = (yy >> 4) * 24 + (xx >> 4);
-            bf16* o = out + (n_img * 576 + patch) * 768 + (yy & 15) * 16 + (xx & 15);
-            store16(o, r, f16);
-            store16(o + 256, g, f16);
-            store16(o + 512, b, f16);
+            const int patch = (yy >> 4) * 24 + (xx0 >> 4);
+            o = out + (n_img * 576 + patch) * 768 + (yy & 15) * 16 + (xx0 & 15);
+            plane = 256;
         }
+        *reinterpret_cast<uint4*>(o) = make_uint4(pack2(pr[0], pr[1], f16), pack2(pr[2], pr[3], f16),
+                                                  pack2(pr[4], pr[5], f16), pack2(pr[6], pr[7], f16));
+        *reinterpret_cast<uint4*>(o + plane) = make_uint4(pack2(pg[0], pg[1], f16), pack2(pg[2], pg[3], f16),
+                                                          pack2(pg[4], pg[5], f16), pack2(pg[6], pg[7], f16));
+        *reinterpret_cast<uint4*>(o + 2 * plane) = make_uint4(pack2(pb[0], pb[1], f16), pack2(pb[2], pb[3], f16),
+                                                              pack2(pb[4], pb[5], f16), pack2(pb[6], pb[7], f16));
     }
+}
+
+__host__ __device__ inline size_t k9_smem_need(int w, int h) {
+    const double sv = (double)((float)h) / OUT, sh = (double)((float)w) / OUT;
+    const double fv = sv < 1.0 ? 1.0 : sv, fh = sh < 1.0 ? 1.0 : sh;
+    const int ks_v = (int)ceil(2.0 * fv) * 2 + 1, ks_h = (int)ceil(2.0 * fh) * 2 + 1;
+    const size_t tables = (size_t)(TILE_ROWS * 2 + TILE_ROWS * ks_v + OUT * 2 + OUT * ks_h) * 4;
+    const size_t band = (size_t)(TILE_ROWS * sv + 2.0 * (2.0 * fv) + 4.0);    // source rows under 16 output rows + support
+    return tables + (band > (size_t)(ks_v + 2) ? band : (size_t)(ks_v + 2)) * OUT * 3 + 64;
 }
 
 // rect (x, y, w, h) on a page -> crop descriptor of page[y:y+h+1, x:x+w+1] (numpy-style clipping), the
@@ -255,7 +286,9 @@ int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int
     }
     MB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), stream));
     dim3 grid(OUT / TILE_ROWS, n);
-    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err, ctx->f16);
+    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_SMALL, stream>>>(descs, out, layout, err, ctx->f16, K9_SMEM_SMALL, 1);
+    MB_LAUNCH_CHECK(ctx);
+    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err, ctx->f16, K9_SMEM_BYTES, 0);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }

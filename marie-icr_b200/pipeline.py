@@ -96,7 +96,9 @@ class PagePipeline:
             raise RuntimeError("CRAFT weights are not loaded")
         n, ph, pw, _ = pages_dev.shape
         tt, lt, low = preset
-        rects, boxes, pidx, counts, maps = [], [], [], [], []
+        rects, boxes, pidx, counts = [], [], [], []
+        scores_all, ratio = None, None
+        # K1 + CRAFT in micro-batches (activation memory), score maps of the whole batch kept in HBM ...
         for i0 in range(0, n, self.micro_batch):
             chunk = pages_dev[i0:i0 + self.micro_batch]
             m = chunk.shape[0]
@@ -107,23 +109,25 @@ class PagePipeline:
             scores = ops.craft_forward(x)
             self.timer.stop("k2_4_craft", t, m)
             del x
-            r2 = (1.0 / ratio) * 2
-            t = self.timer.start()
-            out = ops.craft_post(scores[0], scores[1], tt, lt, low, ratios=[(r2, r2)] * m, page_hw=[(ph, pw)] * m,
-                                 max_labels=self.max_labels, max_boxes=self.max_boxes)
-            self.timer.stop("k5_7_post", t, m)
-            nb = out["n_boxes"].cpu().tolist()          # mb_craft_post has synchronised the stream already
-            for j in range(m):
-                rects.append(out["rects"][j, :nb[j]])
-                boxes.append(out["adj"][j, :nb[j]])
-                pidx.append(torch.full((nb[j],), i0 + j, dtype=torch.int32, device=pages_dev.device))
-            counts.extend(nb)
-            if keep_maps:
-                maps.append(scores)
+            if scores_all is None:
+                scores_all = torch.empty((2, n) + tuple(scores.shape[2:]), dtype=torch.float32, device=pages_dev.device)
+            scores_all[:, i0:i0 + m] = scores
+        # ... then ONE post-processing pass over all pages (launch latency amortised over the batch)
+        r2 = (1.0 / ratio) * 2
+        t = self.timer.start()
+        out = ops.craft_post(scores_all[0], scores_all[1], tt, lt, low, ratios=[(r2, r2)] * n, page_hw=[(ph, pw)] * n,
+                             max_labels=self.max_labels, max_boxes=self.max_boxes)
+        self.timer.stop("k5_7_post", t, n)
+        nb = out["n_boxes"].cpu().tolist()          # mb_craft_post has synchronised the stream already
+        for j in range(n):
+            rects.append(out["rects"][j, :nb[j]])
+            boxes.append(out["adj"][j, :nb[j]])
+            pidx.append(torch.full((nb[j],), j, dtype=torch.int32, device=pages_dev.device))
+        counts = nb
         res = dict(rects=torch.cat(rects).contiguous(), boxes=torch.cat(boxes).contiguous(),
                    page_idx=torch.cat(pidx).contiguous(), counts=counts)
         if keep_maps:
-            res["scores"] = torch.cat(maps, 1)
+            res["scores"] = scores_all
         return res
 
     # ------------------------------------------------------------------------------------------ recognition
