@@ -149,18 +149,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-// exact-erf GELU (timm nn.GELU) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit
-// output rounding): one MUFU.RCP + one MUFU.EX2 + a 5-term Horner instead of erff's long branchy path, which made the
-// fc1 epilogue slower than the tile's MMAs.
+// exact-erf GELU (timm nn.GELU).  erf(z) = 1 - 2^q(z) for z in [0, 3.92] with a degree-6 polynomial q fitted to
+// log2(erfc) (max |erf error| 7.6e-7, max |GELU error| 2.8e-7 — far below the 16-bit output rounding; fit script in
+// profiles/r01_gelu_erf_fit.md): 6 FFMA + ONE MUFU.EX2.  erff's branchy path (and the earlier A&S 7.1.26 form with
+// two MUFU ops) made the fc1 epilogue issue-bound: 539 vs 1114 TFLOP/s for the same GEMM without activation.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float z = fminf(fabsf(x) * 0.70710678118654752440f, 3.92f);
+    float q = fmaf(0.00022097790497355163f, z, -0.004072441719472408f);
+    q = fmaf(q, z, 0.031655170023441315f);
+    q = fmaf(q, z, -0.15032003819942474f);
+    q = fmaf(q, z, -0.9179494380950928f);
+    q = fmaf(q, z, -1.6279493570327759f);
+    const float e = 1.0f - exp2f(q * z);
+    const float hx = 0.5f * x;
+    return fmaf(hx, copysignf(e, x), hx);
+}
+template <int ACT> __device__ __forceinline__ float apply_act(float x) {
+    if (ACT == MB_ACT_RELU) return fmaxf(x, 0.0f);
+    if (ACT == MB_ACT_GELU) return gelu_erf(x);
+    return x;
 }
 
 // ---------------------------------------------------------------- kernel
@@ -315,85 +322,103 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const long long pix0 = ((long long)nn * p.h + hh) * p.w + row0;
             const int rows_valid = min(32, p.w - row0);             // may be <= 0 for a ragged last tile
 
+            const int n_chunks = (p.block_n + 31) >> 5;
+            // residual tile rows are prefetched one chunk ahead (the first chunk before the accumulator is even ready)
+            uint2 rres[8];
+            auto chunk_fast = [&](int ci) {
+                const int n0c = nt * p.block_n + ci * 32;
+                return ci < n_chunks && n0c + 32 <= p.n_out && rows_valid == 32 && vec_out && vec_res;
+            };
+            auto load_res = [&](int ci) {
+                const int n0c = nt * p.block_n + ci * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    rres[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + (pix0 + i * 4 + rr) * p.res_ld + n0c + kk * 4));
+            };
+            if (RES && chunk_fast(half)) load_res(half);
             mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-            const int n_chunks = (p.block_n + 31) >> 5;
+            uint32_t v[32];
+            if (half < n_chunks) tmem_ld32(taddr + (uint32_t)(half * 32), v);     // first chunk's accumulators in flight
 #pragma unroll 1
             for (int ci = half; ci < n_chunks; ci += 2) {
-                const int c = ci * 32;
-                const int n0 = nt * p.block_n + c;
-                if (n0 >= p.n_out || rows_valid <= 0) continue;      // warp-uniform
+                const int n0 = nt * p.block_n + ci * 32;
+                const bool active = n0 < p.n_out && rows_valid > 0;               // warp-uniform
                 const int ncols = min(32, p.n_out - n0);
                 const bool fast = ncols == 32 && rows_valid == 32 && vec_out && vec_res;   // warp-uniform
-                uint2 rres[8];
-                if (RES && fast) {   // residual prefetch in the read-back layout (4 x 16-bit per lane and row group)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        rres[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + (pix0 + i * 4 + rr) * p.res_ld + n0 + kk * 4));
-                }
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)c, v);
                 tmem_wait_ld();
-                float f[32];
-                if (p.bias != nullptr) {
-                    const float bl = (lane < ncols) ? __ldg(p.bias + n0 + lane) : 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                }
-                if (ACT == MB_ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-                } else if (ACT == MB_ACT_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                }
-                if (OUT == MB_OUT_F32_PLANAR) {   // channel planes, pixel-contiguous: already coalesced across lanes
-                    if (lane < rows_valid) {
+                if (OUT == MB_OUT_F32_PLANAR) {   // channel planes, pixel-contiguous: coalesced across lanes as is
+                    if (active && lane < rows_valid) {
                         float* o = reinterpret_cast<float*>(p.out) + pix0 + lane;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) o[(long long)(n0 + j) * p.out_plane] = f[j];
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < ncols) {
+                                float x = __uint_as_float(v[j]);
+                                if (p.bias != nullptr) x += __ldg(p.bias + n0 + j);
+                                o[(long long)(n0 + j) * p.out_plane] = apply_act<ACT>(x);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (ci + 2 < n_chunks) tmem_ld32(taddr + (uint32_t)((ci + 2) * 32), v);
                     continue;
                 }
+                // phase A: raw accumulators -> staging tile (row per lane, 16-byte chunks XOR-swizzled)
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    *reinterpret_cast<float4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) =
-                        make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                    *reinterpret_cast<uint4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+                        make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                 __syncwarp();
-                if (fast) {
+                // the next chunk's TMEM load overlaps phase B (v is dead until the wait at the top of the loop)
+                if (ci + 2 < n_chunks) tmem_ld32(taddr + (uint32_t)((ci + 2) * 32), v);
+                if (active) {
+                    if (fast) {
+                        // phase B: lanes run along the row (8 lanes x 4 columns, 4 rows per pass): bias once per chunk,
+                        // activation, residual, pack, coalesced store
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + kk);
+                        float4 xs[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + rr;
-                        float4 x = *reinterpret_cast<const float4*>(stage + r * 32 + ((kk ^ (r & 7)) << 2));
-                        if (RES) {
-                            const float2 r0 = unpack2t<F16>(rres[i].x), r1 = unpack2t<F16>(rres[i].y);
-                            x.x += r0.x; x.y += r0.y; x.z += r1.x; x.w += r1.y;
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + rr;
+                            float4 x = *reinterpret_cast<const float4*>(stage + r * 32 + ((kk ^ (r & 7)) << 2));
+                            x.x = apply_act<ACT>(x.x + b4.x); x.y = apply_act<ACT>(x.y + b4.y);
+                            x.z = apply_act<ACT>(x.z + b4.z); x.w = apply_act<ACT>(x.w + b4.w);
+                            if (RES) {
+                                const float2 r0 = unpack2t<F16>(rres[i].x), r1 = unpack2t<F16>(rres[i].y);
+                                x.x += r0.x; x.y += r0.y; x.z += r1.x; x.w += r1.y;
+                            }
+                            xs[i] = x;
                         }
-                        if (OUT == MB_OUT_BF16)
-                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) =
-                                make_uint2(pack2t<F16>(x.x, x.y), pack2t<F16>(x.z, x.w));
-                        else
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) = x;
-                    }
-                } else {
-                    // ragged chunk (last rows / last columns / unaligned pitch): one element per lane and row
-#pragma unroll 1
-                    for (int r = 0; r < rows_valid; ++r) {
-                        if (lane < ncols) {
-                            float x = stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
-                            if (RES) x += load16(p.residual + (pix0 + r) * p.res_ld + n0 + lane, F16);
+                        if (RES && chunk_fast(ci + 2)) load_res(ci + 2);    // next chunk's residual rows: a chunk ahead
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + rr;
+                            const float4 x = xs[i];
                             if (OUT == MB_OUT_BF16)
-                                store16(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + lane, x, F16);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) =
+                                    make_uint2(pack2t<F16>(x.x, x.y), pack2t<F16>(x.z, x.w));
                             else
-                                reinterpret_cast<float*>(p.out)[(pix0 + r) * p.out_ld + n0 + lane] = x;
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) = x;
+                        }
+                    } else {
+                        // ragged chunk (last rows / last columns / unaligned pitch): one element per lane and row
+                        const float bl = (p.bias != nullptr && lane < ncols) ? __ldg(p.bias + n0 + lane) : 0.f;
+#pragma unroll 1
+                        for (int r = 0; r < rows_valid; ++r) {
+                            if (lane < ncols) {
+                                float x = apply_act<ACT>(stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))] + bl);
+                                if (RES) x += load16(p.residual + (pix0 + r) * p.res_ld + n0 + lane, F16);
+                                if (OUT == MB_OUT_BF16)
+                                    store16(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + lane, x, F16);
+                                else
+                                    reinterpret_cast<float*>(p.out)[(pix0 + r) * p.out_ld + n0 + lane] = x;
+                            }
                         }
                     }
                 }
+                if (RES && !(active && fast) && chunk_fast(ci + 2)) load_res(ci + 2);   // keep the prefetch chain alive
                 __syncwarp();
             }
             tcgen05_fence_before();
