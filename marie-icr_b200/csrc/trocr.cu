@@ -169,6 +169,11 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // tile [64 rows][64 x 16-bit] with the 16-byte chunk index XOR-swizzled by (row & 7)
 __device__ __forceinline__ int swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
     const bf16* kbase = kptr + img * T * kv_ld + head * DH;
     const bf16* vbase = vptr + img * T * kv_ld + head * DH;
     const int n_tiles = (T + 63) >> 6;
+    const bool warp_active = q0 + warp * 16 < Tq;
 
     auto load_tile = [&](unsigned char* dst, const bf16* src, long long ld, int row0, int limit) {
 #pragma unroll
@@ -236,6 +242,9 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
         }
         cp_async_wait<ATT_STAGES - 1>();               // tile j (and Q) have landed
         __syncthreads();
+        // warps whose 16 query rows are all beyond Tq (decoder cross-attention: Tq = beam <= 8, so warps 1..3) only
+        // help streaming K/V; their HMMAs on zero rows used to cap the kernel at the legacy tensor pipe's rate
+        if (warp_active) {
         if (j == 0) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -259,16 +268,21 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
                 mma16816<F16>(s[nb], aq[kp * 2 + 1], b2, b3);
             }
         }
-        // online softmax (rows g and g+8 of this warp's 16)
-        const int key0 = j * 64 + (lane & 3) * 2;
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        // online softmax (rows g and g+8 of this warp's 16) on the raw scores: the scale is folded into the exp2
+        // argument (one FFMA + one MUFU.EX2 per element), keys are masked only in the ragged last tile, and the
+        // accumulator is rescaled only when some row's running maximum actually moved
+        if (j == n_tiles - 1) {
+            const int key0 = j * 64 + (lane & 3) * 2;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-            const int k = key0 + nb * 8;
-            s[nb][0] = (k < T) ? s[nb][0] * scale_log2e : -INFINITY;
-            s[nb][1] = (k + 1 < T) ? s[nb][1] * scale_log2e : -INFINITY;
-            s[nb][2] = (k < T) ? s[nb][2] * scale_log2e : -INFINITY;
-            s[nb][3] = (k + 1 < T) ? s[nb][3] * scale_log2e : -INFINITY;
+            for (int nb = 0; nb < 8; ++nb) {
+                const int k = key0 + nb * 8;
+                if (k >= T) { s[nb][0] = -INFINITY; s[nb][2] = -INFINITY; }
+                if (k + 1 >= T) { s[nb][1] = -INFINITY; s[nb][3] = -INFINITY; }
+            }
+        }
+        float mx0 = fmaxf(s[0][0], s[0][1]), mx1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+        for (int nb = 1; nb < 8; ++nb) {
             mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
             mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
         }
@@ -276,19 +290,23 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has at least one valid key
-        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
-        m0 = mn0; m1 = mn1;
-        l0 *= c0; l1 *= c1;
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // raw-score maxima; finite: a tile has a valid key
+        if (__any_sync(0xffffffffu, mn0 != m0 || mn1 != m1)) {
+            const float c0 = fast_exp2((m0 - mn0) * scale_log2e), c1 = fast_exp2((m1 - mn1) * scale_log2e);
+            l0 *= c0; l1 *= c1;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) { o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1; }
+            m0 = mn0; m1 = mn1;
+        }
+        const float ms0 = -mn0 * scale_log2e, ms1 = -mn1 * scale_log2e;
         uint32_t ap[4][4];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            const float p0 = exp2f(s[nb][0] - mn0), p1 = exp2f(s[nb][1] - mn0);
-            const float p2 = exp2f(s[nb][2] - mn1), p3 = exp2f(s[nb][3] - mn1);
+            const float p0 = fast_exp2(fmaf(s[nb][0], scale_log2e, ms0)), p1 = fast_exp2(fmaf(s[nb][1], scale_log2e, ms0));
+            const float p2 = fast_exp2(fmaf(s[nb][2], scale_log2e, ms1)), p3 = fast_exp2(fmaf(s[nb][3], scale_log2e, ms1));
             l0 += p0 + p1; l1 += p2 + p3;
             ap[nb >> 1][(nb & 1) * 2] = pack2(p0, p1, F16);
             ap[nb >> 1][(nb & 1) * 2 + 1] = pack2(p2, p3, F16);
-            o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
         }
         // O += P V
 #pragma unroll
@@ -303,6 +321,7 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
                 mma16816<F16>(o[dp * 2 + 1], ap[kk], b2, b3);
             }
         }
+        }   // warp_active
         __syncthreads();   // all warps done with this K/V buffer before a later prefetch overwrites it
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);

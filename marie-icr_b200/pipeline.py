@@ -147,8 +147,13 @@ class PagePipeline:
             patches = ops.pack_crops(pages_dev, r, p, layout=1)
             self.timer.stop("k9_crops", e, r.shape[0])
             e = self.timer.start()
-            t, l, s = ops.trocr_recognize(patches, beam=beam, max_len_b=max_len_b, chunk=self.crop_chunk, out_ld=out_ld)
-            self.timer.stop("k10_12_trocr", e, r.shape[0])
+            enc = ops.trocr_encode(patches)
+            self.timer.stop("k10_encoder", e, r.shape[0])
+            del patches
+            e = self.timer.start()
+            t, l, s, _ = ops.trocr_decode(enc, beam=beam, max_len_b=max_len_b, out_ld=out_ld)
+            self.timer.stop("k11_12_decode", e, r.shape[0])
+            del enc
             tokens[i0:i0 + r.shape[0]] = t
             lengths[i0:i0 + r.shape[0]] = l
             scores[i0:i0 + r.shape[0]] = s
