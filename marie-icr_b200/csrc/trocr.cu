@@ -19,6 +19,10 @@
 #include "common.cuh"
 #include "blob.cuh"
 #include <math.h>
+#include <stdlib.h>
+
+int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D, int heads, float scale_log2e,
+                    cudaStream_t stream);
 
 namespace {
 
@@ -639,6 +643,13 @@ int ensure_arena(mb_ctx* ctx, TrocrModel* m, size_t bytes) {
     return 0;
 }
 
+// MB_ATTN_LEGACY=1 routes the encoder through the mma.sync flash kernel (A/B testing of the tcgen05 kernel)
+bool attention_legacy() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MB_ATTN_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int attention_setup(mb_ctx* ctx) {
     static bool done = false;
     if (done) return 0;
@@ -695,7 +706,9 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
         const EncLayer& L = m->enc[l];
         RC(layernorm(ctx, x, y, L.ln1_w, L.ln1_b, M, D, 1e-6f, s));
         RC(gemm(ctx, y, D, L.qkv_w, 3 * D, M, 3 * D, nullptr, MB_ACT_NONE, nullptr, big, MB_OUT_BF16, s));
-        {
+        if (!attention_legacy()) {
+            RC(mb_attention_tc(ctx, big, y, n, T, D, m->enc_heads, scale_log2e, s));
+        } else {
             dim3 grid((T + 63) / 64, m->enc_heads, n);
             RC(attention_setup(ctx));
             if (ctx->f16) attention_kernel<true><<<grid, 128, ATT_SMEM, s>>>(big, 3LL * D, big + D, big + 2 * D, 3LL * D, y, D, T, T, scale_log2e);
