@@ -154,6 +154,10 @@ int mb_find_line_numbers(mb_ctx* ctx, const int32_t* lines_host, int n_lines, co
  * mb_trocr_forced_logits: parity hook — teacher-forced decoder, logits_out [L, n, vocab] fp32.
  * mb_trocr_recognize: encode + decode over n crops in chunks (0 = default 512 crops per chunk). */
 int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes);
+/* Test hook for the two attention kernels: softmax(Q K^T * scale) V over a packed qkv buffer [n*T, 3*D] (heads of 64)
+ * -> out [n*T, D].  mode 0 = tcgen05/TMEM kernel (encoder), 1 = mma.sync flash kernel (decoder cross-attention). */
+int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, int n, int T, int D, float scale, int mode,
+                   void* stream);
 int mb_trocr_dims(mb_ctx* ctx, int* dims4_host);
 /* cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded} */
 int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3_host);

@@ -7,9 +7,9 @@
 // CTA's softmax overlaps the other's MMAs.  Per 128-key tile:
 //   warp 0      TMA: Q once; K and V tiles (two stages) straight out of the qkv activation buffer [rows, 3D]
 //   warp 1      tcgen05.mma  S[128x128] = Q K^T  (A, B K-major);  O[128x64] += P V  (B = V tile as loaded, MN-major)
-//   warps 2..5  one thread per query row (TMEM lane): pass 1 row maximum of S, O rescale in TMEM when the running
-//               maximum moved, pass 2 P = exp2((S - m) / 8 * log2 e) -> 16-bit -> shared memory in the swizzled
-//               K-major operand layout; after the last tile O / l -> global
+//   warps 2..5  one thread per query row (TMEM lane): P = exp2((S - ref) / 8 * log2 e) -> 16-bit -> shared memory in
+//               the swizzled K-major operand layout, one pass over S per tile (fixed per-row reference, re-based
+//               with an in-TMEM rescale of O only on fp16 head-room overflow); after the last tile O / l -> global
 // Rows / keys beyond the image's 577 tokens are whatever follows in the buffer (finite) or TMA zero fill; keys are
 // masked in the last tile, rows are simply not stored.
 #include "common.cuh"
@@ -143,17 +143,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         const int row = quarter * 32 + lane;                  // query row inside the tile == TMEM lane
         const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t t_o = t_s + O_COL;
-        float m_run = -INFINITY, l_run = 0.f;
+        float l_run = 0.f;
+        float ms = 0.f;                                       // -(reference score) * scale * log2(e) of this row
         const float sc = p.scale_log2e;
-        for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(smem_u32(s_full), j & 1, p.diag, 15);
-            tcgen05_fence_after();
-            const int valid = T - j * TILE;                   // keys >= valid are beyond this image
-            // The TMEM loads are software-pipelined (chunk c+1 is in flight while chunk c is processed): with only two
-            // softmax warps per scheduler an exposed tcgen05.ld round trip per chunk left the MUFU pipe idle.
-            uint32_t va[32], vb[32];
-            // pass 1: row maximum of the raw scores
-            float mx = -INFINITY;
+        uint32_t va[32], vb[32];
+        // The softmax is shift invariant, so instead of the running row maximum (which costs a second pass over S in
+        // TMEM per tile) the row keeps ONE reference: the exact maximum of its first key tile.  Later tiles are read
+        // once; probabilities may exceed 1 and only when one passes 2^11 (fp16 operand head-room) the row is re-based:
+        // O and l are scaled in place and the tile's P is recomputed.  The reference never exceeds the true maximum,
+        // so the largest probability of a row is >= 1 and nothing underflows as a whole.
+        // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed.
+        auto pass_p = [&](int valid, float ms_, float& pmax) -> float {
+            float lsum = 0.f;
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
             tmem_ld32(t_s, va);
 #pragma unroll
             for (int ci = 0; ci < TILE / 32; ++ci) {
@@ -162,57 +164,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
                 tmem_wait_ld();
                 if (ci + 1 < TILE / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
                 const int c = ci * 32;
-                if (c + 32 <= valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c + i < valid) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                }
-            }
-            const float m_new = fmaxf(m_run, mx);
-            tmem_ld32(t_s, va);                                // pass 2's first chunk travels during the correction step
-            // s_full(j) was committed after P V (j-1): O is complete and may be rescaled in place
-            if (j > 0 && __any_sync(0xffffffffu, m_new != m_run)) {
-                const float corr = ex2_approx((m_run - m_new) * sc);
-                l_run *= corr;
-                tmem_wait_ld();
-#pragma unroll 1
-                for (int c = 0; c < HD; c += 32) {
-                    tmem_ld32(t_o + (uint32_t)c, vb);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) * corr);
-                    tmem_st32(t_o + (uint32_t)c, vb);
-                }
-                tmem_wait_st();
-            }
-            m_run = m_new;
-            const float ms = -m_new * sc;
-            // pass 2: probabilities -> 16-bit -> swizzled K-major operand tile
-#pragma unroll
-            for (int ci = 0; ci < TILE / 32; ++ci) {
-                uint32_t* cur = (ci & 1) ? vb : va;
-                uint32_t* nxt = (ci & 1) ? va : vb;
-                tmem_wait_ld();
-                if (ci + 1 < TILE / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
-                const int c = ci * 32;
                 float pr[32];
-                if (c + 32 <= valid) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        pr[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), sc, ms));
-                        l_run += pr[i];
+                for (int i = 0; i < 32; i += 4) {
+                    pr[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), sc, ms_));
+                    pr[i + 1] = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), sc, ms_));
+                    pr[i + 2] = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), sc, ms_));
+                    pr[i + 3] = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), sc, ms_));
+                    if (c + 32 > valid) {                      // ragged last tile only
+                        if (c + i >= valid) pr[i] = 0.f;
+                        if (c + i + 1 >= valid) pr[i + 1] = 0.f;
+                        if (c + i + 2 >= valid) pr[i + 2] = 0.f;
+                        if (c + i + 3 >= valid) pr[i + 3] = 0.f;
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float e = ex2_approx(fmaf(__uint_as_float(cur[i]), sc, ms));
-                        pr[i] = (c + i < valid) ? e : 0.f;
-                        l_run += pr[i];
-                    }
+                    s0 += pr[i]; s1 += pr[i + 1]; s2 += pr[i + 2]; s3 += pr[i + 3];
+                    m0 = fmaxf(m0, pr[i]); m1 = fmaxf(m1, pr[i + 1]); m2 = fmaxf(m2, pr[i + 2]); m3 = fmaxf(m3, pr[i + 3]);
                 }
+                lsum += (s0 + s1) + (s2 + s3);
                 uint8_t* prow = sP + (c >> 6) * TILE_BYTES + row * 128;
                 const int chunk0 = (c & 63) >> 3;             // first 16-byte chunk of these 32 columns inside the atom row
 #pragma unroll
@@ -225,6 +194,58 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
                     *reinterpret_cast<uint4*>(prow + (((chunk0 + q) ^ (row & 7)) << 4)) = w;
                 }
             }
+            pmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            return lsum;
+        };
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(smem_u32(s_full), j & 1, p.diag, 15);
+            tcgen05_fence_after();
+            const int valid = T - j * TILE;                   // keys >= valid are beyond this image
+            if (j == 0) {
+                // exact row maximum of the first tile = the row's reference
+                float mx = -INFINITY;
+                tmem_ld32(t_s, va);
+#pragma unroll
+                for (int ci = 0; ci < TILE / 32; ++ci) {
+                    uint32_t* cur = (ci & 1) ? vb : va;
+                    uint32_t* nxt = (ci & 1) ? va : vb;
+                    tmem_wait_ld();
+                    if (ci + 1 < TILE / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
+                    const int c = ci * 32;
+                    float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (c + i < valid) a0 = fmaxf(a0, __uint_as_float(cur[i]));
+                        if (c + i + 1 < valid) a1 = fmaxf(a1, __uint_as_float(cur[i + 1]));
+                        if (c + i + 2 < valid) a2 = fmaxf(a2, __uint_as_float(cur[i + 2]));
+                        if (c + i + 3 < valid) a3 = fmaxf(a3, __uint_as_float(cur[i + 3]));
+                    }
+                    mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+                }
+                ms = -mx * sc;
+            }
+            float pmax;
+            float lt = pass_p(valid, ms, pmax);
+            if (__any_sync(0xffffffffu, pmax > 2048.f)) {
+                // re-base the rows that grew: shift by log2(pmax) so their largest probability becomes 1
+                const float lg = pmax > 1.f ? log2f(pmax) : 0.f;
+                const float f = ex2_approx(-lg);
+                ms -= lg;
+                l_run *= f;
+                if (j > 0) {                                  // s_full(j) was committed after P V (j-1): O is complete
+#pragma unroll 1
+                    for (int c = 0; c < HD; c += 32) {
+                        tmem_ld32(t_o + (uint32_t)c, vb);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) * f);
+                        tmem_st32(t_o + (uint32_t)c, vb);
+                    }
+                    tmem_wait_st();
+                }
+                lt = pass_p(valid, ms, pmax);
+            }
+            l_run += lt;
             fence_proxy_async_smem();                         // generic-proxy writes of P -> visible to the MMA (async proxy)
             tcgen05_fence_before();
             mbar_arrive(smem_u32(p_full));

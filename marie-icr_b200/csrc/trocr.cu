@@ -892,6 +892,24 @@ extern "C" int mb_trocr_dims(mb_ctx* ctx, int* dims) {
     return 0;
 }
 
+// Test hook: softmax(Q K^T * scale) V over a packed qkv buffer [n*T, 3*D] (heads of 64) -> out [n*T, D].
+// mode 0: tcgen05 kernel (attn_tc.cu); mode 1: mma.sync flash kernel (the one the decoder's cross-attention uses).
+extern "C" int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, int n, int T, int D, float scale,
+                              int mode, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    MB_REQUIRE(ctx, n > 0 && T > 0 && D > 0 && D % DH == 0, "attention16: bad geometry");
+    cudaStream_t s = (cudaStream_t)stream;
+    const float scale_log2e = scale * 1.4426950408889634f;
+    const bf16* q = (const bf16*)qkv_dev;
+    if (mode == 0) return mb_attention_tc(ctx, q, (bf16*)out_dev, n, T, D, D / DH, scale_log2e, s);
+    RC(attention_setup(ctx));
+    dim3 grid((T + 63) / 64, D / DH, n);
+    if (ctx->f16) attention_kernel<true><<<grid, 128, ATT_SMEM, s>>>(q, 3LL * D, q + D, q + 2 * D, 3LL * D, (bf16*)out_dev, D, T, T, scale_log2e);
+    else attention_kernel<false><<<grid, 128, ATT_SMEM, s>>>(q, 3LL * D, q + D, q + 2 * D, 3LL * D, (bf16*)out_dev, D, T, T, scale_log2e);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 // cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded}
 extern "C" int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3) {
     if (!ctx || !ctx->trocr || !out3) return MB_ERR_STATE;

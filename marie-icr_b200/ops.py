@@ -229,3 +229,12 @@ def trocr_recognize(patches, beam=1, max_len_b=200, chunk=0, out_ld=None):
     ctx.call("mb_trocr_recognize", ptr(patches), c_int(n), c_int(beam), c_int(max_len_b), c_int(chunk), ptr(tokens),
              c_int(out_ld), ptr(lengths), ptr(scores), cur_stream())
     return tokens, lengths, scores
+
+
+def attention16(qkv, n, T, scale=0.125, mode=0):
+    """qkv [n*T, 3*D] 16-bit -> softmax(Q K^T * scale) V [n*T, D].  mode 0: tcgen05 kernel, 1: mma.sync kernel."""
+    D = qkv.shape[1] // 3
+    out = torch.empty((n * T, D), dtype=qkv.dtype, device=qkv.device)
+    _ctx(qkv).call("mb_attention16", ptr(qkv.contiguous()), ptr(out), c_int(n), c_int(T), c_int(D), c_float(scale),
+                   c_int(mode), cur_stream())
+    return out
