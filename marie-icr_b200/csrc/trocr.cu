@@ -59,44 +59,17 @@ struct TrocrModel {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// One warp per row; D % 8 == 0, D <= 2048.  in/out 16-bit (may alias), gamma/beta fp32, statistics in fp32
+// One warp per row (grid-stride over rows); D % 8 == 0, D <= 1024.  in/out 16-bit (may alias), gamma/beta fp32, statistics in fp32
 // (two-pass: mean, then centred variance — the order torch's CPU kernel uses up to summation order).
-constexpr int LN_MAXV = 8;
+constexpr int LN_MAXV = 4;      // D <= 1024
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long long rows, int D, float eps, int f16) {
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int nv = D >> 3;
-    const uint4* src = reinterpret_cast<const uint4*>(in + row * D);
-    float v[LN_MAXV][8];
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int vi = lane + 32 * i;
-        if (vi < nv) {
-            const uint4 u = src[vi];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = unpack2(w[k], f16);
-                v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
-                sum += f.x + f.y;
-            }
-        }
-    }
-    const float mean = warp_sum(sum) / (float)D;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        if (lane + 32 * i < nv) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; sq += d * d; }
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
-    uint4* dst = reinterpret_cast<uint4*>(out + row * D);
+    // each warp keeps its slice of gamma / beta in registers and strides over rows: re-reading 6 KB of fp32 affine
+    // parameters per 1.5 KB row made the first version L1-bound (2.9 TB/s of row traffic)
+    float g[LN_MAXV][8], bt[LN_MAXV][8];
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
         const int vi = lane + 32 * i;
@@ -105,12 +78,51 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
             const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
-            uint4 o;
-            o.x = pack2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y, f16);
-            o.y = pack2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w, f16);
-            o.z = pack2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y, f16);
-            o.w = pack2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w, f16);
-            dst[vi] = o;
+            g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+            bt[i][0] = b0.x; bt[i][1] = b0.y; bt[i][2] = b0.z; bt[i][3] = b0.w; bt[i][4] = b1.x; bt[i][5] = b1.y; bt[i][6] = b1.z; bt[i][7] = b1.w;
+        }
+    }
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+        const uint4* src = reinterpret_cast<const uint4*>(in + row * D);
+        float v[LN_MAXV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + 32 * i;
+            if (vi < nv) {
+                const uint4 u = src[vi];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack2(w[k], f16);
+                    v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+                    sum += f.x + f.y;
+                }
+            }
+        }
+        const float mean = warp_sum(sum) / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            if (lane + 32 * i < nv) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; sq += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+        uint4* dst = reinterpret_cast<uint4*>(out + row * D);
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + 32 * i;
+            if (vi < nv) {
+                uint4 o;
+                o.x = pack2((v[i][0] - mean) * rstd * g[i][0] + bt[i][0], (v[i][1] - mean) * rstd * g[i][1] + bt[i][1], f16);
+                o.y = pack2((v[i][2] - mean) * rstd * g[i][2] + bt[i][2], (v[i][3] - mean) * rstd * g[i][3] + bt[i][3], f16);
+                o.z = pack2((v[i][4] - mean) * rstd * g[i][4] + bt[i][4], (v[i][5] - mean) * rstd * g[i][5] + bt[i][5], f16);
+                o.w = pack2((v[i][6] - mean) * rstd * g[i][6] + bt[i][6], (v[i][7] - mean) * rstd * g[i][7] + bt[i][7], f16);
+                dst[vi] = o;
+            }
         }
     }
 }
@@ -676,7 +688,9 @@ int gemm(mb_ctx* ctx, const bf16* a, int K, const bf16* w, int rows_w, long long
 int layernorm(mb_ctx* ctx, const bf16* in, bf16* out, const float* g, const float* b, long long rows, int D, float eps,
               cudaStream_t s) {
     if (D % 8 != 0 || D > 256 * LN_MAXV) return mb_set_err(ctx, MB_ERR_ARG, "layernorm: unsupported width %d", D);
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(in, out, g, b, rows, D, eps, ctx->f16);
+    const long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)ctx->num_sms * 16;
+    layernorm_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(in, out, g, b, rows, D, eps, ctx->f16);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
