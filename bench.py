@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--crop-chunk", type=int, default=2048, help="crops per recogniser chunk")
     return ap.parse_args()
 
 
@@ -182,7 +183,7 @@ def run_ours(args, rank, world, local_rank):
     pages_np, _ = make_pages(idx)
     craft_sd, tsd, cfg = make_weights(dt)
     pipe = PagePipeline(device=local_rank, craft_blob=weights.pack_craft(craft_sd, dt),
-                        trocr_blob=weights.pack_trocr(tsd, cfg, dt), micro_batch=8, crop_chunk=1024)
+                        trocr_blob=weights.pack_trocr(tsd, cfg, dt), micro_batch=8, crop_chunk=args.crop_chunk)
     pages_host = torch.from_numpy(pages_np).pin_memory()
     pages_dev = pages_host.cuda(non_blocking=True)
     page_ids = torch.tensor(idx, dtype=torch.int32, device="cuda")

@@ -1,0 +1,79 @@
+"""BASELINE.json configs 3-5 as parity-test cases (not bench lines): TrOCR-large geometry, beam 5, a 4096x4096 page in
+LINE mode, a high-density form page (~800 crops)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trocr_large_encoder_and_greedy(cuda_ctx):
+    """config 4/5: TrOCR-large (ViT 1024/24/16 + decoder 1024/12)."""
+    from marie_icr_b200 import ops, weights
+    from oracle import trocr
+    from test_trocr_gpu import _fragments, _inputs, _rel
+    cuda_ctx.set_dtype("fp16")
+    cfg = trocr.trocr_large()
+    sd = trocr.synth_trocr_state(cfg, 0, round_to=torch.float16)
+    from synthetic import weights as sw
+    sw.apply_eos_row(sd, "trocr_large_seed0")
+    ops.load_trocr(weights.pack_trocr(sd, cfg, torch.float16))
+    patches, chw = _inputs(_fragments(2, seed=8), torch.float16)
+    with torch.no_grad():
+        ref = trocr.encoder_forward(sd, cfg, chw)
+    enc = ops.trocr_encode(patches)
+    rel = _rel(enc.float().cpu(), ref)
+    print("large encoder rel L2", rel)
+    assert rel <= 1e-2
+    with torch.no_grad():
+        hyps = trocr.generate(sd, cfg, enc.float().cpu(), beam=1, max_len_b=12)
+    toks, lens, _, _ = ops.trocr_decode(enc, beam=1, max_len_b=12)
+    for i, h in enumerate(hyps):
+        assert toks[i, :int(lens[i])].cpu().tolist() == h[0]["tokens"].tolist()
+
+
+def test_beam5_matches_oracle_tiny(cuda_ctx):
+    """config 3: beam 5 — hypotheses and length-normalised scores against the fairseq-search restatement."""
+    from marie_icr_b200 import ops
+    from oracle import trocr
+    from test_trocr_gpu import _fragments, _inputs, _setup
+    cuda_ctx.set_dtype("fp16")
+    cfg = trocr.trocr_tiny()
+    sd = _setup(cfg, torch.float16, 11)
+    patches, _ = _inputs(_fragments(9, seed=12), torch.float16)
+    enc = ops.trocr_encode(patches)
+    with torch.no_grad():
+        ref = trocr.generate(sd, cfg, enc.float().cpu(), beam=5, max_len_b=20)
+    toks, lens, scores, _ = ops.trocr_decode(enc, beam=5, max_len_b=20)
+    exact = 0
+    for i, h in enumerate(ref):
+        got = toks[i, :int(lens[i])].cpu().tolist()
+        if got == h[0]["tokens"].tolist():
+            exact += 1
+            assert abs(float(scores[i]) - h[0]["score"]) <= 2e-2
+    assert exact >= len(ref) - 1, f"{exact}/{len(ref)}"
+
+
+def test_4096_page_line_mode_and_dense_page(cuda_ctx):
+    """config 5 (4096x4096 page, LINE preset) and config 4 (high-density page): detection through the plugin, boxes
+    checked against the oracle post-processing on the device's own score maps."""
+    from marie_icr_b200 import ops
+    from marie_icr_b200.boxes import BoxProcessorCraftB200
+    from marie_icr_b200.plugin_api import PSMode
+    from oracle import craft_net, craft_post, synth
+    cuda_ctx.set_dtype("fp16")
+    box = BoxProcessorCraftB200(state_dict=craft_net.glyph_craft_state(0))
+    page, words = synth.synth_page(3, height=4096, width=4096)
+    rects, frags, line_ids, pred, _ = box.extract_bounding_boxes("c5", "k", page, PSMode.LINE)
+    assert abs(len(rects) - words) <= max(3, words // 50), (len(rects), words)
+    x, ratio = ops.page_preprocess(torch.from_numpy(page[None]).cuda())
+    assert ratio == 1.0 and tuple(x.shape) == (1, 4096, 4096, 4)
+    scores = ops.craft_forward(x)
+    det, _, _ = craft_post.det_boxes_cv(scores[0, 0].cpu().numpy(), scores[1, 0].cpu().numpy(), 0.4, 0.2, 0.3)
+    want = craft_post.boxes_to_rects(craft_post.adjust_result_coordinates([b.copy() for b in det], 1.0, 1.0), 4096, 4096)
+    mism = sum(r != w for r, w in zip(rects, want))
+    assert len(want) == len(rects) and mism <= max(1, len(want) // 100), (mism, len(want))
+    dense, dwords = synth.dense_page(1)
+    drects, dfrags, _, _, _ = box.extract_bounding_boxes("c4", "k", dense, PSMode.SPARSE)
+    print("dense page:", dwords, "words ->", len(drects), "boxes")
+    assert len(drects) > 600 and all(f.shape[0] > 0 and f.shape[1] > 0 for f in dfrags)
