@@ -129,12 +129,11 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 // [N*576, 768] with k = c*256 + py*16 + px (the A operand of the ViT patch-embedding GEMM).
 __global__ void __launch_bounds__(K9_THREADS)
 crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, int layout, int* __restrict__ err,
-                   int f16, int smem_limit, int small_only) {
+                   int f16, int smem_limit, int small_only, int tiles_per_cta) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ float lut[256];
     __shared__ int s_r0, s_r1;
     const CropDesc cd = crops[blockIdx.y];
-    const int tile = blockIdx.x;
     const int w = cd.w, h = cd.h;
     if (w <= 0 || h <= 0) return;
     // two launches share this kernel: the common one with a small shared-memory budget (5 CTAs/SM) takes the crops
@@ -156,12 +155,16 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
     int* hk = hb + OUT * 2;
     uint8_t* tmp = reinterpret_cast<uint8_t*>(hk + OUT * ks_h);
 
+    // horizontal coefficients once per CTA, shared by its `tiles_per_cta` row tiles (the fp64 coefficient evaluation
+    // was a third of the kernel's instructions when every 16-row tile recomputed all 384 columns)
+    for (int xx = threadIdx.x; xx < OUT; xx += blockDim.x)
+        pil_coef(w, xx, ks_h, &hb[xx * 2], &hb[xx * 2 + 1], hk + xx * ks_h);
+    for (int tile = blockIdx.x * tiles_per_cta; tile < (blockIdx.x + 1) * tiles_per_cta; ++tile) {
+    __syncthreads();                  // previous tile's passes are done with vb / vk / tmp
     if (threadIdx.x < TILE_ROWS) {
         const int yy = tile * TILE_ROWS + threadIdx.x;
         pil_coef(h, yy, ks_v, &vb[threadIdx.x * 2], &vb[threadIdx.x * 2 + 1], vk + threadIdx.x * ks_v);
     }
-    for (int xx = threadIdx.x; xx < OUT; xx += blockDim.x)
-        pil_coef(w, xx, ks_h, &hb[xx * 2], &hb[xx * 2 + 1], hk + xx * ks_h);
     __syncthreads();
     if (threadIdx.x == 0) {
         int r0 = vb[0], r1 = vb[0] + vb[1];
@@ -238,6 +241,7 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
         *reinterpret_cast<uint4*>(o + 2 * plane) = make_uint4(pack2(pb[0], pb[1], f16), pack2(pb[2], pb[3], f16),
                                                               pack2(pb[4], pb[5], f16), pack2(pb[6], pb[7], f16));
     }
+}   // tile loop
 }
 
 __host__ __device__ inline size_t k9_smem_need(int w, int h) {
@@ -285,10 +289,13 @@ int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int
         attr_set = true;
     }
     MB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), stream));
-    dim3 grid(OUT / TILE_ROWS, n);
-    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_SMALL, stream>>>(descs, out, layout, err, ctx->f16, K9_SMEM_SMALL, 1);
+    constexpr int TPC = 4;            // row tiles per CTA in the common launch
+    crop_resize_kernel<<<dim3(OUT / TILE_ROWS / TPC, n), K9_THREADS, K9_SMEM_SMALL, stream>>>(descs, out, layout, err, ctx->f16,
+                                                                                              K9_SMEM_SMALL, 1, TPC);
     MB_LAUNCH_CHECK(ctx);
-    crop_resize_kernel<<<grid, K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err, ctx->f16, K9_SMEM_BYTES, 0);
+    // large crops: one CTA per crop walks all 24 tiles (an empty launch then costs n CTAs, not 24 n)
+    crop_resize_kernel<<<dim3(1, n), K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err, ctx->f16, K9_SMEM_BYTES, 0,
+                                                                          OUT / TILE_ROWS);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
