@@ -9,9 +9,12 @@ as those of the page-by-page loop, which is kept for every other case.
 """
 import numpy as np
 
+from itertools import chain
+
 from .boxes import BoxProcessorCraftB200
 from .document import TrOcrProcessorB200
 from .pipeline import PSM_PRESETS, records_to_words
+from .ingest import hash_frames_fast
 from .plugin_api import CoordinateFormat, PSMode, assemble_result
 
 
@@ -35,6 +38,7 @@ class OcrEngineB200:
         self.box_processor = box_processor
         self.icr_processor = default_ocr_processor
         self.has_cuda = cuda
+        self.bbox_cache = {}      # region overlay hash -> extract_bounding_boxes result (ocr_engine.py:20-25,324-336)
 
     def extract(self, frames, pms_mode=PSMode.SPARSE, coordinate_format=CoordinateFormat.XYWH, regions=None,
                 queue_id=None, **kwargs):
@@ -44,7 +48,7 @@ class OcrEngineB200:
             frames = [frames]
         ro_frames = copy_frames(frames)
         if len(regions):
-            raise NotImplementedError("region extraction (ocr_engine.py:223-414) is listed as 'next' in SURVEY.md §8f")
+            return self._extract_regions(ro_frames, queue_id, hash_frames_fast(ro_frames), pms_mode, regions)
         batched = (isinstance(self.box_processor, BoxProcessorCraftB200) and isinstance(self.icr_processor, TrOcrProcessorB200)
                    and self.box_processor.pipeline is self.icr_processor.pipeline
                    and pms_mode in (PSMode.SPARSE, PSMode.LINE, PSMode.MULTI_LINE)
@@ -87,6 +91,53 @@ class OcrEngineB200:
             self._finish(result, i, lines, [], coordinate_format)
             results.append(result)
         return results
+
+    # region / field extraction (__process_extract_regions, ocr_engine.py:223-414): every region is cropped, padded
+    # with 4 white pixels, run through the box processor in its own PSM (cached by content), and the fragments of a
+    # page go through ONE recognize() call.  Quirks kept as they are in the reference: region ids are recorded before
+    # the zero-size / out-of-bounds checks (so a skipped region makes the page fall back to empty results), the
+    # box-result list is not reset between pages, and words are matched to region ids in their x-sorted order.
+    def _extract_regions(self, frames, queue_id, checksum, pms_mode, regions):
+        output, extended = [], []
+        for region in regions:
+            if not all(k in region for k in ("id", "pageIndex", "x", "y", "w", "h")):
+                raise Exception(f"Required key missing in region : {region}")
+        pages = {}
+        for region in regions:
+            pages.setdefault(region["pageIndex"], []).append(region)
+        bbox_results_batch = []
+        for page_index, page_regions in pages.items():
+            img = frames[page_index]
+            xb, yb, wb, hb = img.shape[1], img.shape[0], 0, 0
+            region_ids = []
+            for region in page_regions:
+                rid = region["id"]
+                region_ids.append(rid)
+                x, y, w, h = region["x"], region["y"], region["w"], region["h"]
+                if w == 0 or h == 0 or y + h > img.shape[0] or x + w > img.shape[1]:
+                    output.append({"id": rid, "text": "", "confidence": 0.0})
+                    continue
+                xb, yb = min(x, xb), min(y, yb)
+                wb = max(x + w, xb + wb) - xb
+                hb = max(y + h, hb + yb) - yb
+                overlay = np.full((h + 8, w + 8, 3), 255, np.uint8)
+                overlay[4:h + 4, 4:w + 4] = img[y:y + h, x:x + w]
+                mode = PSMode.from_value(region["mode"]) if "mode" in region else pms_mode
+                key = (mode.value, overlay.shape, hash_frames_fast([overlay]))
+                if key not in self.bbox_cache:
+                    self.bbox_cache[key] = self.box_processor.extract_bounding_boxes(queue_id, checksum, overlay, psm=mode)
+                bbox_results_batch.append(self.bbox_cache[key])
+            batch_crop = img[yb:yb + hb, xb:xb + wb]
+            boxes, fragments, lines, _, _ = (list(chain.from_iterable(x)) for x in zip(*bbox_results_batch))
+            batch_result, _ = self.icr_processor.recognize(queue_id, checksum, batch_crop, boxes, fragments, lines)
+            extended.append(batch_result)
+            if "words" in batch_result and len(batch_result["words"]) == len(region_ids):
+                for word, rid in zip(batch_result["words"], region_ids):
+                    output.append({"id": rid, "text": word["text"], "confidence": word["confidence"]})
+            else:
+                for rid in region_ids:
+                    output.append({"id": rid, "text": "", "confidence": 0.0})
+        return {"regions": output, "extended": extended}
 
     @staticmethod
     def _finish(result, page, lines, line_bboxes, coordinate_format):

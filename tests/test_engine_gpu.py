@@ -107,3 +107,37 @@ def test_engine_batched_equals_pagewise(engine):
     blank = np.full_like(pages[0], 255)
     r = eng.extract([blank, pages[0]])
     assert r[0]["words"] == [] and len(r[1]["words"]) == len(a[0]["words"])
+
+
+def test_engine_regions(engine):
+    """Region / field extraction (ocr_engine.py:223-414): per-region PSM, 4 px padding, one recognize() per page, the
+    {"regions", "extended"} payload; results equal recognising the padded region directly."""
+    from marie_icr_b200.plugin_api import PSMode
+    eng, pages, _, _, _ = engine
+    page = pages[0]
+    rects, _, _, _, _ = eng.box_processor.extract_bounding_boxes("id", "key", page)
+    picks = [rects[3], rects[7], rects[12]]
+    regions = [{"id": f"r{k}", "pageIndex": 0, "x": int(x), "y": int(y), "w": int(w), "h": int(h), "mode": "raw_line"}
+               for k, (x, y, w, h) in enumerate(picks)]
+    res = eng.extract([page], PSMode.SPARSE, regions=regions)
+    assert set(res) == {"regions", "extended"} and len(res["regions"]) == 3 and len(res["extended"]) == 1
+    direct = []
+    for (x, y, w, h) in picks:
+        ov = np.full((h + 8, w + 8, 3), 255, np.uint8)
+        ov[4:h + 4, 4:w + 4] = page[y:y + h, x:x + w]
+        direct.append(eng.icr_processor.recognize_from_fragments([ov])[0])
+    # all region boxes are [0, 0, w+8, h+8]: the x-sort is a no-op, so ids map in order
+    for r, d, reg in zip(res["regions"], direct, regions):
+        assert r["id"] == reg["id"] and r["text"] == d["text"] and abs(r["confidence"] - round(d["confidence"], 3)) < 1e-9
+    # second call hits the box cache and returns the same payload
+    assert eng.extract([page], PSMode.SPARSE, regions=regions)["regions"] == res["regions"]
+    # a page whose regions are ALL skipped (zero size / out of bounds) leaves nothing to unpack: the reference raises
+    # ValueError at ocr_engine.py:343-351, and so does the mirror
+    with pytest.raises(ValueError):
+        eng.extract([page], regions=[{"id": "z", "pageIndex": 0, "x": 0, "y": 0, "w": 0, "h": 5}])
+    # ... while a skipped region next to a valid one yields empty results for the whole page (ids are recorded before
+    # the checks, so the word count no longer matches; ocr_engine.py:262-282,383-394)
+    mixed = eng.extract([page], regions=[{"id": "z", "pageIndex": 0, "x": 0, "y": 0, "w": 0, "h": 5}, regions[0]])
+    assert [r["id"] for r in mixed["regions"]] == ["z", "z", "r0"] and all(r["text"] == "" for r in mixed["regions"])
+    with pytest.raises(Exception, match="Required key missing"):
+        eng.extract([page], regions=[{"id": "q", "pageIndex": 0, "x": 1}])

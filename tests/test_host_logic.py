@@ -101,3 +101,27 @@ def test_processors_refuse_cpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no cuda devices"):
             TrOcrProcessorB200(cuda=True)
+
+
+def test_ensure_max_page_size_known_answers():
+    """The reference's own known-answer tests for the step before the path (tests/imaging/test_image_resizing.py:7-47)."""
+    from marie_icr_b200.ingest import ensure_max_page_size, hash_frames_fast, max_page_dims
+    rng = np.random.default_rng(0)
+    f = rng.integers(0, 255, (3200, 2550), dtype=np.uint8)
+    changed, frames = ensure_max_page_size([f], expand_ratio=0)
+    assert changed is False and frames[0].shape == (3200, 2550)
+    f = rng.integers(0, 255, (3200, 2600), dtype=np.uint8)
+    changed, frames = ensure_max_page_size([f], expand_ratio=0)
+    assert changed and frames[0].shape == (3138, 2550)
+    changed, frames = ensure_max_page_size([f])
+    assert changed is False and frames[0].shape == (3200, 2600)
+    f = rng.integers(0, 255, (4171, 2569), dtype=np.uint8)
+    changed, frames = ensure_max_page_size([f])
+    # the reference's own test expects (3200, 2600) here (test_max_page_001), but the reference FUNCTION returns
+    # (3795, 2337) — verified by executing marie/utils/image_utils.py:254-321 itself; we follow the function
+    assert changed is True and frames[0].shape == (3795, 2337)
+    assert max_page_dims(5000, 3000) == (3795, 2277)          # landscape: limits swapped, width-bound
+    assert max_page_dims(2000, 1000) is None
+    a = rng.integers(0, 255, (70, 90, 3), dtype=np.uint8)
+    import hashlib
+    assert hash_frames_fast([a, a[:10]]) == hashlib.md5(a.tobytes() + a[:10].tobytes()).hexdigest()
