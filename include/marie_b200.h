@@ -69,6 +69,12 @@ int mb_gemm16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, 
                  int M, int N, int K, const float* bias_dev, int act, const void* residual_dev,
                  long long res_ld, void* out_dev, long long out_ld, int out_mode, void* stream);
 
+/* Block-diagonal variant: batch b uses A columns [b*a_col_stride, +K), weight rows [b*w_row_stride, +N) and writes
+ * output / bias columns [b*out_col_stride, +N) — the per-head projections of the decoder's cross-attention. */
+int mb_gemm16_batched(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w, int M, int N, int K,
+                      int batches, int a_col_stride, int w_row_stride, int out_col_stride, const float* bias_dev, int act,
+                      void* out_dev, long long out_ld, void* stream);
+
 /* NHWC convolution as implicit GEMM (taps = 1: 1x1; taps = 9: 3x3 with padding = dilation).  Input is the
  * channel-concatenation of up to two NHWC tensors (the U-Net `torch.cat`, marie/models/craft/craft.py:64-77).
  * Weights are [n_rows_w, taps*(c0+c1)] with k = (ky*3+kx)*(c0+c1) + c.  Replaces cuDNN behind nn.Conv2d in

@@ -94,6 +94,9 @@ struct TapGemm {
     const bf16* residual = nullptr; int res_ld = 0;  // added after activation
     void* out = nullptr; long long out_ld = 0; int out_mode = MB_OUT_BF16;
     long long out_plane = 0;      // MB_OUT_F32_PLANAR: elements between channel planes
+    // block-diagonal batches (per-head projections): batch b reads A columns [b*a_col_stride, +c0), weight rows
+    // [b*w_row_stride, +n_out) and writes output / bias / residual columns [b*out_col_stride, +n_out)
+    int batches = 1, a_col_stride = 0, w_row_stride = 0, out_col_stride = 0;
 };
 int mb_tap_gemm(mb_ctx* ctx, const TapGemm& p, cudaStream_t stream);
 void mb_profile_drain(mb_ctx* ctx);

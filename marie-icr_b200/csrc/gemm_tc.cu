@@ -50,6 +50,7 @@ struct KParams {
     int out_mode;
     long long out_plane;
     int f16;               // operand / 16-bit output element type: 0 = bf16, 1 = fp16
+    int batches, a_col_stride, w_row_stride, out_col_stride;   // block-diagonal (per-head) GEMMs
     unsigned int* diag;
 };
 
@@ -127,7 +128,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     tcgen05_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_per_batch * p.batches;
     const int kb_per_tap = p.kb0 + p.kb1;
     const int k_iters = p.taps * kb_per_tap;
 
@@ -138,13 +140,16 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             uint32_t phase = 0;
             const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
-                const int mt = tile / p.n_tiles;
+                const int bt = tile / tiles_per_batch;
+                const int trem = tile - bt * tiles_per_batch;
+                const int nt = trem % p.n_tiles;
+                const int mt = trem / p.n_tiles;
                 const int wt = mt % p.w_tiles;
                 const int rest = mt / p.w_tiles;
                 const int hh = rest % p.h;
                 const int nn = rest / p.h;
                 const int w0 = wt * BLOCK_M;
+                const int acol = bt * p.a_col_stride, wrow = bt * p.w_row_stride;
                 for (int tap = 0; tap < p.taps; ++tap) {
                     const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
                     const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
@@ -155,10 +160,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                         const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
                         if (kb < p.kb0)
-                            tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K, w0 + dx, hh + dy, nn);
+                            tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K + acol, w0 + dx, hh + dy, nn);
                         else
                             tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 + dx, hh + dy, nn);
-                        tma_load_2d(sb, &tmB, fb, (tap * kb_per_tap + kb) * BLOCK_K, nt * p.block_n);
+                        tma_load_2d(sb, &tmB, fb, (tap * kb_per_tap + kb) * BLOCK_K, nt * p.block_n + wrow);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -216,12 +221,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles;
-            const int mt = tile / p.n_tiles;
+            const int bt = tile / tiles_per_batch;
+            const int trem = tile - bt * tiles_per_batch;
+            const int nt = trem % p.n_tiles;
+            const int mt = trem / p.n_tiles;
             const int wt = mt % p.w_tiles;
             const int rest = mt / p.w_tiles;
             const int hh = rest % p.h;
             const int nn = rest / p.h;
+            const int nbase = bt * p.out_col_stride;                // output / bias / residual column of this batch
             const int row0 = wt * BLOCK_M + q * 32;                 // first tile row (pixel) of this warp
             const long long pix0 = ((long long)nn * p.h + hh) * p.w + row0;
             const int rows_valid = min(32, p.w - row0);             // may be <= 0 for a ragged last tile
@@ -237,7 +245,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const int n0c = nt * p.block_n + ci * 32;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    rres[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + (pix0 + i * 4 + rr) * p.res_ld + n0c + kk * 4));
+                    rres[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + (pix0 + i * 4 + rr) * p.res_ld + nbase + n0c + kk * 4));
             };
             if (RES && chunk_fast(half)) load_res(half);
             mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
@@ -259,8 +267,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         for (int j = 0; j < 32; ++j) {
                             if (j < ncols) {
                                 float x = __uint_as_float(v[j]);
-                                if (p.bias != nullptr) x += __ldg(p.bias + n0 + j);
-                                o[(long long)(n0 + j) * p.out_plane] = apply_act<ACT>(x);
+                                if (p.bias != nullptr) x += __ldg(p.bias + nbase + n0 + j);
+                                o[(long long)(nbase + n0 + j) * p.out_plane] = apply_act<ACT>(x);
                             }
                         }
                     }
@@ -281,7 +289,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         // phase B: lanes run along the row (8 lanes x 4 columns, 4 rows per pass): bias once per chunk,
                         // activation, residual, pack, coalesced store
                         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + kk);
+                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + n0) + kk);
                         float4 xs[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -301,23 +309,23 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             const int r = i * 4 + rr;
                             const float4 x = xs[i];
                             if (OUT == MB_OUT_BF16)
-                                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) =
+                                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + nbase + n0 + kk * 4) =
                                     make_uint2(pack2t<F16>(x.x, x.y), pack2t<F16>(x.z, x.w));
                             else
-                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (pix0 + r) * p.out_ld + n0 + kk * 4) = x;
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (pix0 + r) * p.out_ld + nbase + n0 + kk * 4) = x;
                         }
                     } else {
                         // ragged chunk (last rows / last columns / unaligned pitch): one element per lane and row
-                        const float bl = (p.bias != nullptr && lane < ncols) ? __ldg(p.bias + n0 + lane) : 0.f;
+                        const float bl = (p.bias != nullptr && lane < ncols) ? __ldg(p.bias + nbase + n0 + lane) : 0.f;
 #pragma unroll 1
                         for (int r = 0; r < rows_valid; ++r) {
                             if (lane < ncols) {
                                 float x = apply_act<ACT>(stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))] + bl);
-                                if (RES) x += load16(p.residual + (pix0 + r) * p.res_ld + n0 + lane, F16);
+                                if (RES) x += load16(p.residual + (pix0 + r) * p.res_ld + nbase + n0 + lane, F16);
                                 if (OUT == MB_OUT_BF16)
-                                    store16(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + n0 + lane, x, F16);
+                                    store16(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + nbase + n0 + lane, x, F16);
                                 else
-                                    reinterpret_cast<float*>(p.out)[(pix0 + r) * p.out_ld + n0 + lane] = x;
+                                    reinterpret_cast<float*>(p.out)[(pix0 + r) * p.out_ld + nbase + n0 + lane] = x;
                             }
                         }
                     }
@@ -456,7 +464,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     }
     if (g.block_n == 0) {
         // small problems (decoder steps): shrink the N tile until the grid covers the SMs
-        const long long m_tiles = (long long)g.n * g.h * mb_cdiv(g.w, BLOCK_M);
+        const long long m_tiles = (long long)g.n * g.h * mb_cdiv(g.w, BLOCK_M) * (g.batches > 0 ? g.batches : 1);
         while (block_n > 64 && m_tiles * mb_cdiv(g.n_out, block_n) < ctx->num_sms) block_n >>= 1;
     }
     MB_REQUIRE(ctx, block_n % 16 == 0 && block_n >= 16 && block_n <= 256, "tap_gemm: bad block_n %d", block_n);
@@ -479,10 +487,12 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.residual = g.residual; p.res_ld = g.res_ld;
     p.out = g.out; p.out_ld = g.out_ld; p.out_mode = g.out_mode; p.out_plane = g.out_plane;
     p.f16 = ctx->f16;
+    p.batches = g.batches > 0 ? g.batches : 1;
+    p.a_col_stride = g.a_col_stride; p.w_row_stride = g.w_row_stride; p.out_col_stride = g.out_col_stride;
     p.diag = ctx->dev_diag;
 
     CUtensorMap tmA0, tmA1, tmB;
-    int rc = encode_act_map(ctx, &tmA0, g.a0, g.c0, g.a0_ld, g.n, g.h, g.w, ctx->f16);
+    int rc = encode_act_map(ctx, &tmA0, g.a0, g.batches > 1 ? g.a0_ld : g.c0, g.a0_ld, g.n, g.h, g.w, ctx->f16);
     if (rc) return rc;
     if (g.c1 > 0) {
         MB_REQUIRE(ctx, g.a1 != nullptr, "tap_gemm: c1>0 but a1 null");
@@ -512,7 +522,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         return mb_set_err(ctx, MB_ERR_ARG, "tap_gemm: unsupported epilogue (act %d, out_mode %d, residual %d)", g.act,
                           g.out_mode, (int)res);
     MB_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    const long long total = (long long)p.m_tiles * p.n_tiles;
+    const long long total = (long long)p.m_tiles * p.n_tiles * p.batches;
     const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profile) {
@@ -545,6 +555,22 @@ extern "C" int mb_gemm16(mb_ctx* ctx, const void* a_dev, long long lda, const vo
     g.bias = bias_dev; g.act = act;
     g.residual = (const bf16*)residual_dev; g.res_ld = (int)res_ld;
     g.out = out_dev; g.out_ld = out_ld; g.out_mode = out_mode;
+    return mb_tap_gemm(ctx, g, (cudaStream_t)stream);
+}
+
+// Block-diagonal GEMM: for batch b, out[:, b*out_col_stride + n] = act(A[:, b*a_col_stride : +K] @ W[b*w_row_stride + n, :K]^T
+// + bias[b*out_col_stride + n]).  Used for the per-head projections of the decoder's cross-attention (trocr.cu).
+extern "C" int mb_gemm16_batched(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w, int M,
+                                 int N, int K, int batches, int a_col_stride, int w_row_stride, int out_col_stride,
+                                 const float* bias_dev, int act, void* out_dev, long long out_ld, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    TapGemm g;
+    g.a0 = (const bf16*)a_dev; g.c0 = K; g.a0_ld = (int)lda;
+    g.n = 1; g.h = 1; g.w = M;
+    g.wgt = (const bf16*)w_dev; g.n_rows_w = n_rows_w; g.n_out = N;
+    g.bias = bias_dev; g.act = act;
+    g.out = out_dev; g.out_ld = out_ld; g.out_mode = MB_OUT_BF16;
+    g.batches = batches; g.a_col_stride = a_col_stride; g.w_row_stride = w_row_stride; g.out_col_stride = out_col_stride;
     return mb_tap_gemm(ctx, g, (cudaStream_t)stream);
 }
 

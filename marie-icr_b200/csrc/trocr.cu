@@ -35,7 +35,7 @@ struct EncLayer {
     const bf16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
 };
 struct DecLayer {
-    const bf16 *sqkv_w, *sout_w, *cq_w, *ckv_w, *cout_w, *fc1_w, *fc2_w;
+    const bf16 *sqkv_w, *sout_w, *cq_w, *ckv_w, *ckT_w, *cout_w, *fc1_w, *fc2_w;
     const float *sqkv_b, *sout_b, *cq_b, *ckv_b, *cout_b, *fc1_b, *fc2_b;
     const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
 };
@@ -359,6 +359,157 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
         if (q0 + r < Tq)
             *reinterpret_cast<uint4*>(out + (img * Tq + q0 + r) * o_ld + head * DH + c * 8) =
                 *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ greedy cross-attention
+// Cross-attention of a greedy (beam 1) decode step WITHOUT a K/V cache.  The cached form reads K and V = 2 x 577 x 1024
+// 16-bit values per crop and layer every step (2.36 MB; HBM-bound, ~60 % of a decode step).  Since
+//   score_t^h = q^h . (Wk^h e_t + bk^h) = (Wk^h^T q^h) . e_t + const      (the constant cancels in the softmax)
+//   out^h     = sum_t p_t (Wv^h e_t + bv^h) = Wv^h (sum_t p_t e_t) + bv^h
+// the step can attend over the ENCODER STATES e_t themselves (577 x E, 0.89 MB for E = 768) with per-head projected
+// queries q'^h = Wk^h^T q^h in R^E: 2.7x fewer bytes per layer, no per-crop K/V precompute (12 GEMMs per chunk) and no
+// 29 GB cache.  The two per-head projections are block-diagonal tap-GEMMs (gemm_tc.cu, `batches`).
+// This kernel: one CTA per crop, the 16 heads are the 16 rows of an m16n8k16 tile; 4 warps split the E dimension (8 warps measured slower: the redundant per-warp softmax and the larger partial-score reduction outweigh the extra latency hiding)
+// (scores: partial sums reduced through shared memory; context: each warp owns E/4 output columns); encoder rows are
+// streamed in 32-key tiles through a cp.async ring.  qp, ctx: [rows, 16*E]; enc: [rows*T, E].
+constexpr int XE_KEYS = 32;
+template <bool F16, int ESLICE, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) dec_cross_enc_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ enc,
+                                                                bf16* __restrict__ ctxo, int T, int heads) {
+    constexpr int E = ESLICE * WARPS;
+    constexpr int NT = WARPS * 32;
+    constexpr int ROWB = E * 2;                       // bytes per smem row
+    constexpr int NB = ESLICE / 8;                    // 8-wide output blocks per warp
+    extern __shared__ __align__(128) unsigned char xe_smem[];
+    unsigned char* sQ = xe_smem;                      // [16][E]
+    unsigned char* sE = sQ + 16 * ROWB;               // STAGES x [32][E]
+    float* sS = reinterpret_cast<float*>(sE + STAGES * XE_KEYS * ROWB);   // [WARPS][16][32] partial scores
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long crop = blockIdx.x;
+    const bf16* qbase = qp + crop * heads * E;     // heads <= 16 rows; the rest of the m16 tile is zero
+    const bf16* ebase = enc + crop * T * E;
+    const int n_tiles = (T + XE_KEYS - 1) / XE_KEYS;
+    auto swz_w = [](int row, int chunk) { return row * ROWB + ((chunk ^ (row & 7)) << 4); };
+    auto load_rows = [&](unsigned char* dst, const bf16* src, int rows, int row0, int limit) {
+        const int chunks = rows * (E / 8);
+        for (int idx = tid; idx < chunks; idx += NT) {
+            const int r = idx / (E / 8), c = idx - r * (E / 8);
+            const bool ok = row0 + r < limit;
+            cp_async16(smem_addr(dst + swz_w(r, c)), src + (long long)(ok ? row0 + r : 0) * E + c * 8, ok);
+        }
+    };
+    load_rows(sQ, qbase, 16, 0, heads);
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; ++st) {
+        if (st < n_tiles) load_rows(sE + st * XE_KEYS * ROWB, ebase, XE_KEYS, st * XE_KEYS, T);
+        cp_async_commit();
+    }
+    float o[NB][4];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int g = lane >> 2, tg = lane & 3;
+    const int cbase = warp * (ESLICE / 8);            // first 16-byte chunk of this warp's E slice
+    for (int j = 0; j < n_tiles; ++j) {
+        unsigned char* tile = sE + (j % STAGES) * XE_KEYS * ROWB;
+        {
+            const int jn = j + STAGES - 1;
+            if (jn < n_tiles) load_rows(sE + (jn % STAGES) * XE_KEYS * ROWB, ebase, XE_KEYS, jn * XE_KEYS, T);
+            cp_async_commit();
+        }
+        cp_async_wait<STAGES - 1>();
+        __syncthreads();
+        // partial scores over this warp's slice of E: S[16 heads x 32 keys]
+        float s[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
+#pragma unroll
+        for (int kp = 0; kp < ESLICE / 32; ++kp) {
+            uint32_t a0[4], a1[4];
+            {
+                const int r = (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = cbase + kp * 4 + (lane >> 4);
+                ldsm_x4(smem_addr(sQ + swz_w(r, c)), a0[0], a0[1], a0[2], a0[3]);
+                ldsm_x4(smem_addr(sQ + swz_w(r, c + 2)), a1[0], a1[1], a1[2], a1[3]);
+            }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(smem_addr(tile + swz_w(nb * 8 + (lane & 7), cbase + kp * 4 + (lane >> 3))), b0, b1, b2, b3);
+                mma16816<F16>(s[nb], a0, b0, b1);
+                mma16816<F16>(s[nb], a1, b2, b3);
+            }
+        }
+        float* mine = sS + warp * 16 * 32;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            *reinterpret_cast<float2*>(mine + g * 32 + nb * 8 + tg * 2) = make_float2(s[nb][0], s[nb][1]);
+            *reinterpret_cast<float2*>(mine + (g + 8) * 32 + nb * 8 + tg * 2) = make_float2(s[nb][2], s[nb][3]);
+        }
+        __syncthreads();
+        const int key0 = j * XE_KEYS + tg * 2;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const float2 u0 = *reinterpret_cast<const float2*>(sS + w * 512 + g * 32 + nb * 8 + tg * 2);
+                const float2 u1 = *reinterpret_cast<const float2*>(sS + w * 512 + (g + 8) * 32 + nb * 8 + tg * 2);
+                t0.x += u0.x; t0.y += u0.y; t1.x += u1.x; t1.y += u1.y;
+            }
+            const int k = key0 + nb * 8;
+            s[nb][0] = k < T ? t0.x : -INFINITY; s[nb][1] = k + 1 < T ? t0.y : -INFINITY;
+            s[nb][2] = k < T ? t1.x : -INFINITY; s[nb][3] = k + 1 < T ? t1.y : -INFINITY;
+        }
+        float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+        float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+        mx0 = fmaxf(mx0, fmaxf(fmaxf(s[2][0], s[2][1]), fmaxf(s[3][0], s[3][1])));
+        mx1 = fmaxf(mx1, fmaxf(fmaxf(s[2][2], s[2][3]), fmaxf(s[3][2], s[3][3])));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float L2E = 1.4426950408889634f;
+        if (__any_sync(0xffffffffu, mn0 != m0 || mn1 != m1)) {
+            const float c0 = fast_exp2((m0 - mn0) * L2E), c1 = fast_exp2((m1 - mn1) * L2E);
+            l0 *= c0; l1 *= c1;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+            m0 = mn0; m1 = mn1;
+        }
+        uint32_t ap[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            const float p0 = fast_exp2((s[nb][0] - mn0) * L2E), p1 = fast_exp2((s[nb][1] - mn0) * L2E);
+            const float p2 = fast_exp2((s[nb][2] - mn1) * L2E), p3 = fast_exp2((s[nb][3] - mn1) * L2E);
+            l0 += p0 + p1; l1 += p2 + p3;
+            ap[nb >> 1][(nb & 1) * 2] = pack2(p0, p1, F16);
+            ap[nb >> 1][(nb & 1) * 2 + 1] = pack2(p2, p3, F16);
+        }
+        // context slice: O[16 x ESLICE] += P[16 x 32] . E[32 x ESLICE]
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+            for (int dp = 0; dp < NB / 2; ++dp) {
+                uint32_t b0, b1, b2, b3;
+                const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                ldsm_x4_t(smem_addr(tile + swz_w(r, cbase + dp * 2 + (lane >> 4))), b0, b1, b2, b3);
+                mma16816<F16>(o[dp * 2], ap[kk], b0, b1);
+                mma16816<F16>(o[dp * 2 + 1], ap[kk], b2, b3);
+            }
+        }
+        __syncthreads();   // tile and sS are free for the next iteration
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    bf16* obase = ctxo + crop * heads * E + warp * ESLICE;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        if (g < heads)
+            *reinterpret_cast<uint32_t*>(obase + (long long)g * E + nb * 8 + tg * 2) = pack2(o[nb][0] * i0, o[nb][1] * i0, F16);
+        if (g + 8 < heads)
+            *reinterpret_cast<uint32_t*>(obase + (long long)(g + 8) * E + nb * 8 + tg * 2) = pack2(o[nb][2] * i1, o[nb][3] * i1, F16);
     }
 }
 
@@ -740,16 +891,33 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
 
 struct DecodeWs {
     bf16 *cross_kv, *kcache, *vcache, *x, *qkv, *att, *tmp, *ffn;
+    bf16 *qp, *ctxe;              // greedy mode: per-head projected queries / attended encoder states [R, heads*E]
+    bool greedy;
     float* logits; float* cand_val; int* cand_idx;
     SearchState st;
 };
+
+// beam 1 attends over the encoder states directly (dec_cross_enc_kernel); MB_CROSS_CACHED=1 forces the K/V-cache path
+bool cross_uncached(const TrocrModel* m, int beam) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("MB_CROSS_CACHED"); forced = (e && e[0] == '1') ? 1 : 0; }
+    return beam == 1 && !forced && m->dec_heads <= 16 && (m->enc_dim == 128 || m->enc_dim == 768 || m->enc_dim == 1024);
+}
 
 size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* base, DecodeWs* w) {
     Arena a{base, 0, 0};
     const int H = m->dec_dim, T = m->tokens, L = m->dec_layers, V = m->vocab;
     const long long R = (long long)n * beam;
     const int cand = 2 * beam;
-    w->cross_kv = a.take<bf16>((size_t)L * n * T * 2 * H);
+    w->greedy = cross_uncached(m, beam);
+    if (w->greedy) {
+        w->cross_kv = nullptr;
+        w->qp = a.take<bf16>((size_t)R * m->dec_heads * m->enc_dim);
+        w->ctxe = a.take<bf16>((size_t)R * m->dec_heads * m->enc_dim);
+    } else {
+        w->qp = w->ctxe = nullptr;
+        w->cross_kv = a.take<bf16>((size_t)L * n * T * 2 * H);
+    }
     w->kcache = a.take<bf16>((size_t)L * (max_len + 1) * R * H);
     w->vcache = a.take<bf16>((size_t)L * (max_len + 1) * R * H);
     w->x = a.take<bf16>(R * H);
@@ -777,7 +945,44 @@ size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* b
 }
 
 // one decoder step for all R rows: tokens[:, step] -> logits [R, V]
-int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, int n, int beam, int step, int max_len, cudaStream_t s) {
+template <bool F16, int ESLICE, int WARPS, int STAGES>
+int launch_cross_enc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* ctxe, int n, int T, int heads, cudaStream_t s) {
+    const size_t smem = (size_t)(16 + STAGES * XE_KEYS) * ESLICE * WARPS * 2 + WARPS * 16 * 32 * sizeof(float);
+    static bool done = false;
+    if (!done) {
+        MB_CUDA(ctx, cudaFuncSetAttribute(dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES><<<n, WARPS * 32, smem, s>>>(qp, enc, ctxe, T, heads);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// greedy cross-attention of one layer: q [R, H] (in w.qkv) -> w.att [R, H]
+int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer& L, const bf16* enc_out, int n, cudaStream_t s) {
+    const int H = m->dec_dim, E = m->enc_dim, heads = m->dec_heads, T = m->tokens;
+    TapGemm g;                                    // q'^h = Wk^h^T q^h  : [R, heads*E]
+    g.a0 = w.qkv; g.c0 = DH; g.a0_ld = H; g.n = 1; g.h = 1; g.w = n;
+    g.wgt = L.ckT_w; g.n_rows_w = heads * E; g.n_out = E;
+    g.out = w.qp; g.out_ld = (long long)heads * E; g.out_mode = MB_OUT_BF16;
+    g.batches = heads; g.a_col_stride = DH; g.w_row_stride = E; g.out_col_stride = E;
+    RC(mb_tap_gemm(ctx, g, s));
+    int rc;
+    if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 192, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
+    else if (E == 1024) rc = ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
+    else if (E == 128) rc = ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
+    else return mb_set_err(ctx, MB_ERR_STATE, "cross_enc_attention: unsupported encoder width %d", E);
+    if (rc) return rc;
+    TapGemm v;                                    // att^h = Wv^h ctx^h + bv^h : [R, H]
+    v.a0 = w.ctxe; v.c0 = E; v.a0_ld = heads * E; v.n = 1; v.h = 1; v.w = n;
+    v.wgt = L.ckv_w + (size_t)H * E; v.n_rows_w = H; v.n_out = DH;
+    v.bias = L.ckv_b + H;
+    v.out = w.att; v.out_ld = H; v.out_mode = MB_OUT_BF16;
+    v.batches = heads; v.a_col_stride = E; v.w_row_stride = DH; v.out_col_stride = DH;
+    return mb_tap_gemm(ctx, v, s);
+}
+
+int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const bf16* enc_out, int n, int beam, int step, int max_len, cudaStream_t s) {
     const int H = m->dec_dim, T = m->tokens, F = m->dec_ffn, V = m->vocab;
     const int R = n * beam;
     dec_embed_kernel<<<R, 128, 0, s>>>(w.st.tokens, max_len + 2, step, m->embed, m->pe, w.x, R, H, sqrtf((float)H), ctx->f16);
@@ -792,7 +997,9 @@ int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, int n, int beam, int s
         RC(gemm(ctx, w.att, H, L.sout_w, H, R, H, L.sout_b, MB_ACT_NONE, w.x, w.tmp, MB_OUT_BF16, s));
         RC(layernorm(ctx, w.tmp, w.x, L.ln1_w, L.ln1_b, R, H, 1e-5f, s));
         RC(gemm(ctx, w.x, H, L.cq_w, H, R, H, L.cq_b, MB_ACT_NONE, nullptr, w.qkv, MB_OUT_BF16, s));
-        {
+        if (w.greedy) {
+            RC(cross_enc_attention(ctx, m, w, L, enc_out, n, s));
+        } else {
             // all beams of a crop share one pass over the crop's cached K/V (q is pre-scaled: weights carry d^-0.5)
             const bf16* kvl = w.cross_kv + (size_t)l * n * T * 2 * H;
             dim3 grid(1, m->dec_heads, n);
@@ -814,8 +1021,8 @@ int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, int n, int beam, int s
 int decode_prepare(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const bf16* enc_out, int n, int beam, int max_len,
                    cudaStream_t s) {
     const int H = m->dec_dim, T = m->tokens, D = m->enc_dim;
-    // static cross-attention K/V, once per crop (not per beam): [n*T, 2H] per layer
-    for (int l = 0; l < m->dec_layers; ++l)
+    // static cross-attention K/V, once per crop (not per beam): [n*T, 2H] per layer — not needed in greedy mode
+    for (int l = 0; l < m->dec_layers && !w.greedy; ++l)
         RC(gemm(ctx, enc_out, D, m->dec[l].ckv_w, 2 * H, (long long)n * T, 2 * H, m->dec[l].ckv_b, MB_ACT_NONE, nullptr,
                 w.cross_kv + (size_t)l * n * T * 2 * H, MB_OUT_BF16, s));
     const int R = n * beam;
@@ -885,7 +1092,7 @@ extern "C" int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes) 
         const std::string p = "dec.L" + std::to_string(i) + ".";
         DecLayer& L = m->dec[i];
         L.sqkv_w = W(p + "self.qkv.w"); L.sqkv_b = Fp(p + "self.qkv.b"); L.sout_w = W(p + "self.out.w"); L.sout_b = Fp(p + "self.out.b");
-        L.cq_w = W(p + "cross.q.w"); L.cq_b = Fp(p + "cross.q.b"); L.ckv_w = W(p + "cross.kv.w"); L.ckv_b = Fp(p + "cross.kv.b");
+        L.cq_w = W(p + "cross.q.w"); L.cq_b = Fp(p + "cross.q.b"); L.ckv_w = W(p + "cross.kv.w"); L.ckv_b = Fp(p + "cross.kv.b"); L.ckT_w = W(p + "cross.kT.w");
         L.cout_w = W(p + "cross.out.w"); L.cout_b = Fp(p + "cross.out.b");
         L.fc1_w = W(p + "fc1.w"); L.fc1_b = Fp(p + "fc1.b"); L.fc2_w = W(p + "fc2.w"); L.fc2_b = Fp(p + "fc2.b");
         L.ln1_w = Fp(p + "ln1.w"); L.ln1_b = Fp(p + "ln1.b"); L.ln2_w = Fp(p + "ln2.w"); L.ln2_b = Fp(p + "ln2.b");
@@ -969,7 +1176,7 @@ extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int 
     const int R = n * beam, cand = 2 * beam;
     int step = 0;
     for (; step <= max_len; ++step) {
-        RC(decoder_step(ctx, m, w, n, beam, step, max_len, s));
+        RC(decoder_step(ctx, m, w, (const bf16*)enc_out_dev, n, beam, step, max_len, s));
         logits_topk_kernel<<<R, TOPK_THREADS, 0, s>>>(w.logits, m->vocab, m->vocab, cand, step < 1, step >= max_len,
                                                      w.cand_val, w.cand_idx);
         MB_LAUNCH_CHECK(ctx);
@@ -1007,7 +1214,7 @@ extern "C" int mb_trocr_forced_logits(mb_ctx* ctx, const void* enc_out_dev, int 
     plan_decode(m, n, 1, L, (unsigned char*)m->arena, &w);
     RC(decode_prepare(ctx, m, w, (const bf16*)enc_out_dev, n, 1, L, s));
     for (int step = 0; step < L; ++step) {
-        RC(decoder_step(ctx, m, w, n, 1, step, L, s));
+        RC(decoder_step(ctx, m, w, (const bf16*)enc_out_dev, n, 1, step, L, s));
         MB_CUDA(ctx, cudaMemcpyAsync(logits_out_dev + (size_t)step * n * m->vocab, w.logits, (size_t)n * m->vocab * 4,
                                      cudaMemcpyDeviceToDevice, s));
         forced_step_kernel<<<mb_cdiv(n, 128), 128, 0, s>>>(w.st, w.logits, m->vocab, m->vocab, forced_dev, L, n, step, L);

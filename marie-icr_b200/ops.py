@@ -238,3 +238,13 @@ def attention16(qkv, n, T, scale=0.125, mode=0):
     _ctx(qkv).call("mb_attention16", ptr(qkv.contiguous()), ptr(out), c_int(n), c_int(T), c_int(D), c_float(scale),
                    c_int(mode), cur_stream())
     return out
+
+
+def gemm16_batched(a, w, batches, n, k, a_col_stride, w_row_stride, out_col_stride, out_cols, bias=None, act=ACT_NONE):
+    """Block-diagonal GEMM (see mb_gemm16_batched).  a [M, lda], w [rows, k] -> out [M, out_cols]."""
+    M = a.shape[0]
+    out = torch.zeros((M, out_cols), device=a.device, dtype=a.dtype)
+    _ctx(a).call("mb_gemm16_batched", ptr(a), c_ll(a.stride(0)), ptr(w), c_int(w.shape[0]), c_int(M), c_int(n), c_int(k),
+                 c_int(batches), c_int(a_col_stride), c_int(w_row_stride), c_int(out_col_stride), ptr(bias), c_int(act),
+                 ptr(out), c_ll(out.stride(0)), cur_stream())
+    return out

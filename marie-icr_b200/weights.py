@@ -155,6 +155,9 @@ def pack_trocr(state_dict, cfg, dtype=torch.float16):
         t[p + "cross.q.w"], t[p + "cross.q.b"] = (sd[ca + "q_proj.weight"] * sc).to(dtype), sd[ca + "q_proj.bias"] * sc
         t[p + "cross.kv.w"] = torch.cat([sd[ca + "k_proj.weight"], sd[ca + "v_proj.weight"]], 0).to(dtype)
         t[p + "cross.kv.b"] = torch.cat([sd[ca + "k_proj.bias"], sd[ca + "v_proj.bias"]], 0)
+        # per-head transposed key projection for the cache-free greedy cross-attention: row (h, j) = Wk[h*64:(h+1)*64, j]
+        wk = sd[ca + "k_proj.weight"]
+        t[p + "cross.kT.w"] = wk.view(H // 64, 64, wk.shape[1]).transpose(1, 2).reshape(-1, 64).to(dtype)
         t[p + "cross.out.w"], t[p + "cross.out.b"] = sd[ca + "out_proj.weight"].to(dtype), sd[ca + "out_proj.bias"]
         t[p + "fc1.w"], t[p + "fc1.b"] = sd[b + "fc1.weight"].to(dtype), sd[b + "fc1.bias"]
         t[p + "fc2.w"], t[p + "fc2.b"] = sd[b + "fc2.weight"].to(dtype), sd[b + "fc2.bias"]

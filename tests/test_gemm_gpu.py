@@ -80,3 +80,21 @@ def test_conv1x1_concat_and_planar(cuda_ctx, dtype16):
     ref2 = F.conv2d(x1.float().permute(0, 3, 1, 2), w2[:2].to(dtype16).float()[:, :, None, None], b2)
     assert planes.shape == (2, 1, h, w)
     assert (planes[:, 0] - ref2[0]).abs().max().item() < 2e-3 * ref2.abs().max().item() + 1e-4
+
+
+def test_gemm_block_diagonal(cuda_ctx, dtype16):
+    """Per-head projections: 16 batches, (K=64 -> N=768) and (K=768 -> N=64) with per-batch column / row offsets."""
+    from marie_icr_b200 import ops
+    torch.manual_seed(9)
+    R, H, E, heads = 300, 1024, 768, 16
+    q = torch.randn(R, H, device="cuda").to(dtype16)
+    wk = (torch.randn(heads * E, 64, device="cuda") * 0.125).to(dtype16)       # row (h, j): 64 inputs of head h
+    qp = ops.gemm16_batched(q, wk, heads, E, 64, 64, E, E, heads * E)
+    ref = torch.einsum("rhd,hjd->rhj", q.float().view(R, heads, 64), wk.float().view(heads, E, 64)).reshape(R, heads * E)
+    _close(qp, ref, "per-head K-side projection")
+    ctx = torch.randn(R, heads * E, device="cuda").to(dtype16)
+    wv = (torch.randn(H, E, device="cuda") * E ** -0.5).to(dtype16)
+    bias = torch.randn(H, device="cuda")
+    att = ops.gemm16_batched(ctx, wv, heads, 64, E, E, 64, 64, H, bias=bias)
+    ref2 = torch.einsum("rhe,hde->rhd", ctx.float().view(R, heads, E), wv.float().view(heads, 64, E)).reshape(R, H) + bias
+    _close(att, ref2, "per-head V-side projection")

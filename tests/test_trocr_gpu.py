@@ -171,3 +171,24 @@ def test_recognize_chunks_and_beam5(cuda_ctx):
     for i in range(11):
         n = int(l1[i])
         assert 2 <= n <= 21 and int(t1[i, n - 1]) == 2 and 1 not in t1[i, :n].tolist()
+
+
+def test_greedy_cross_attention_paths_agree(cuda_ctx):
+    """Greedy decoding uses the cache-free cross-attention (attend over encoder states with per-head projected queries);
+    forced logits of that path must match the oracle like the K/V-cache path does (beam >= 2 exercises the latter)."""
+    from marie_icr_b200 import ops
+    from oracle import trocr
+    cfg = trocr.trocr_tiny()
+    sd = _setup(cfg, torch.float16, 21)
+    patches, _ = _inputs(_fragments(7, seed=22), torch.float16)
+    enc_dev = ops.trocr_encode(patches)
+    enc = enc_dev.float().cpu()
+    with torch.no_grad():
+        g1 = trocr.generate(sd, cfg, enc, beam=1, max_len_b=16)
+        g2 = trocr.generate(sd, cfg, enc, beam=2, max_len_b=16)
+    t1, l1, s1, _ = ops.trocr_decode(enc_dev, beam=1, max_len_b=16)       # cache-free path
+    t2, l2, s2, _ = ops.trocr_decode(enc_dev, beam=2, max_len_b=16)       # K/V-cache path
+    for i in range(7):
+        assert t1[i, :int(l1[i])].cpu().tolist() == g1[i][0]["tokens"].tolist()
+        assert t2[i, :int(l2[i])].cpu().tolist() == g2[i][0]["tokens"].tolist()
+        assert abs(float(s1[i]) - g1[i][0]["score"]) <= 2e-2
