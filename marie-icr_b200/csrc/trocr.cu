@@ -375,15 +375,15 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
 // streamed in 32-key tiles through a cp.async ring.  qp, ctx: [rows, 16*E]; enc: [rows*T, E].
 constexpr int XE_KEYS = 32;
 template <bool F16, int ESLICE, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 1) dec_cross_enc_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ enc,
+__global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) dec_cross_enc_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ enc,
                                                                 bf16* __restrict__ ctxo, int T, int heads) {
     constexpr int E = ESLICE * WARPS;
     constexpr int NT = WARPS * 32;
     constexpr int ROWB = E * 2;                       // bytes per smem row
     constexpr int NB = ESLICE / 8;                    // 8-wide output blocks per warp
     extern __shared__ __align__(128) unsigned char xe_smem[];
-    unsigned char* sQ = xe_smem;                      // [16][E]
-    unsigned char* sE = sQ + 16 * ROWB;               // STAGES x [32][E]
+    unsigned char* sE = xe_smem;                      // STAGES x [32][E]; the projected queries are staged through stage 0
+    unsigned char* sQ = sE;                           // [16][E], only until their fragments sit in registers
     float* sS = reinterpret_cast<float*>(sE + STAGES * XE_KEYS * ROWB);   // [WARPS][16][32] partial scores
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long crop = blockIdx.x;
@@ -399,7 +399,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dec_cross_enc_kernel(const bf16
             cp_async16(smem_addr(dst + swz_w(r, c)), src + (long long)(ok ? row0 + r : 0) * E + c * 8, ok);
         }
     };
+    const int cbase = warp * (ESLICE / 8);            // first 16-byte chunk of this warp's E slice
     load_rows(sQ, qbase, 16, 0, heads);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    uint32_t aq[ESLICE / 16][4];                      // this warp's A fragments of q' (16 heads x ESLICE), kept for all tiles
+#pragma unroll
+    for (int ks = 0; ks < ESLICE / 16; ++ks)
+        ldsm_x4(smem_addr(sQ + swz_w((lane & 7) + ((lane >> 3) & 1) * 8, cbase + ks * 2 + (lane >> 4))), aq[ks][0], aq[ks][1],
+                aq[ks][2], aq[ks][3]);
+    __syncthreads();
 #pragma unroll
     for (int st = 0; st < STAGES - 1; ++st) {
         if (st < n_tiles) load_rows(sE + st * XE_KEYS * ROWB, ebase, XE_KEYS, st * XE_KEYS, T);
@@ -410,7 +420,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dec_cross_enc_kernel(const bf16
     for (int i = 0; i < NB; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const int g = lane >> 2, tg = lane & 3;
-    const int cbase = warp * (ESLICE / 8);            // first 16-byte chunk of this warp's E slice
     for (int j = 0; j < n_tiles; ++j) {
         unsigned char* tile = sE + (j % STAGES) * XE_KEYS * ROWB;
         {
@@ -426,19 +435,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dec_cross_enc_kernel(const bf16
         for (int nb = 0; nb < 4; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
 #pragma unroll
         for (int kp = 0; kp < ESLICE / 32; ++kp) {
-            uint32_t a0[4], a1[4];
-            {
-                const int r = (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int c = cbase + kp * 4 + (lane >> 4);
-                ldsm_x4(smem_addr(sQ + swz_w(r, c)), a0[0], a0[1], a0[2], a0[3]);
-                ldsm_x4(smem_addr(sQ + swz_w(r, c + 2)), a1[0], a1[1], a1[2], a1[3]);
-            }
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 uint32_t b0, b1, b2, b3;
                 ldsm_x4(smem_addr(tile + swz_w(nb * 8 + (lane & 7), cbase + kp * 4 + (lane >> 3))), b0, b1, b2, b3);
-                mma16816<F16>(s[nb], a0, b0, b1);
-                mma16816<F16>(s[nb], a1, b2, b3);
+                mma16816<F16>(s[nb], aq[kp * 2], b0, b1);
+                mma16816<F16>(s[nb], aq[kp * 2 + 1], b2, b3);
             }
         }
         float* mine = sS + warp * 16 * 32;
@@ -947,7 +949,7 @@ size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* b
 // one decoder step for all R rows: tokens[:, step] -> logits [R, V]
 template <bool F16, int ESLICE, int WARPS, int STAGES>
 int launch_cross_enc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* ctxe, int n, int T, int heads, cudaStream_t s) {
-    const size_t smem = (size_t)(16 + STAGES * XE_KEYS) * ESLICE * WARPS * 2 + WARPS * 16 * 32 * sizeof(float);
+    const size_t smem = (size_t)(STAGES * XE_KEYS) * ESLICE * WARPS * 2 + WARPS * 16 * 32 * sizeof(float);
     static bool done = false;
     if (!done) {
         MB_CUDA(ctx, cudaFuncSetAttribute(dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -968,7 +970,7 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     g.batches = heads; g.a_col_stride = DH; g.w_row_stride = E; g.out_col_stride = E;
     RC(mb_tap_gemm(ctx, g, s));
     int rc;
-    if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 192, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
+    if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
     else if (E == 1024) rc = ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
     else if (E == 128) rc = ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
     else return mb_set_err(ctx, MB_ERR_STATE, "cross_enc_attention: unsupported encoder width %d", E);
