@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "crops_per_s": value * float(np.mean(crops)),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -301,10 +301,28 @@ def run_ours(args, rank, world, local_rank):
                                 "sample": "one pass: K1+CRAFT+getDetBoxes+crops on an 825-row strip of one page, TrOCR-base fp32 "
                                           "on 4 crops, extrapolated to the page (%.1f s measured)" % (time.perf_counter() - t0),
                                 "detail": detail}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 during the run (NCCL prints its version
+    banner there) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
