@@ -160,6 +160,9 @@ int mb_find_line_numbers(mb_ctx* ctx, const int32_t* lines_host, int n_lines, co
  * mb_trocr_forced_logits: parity hook — teacher-forced decoder, logits_out [L, n, vocab] fp32.
  * mb_trocr_recognize: encode + decode over n crops in chunks (0 = default 512 crops per chunk). */
 int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes);
+/* Test hook: row-wise LayerNorm (fp32 statistics) of a [rows, D] 16-bit matrix, D % 8 == 0, D <= 1024. */
+int mb_layernorm16(mb_ctx* ctx, const void* in_dev, void* out_dev, const float* gamma_dev, const float* beta_dev,
+                   long long rows, int D, float eps, void* stream);
 /* Test hook for the two attention kernels: softmax(Q K^T * scale) V over a packed qkv buffer [n*T, 3*D] (heads of 64)
  * -> out [n*T, D].  mode 0 = tcgen05/TMEM kernel (encoder), 1 = mma.sync flash kernel (decoder cross-attention). */
 int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, int n, int T, int D, float scale, int mode,

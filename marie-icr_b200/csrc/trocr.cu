@@ -62,37 +62,42 @@ namespace {
 // One warp per row (grid-stride over rows); D % 8 == 0, D <= 1024.  in/out 16-bit (may alias), gamma/beta fp32, statistics in fp32
 // (two-pass: mean, then centred variance — the order torch's CPU kernel uses up to summation order).
 constexpr int LN_MAXV = 4;      // D <= 1024
+// gamma / beta live in shared memory (fp32), each warp strides over rows and keeps the NEXT row's 16-byte loads in
+// flight while it reduces the current one.  History: re-reading the affine parameters through L1 for every row and one
+// row in flight per warp left the kernel latency-bound at 2.7 TB/s (9 % of a bench step, profiles/r01_launches_bench_summary.md).
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long long rows, int D, float eps, int f16) {
+    __shared__ __align__(16) float sg[1024], sb[1024];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { sg[i] = gamma[i]; sb[i] = beta[i]; }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nv = D >> 3;
-    // each warp keeps its slice of gamma / beta in registers and strides over rows: re-reading 6 KB of fp32 affine
-    // parameters per 1.5 KB row made the first version L1-bound (2.9 TB/s of row traffic)
-    float g[LN_MAXV][8], bt[LN_MAXV][8];
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int vi = lane + 32 * i;
-        if (vi < nv) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
-            g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
-            bt[i][0] = b0.x; bt[i][1] = b0.y; bt[i][2] = b0.z; bt[i][3] = b0.w; bt[i][4] = b1.x; bt[i][5] = b1.y; bt[i][6] = b1.z; bt[i][7] = b1.w;
-        }
-    }
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint4 nxt[LN_MAXV];
+    if (row < rows) {
         const uint4* src = reinterpret_cast<const uint4*>(in + row * D);
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i)
+            if (lane + 32 * i < nv) nxt[i] = src[lane + 32 * i];
+    }
+    for (; row < rows; row += wstride) {
+        uint4 cur[LN_MAXV];
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) cur[i] = nxt[i];
+        if (row + wstride < rows) {
+            const uint4* src = reinterpret_cast<const uint4*>(in + (row + wstride) * D);
+#pragma unroll
+            for (int i = 0; i < LN_MAXV; ++i)
+                if (lane + 32 * i < nv) nxt[i] = src[lane + 32 * i];
+        }
         float v[LN_MAXV][8];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < LN_MAXV; ++i) {
-            const int vi = lane + 32 * i;
-            if (vi < nv) {
-                const uint4 u = src[vi];
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            if (lane + 32 * i < nv) {
+                const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float2 f = unpack2(w[k], f16);
@@ -116,11 +121,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
         for (int i = 0; i < LN_MAXV; ++i) {
             const int vi = lane + 32 * i;
             if (vi < nv) {
+                const float4 g0 = *reinterpret_cast<const float4*>(sg + vi * 8), g1 = *reinterpret_cast<const float4*>(sg + vi * 8 + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sb + vi * 8), b1 = *reinterpret_cast<const float4*>(sb + vi * 8 + 4);
                 uint4 o;
-                o.x = pack2((v[i][0] - mean) * rstd * g[i][0] + bt[i][0], (v[i][1] - mean) * rstd * g[i][1] + bt[i][1], f16);
-                o.y = pack2((v[i][2] - mean) * rstd * g[i][2] + bt[i][2], (v[i][3] - mean) * rstd * g[i][3] + bt[i][3], f16);
-                o.z = pack2((v[i][4] - mean) * rstd * g[i][4] + bt[i][4], (v[i][5] - mean) * rstd * g[i][5] + bt[i][5], f16);
-                o.w = pack2((v[i][6] - mean) * rstd * g[i][6] + bt[i][6], (v[i][7] - mean) * rstd * g[i][7] + bt[i][7], f16);
+                o.x = pack2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y, f16);
+                o.y = pack2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w, f16);
+                o.z = pack2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y, f16);
+                o.w = pack2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w, f16);
                 dst[vi] = o;
             }
         }
@@ -842,7 +849,7 @@ int layernorm(mb_ctx* ctx, const bf16* in, bf16* out, const float* g, const floa
               cudaStream_t s) {
     if (D % 8 != 0 || D > 256 * LN_MAXV) return mb_set_err(ctx, MB_ERR_ARG, "layernorm: unsupported width %d", D);
     const long long blocks = (rows + 7) / 8;
-    const long long cap = (long long)ctx->num_sms * 16;
+    const long long cap = (long long)ctx->num_sms * 8;
     layernorm_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(in, out, g, b, rows, D, eps, ctx->f16);
     MB_LAUNCH_CHECK(ctx);
     return 0;
@@ -1113,6 +1120,13 @@ extern "C" int mb_trocr_dims(mb_ctx* ctx, int* dims) {
     TrocrModel* m = ctx->trocr;
     dims[0] = m->enc_dim; dims[1] = m->dec_dim; dims[2] = m->vocab; dims[3] = m->tokens;
     return 0;
+}
+
+// Test hook: row-wise LayerNorm of a [rows, D] 16-bit matrix with fp32 gamma / beta.
+extern "C" int mb_layernorm16(mb_ctx* ctx, const void* in_dev, void* out_dev, const float* gamma_dev, const float* beta_dev,
+                              long long rows, int D, float eps, void* stream) {
+    if (!ctx) return MB_ERR_ARG;
+    return layernorm(ctx, (const bf16*)in_dev, (bf16*)out_dev, gamma_dev, beta_dev, rows, D, eps, (cudaStream_t)stream);
 }
 
 // Test hook: softmax(Q K^T * scale) V over a packed qkv buffer [n*T, 3*D] (heads of 64) -> out [n*T, D].

@@ -248,3 +248,10 @@ def gemm16_batched(a, w, batches, n, k, a_col_stride, w_row_stride, out_col_stri
                  c_int(batches), c_int(a_col_stride), c_int(w_row_stride), c_int(out_col_stride), ptr(bias), c_int(act),
                  ptr(out), c_ll(out.stride(0)), cur_stream())
     return out
+
+
+def layernorm16(x, gamma, beta, eps=1e-6):
+    out = torch.empty_like(x)
+    rows, D = x.shape
+    _ctx(x).call("mb_layernorm16", ptr(x), ptr(out), ptr(gamma), ptr(beta), c_ll(rows), c_int(D), c_float(eps), cur_stream())
+    return out

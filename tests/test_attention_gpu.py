@@ -45,3 +45,16 @@ def test_attention_sharp_and_growing_scores(cuda_ctx, dtype16, mode):
     rel = ((out - ref).norm() / ref.norm()).item()
     assert torch.isfinite(out).all()
     assert rel <= (4e-3 if dtype16 == torch.float16 else 2e-2), rel
+
+
+@pytest.mark.parametrize("rows,D", [(577 * 3, 768), (1000, 1024), (37, 128), (5, 768)])
+def test_layernorm_matches_torch(cuda_ctx, dtype16, rows, D):
+    from marie_icr_b200 import ops
+    torch.manual_seed(rows + D)
+    x = (torch.randn(rows, D, device="cuda") * 2 + 0.3).to(dtype16)
+    g = torch.randn(D, device="cuda") * 0.1 + 1
+    b = torch.randn(D, device="cuda") * 0.1
+    out = ops.layernorm16(x, g, b, 1e-6).float()
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), g, b, 1e-6)
+    tol = 2e-3 if dtype16 == torch.float16 else 1.6e-2
+    assert (out - ref).abs().max().item() <= tol * ref.abs().max().item()

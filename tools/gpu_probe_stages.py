@@ -46,6 +46,11 @@ def main():
     t = timeit(lambda: ops.pack_crops(dpages, rects, pidx, layout=1))
     print(f"K9 crops: {t / n * 1e3:.2f} us/crop ({0.9e-3 / (t / n):.0f} GB/s algorithmic), n={n}")
     patches = ops.pack_crops(dpages, rects, pidx, layout=1)
+    xln = torch.randn(1024 * 577, 768, device="cuda").to(dt)
+    gl, bl = torch.ones(768, device="cuda"), torch.zeros(768, device="cuda")
+    t = timeit(lambda: ops.layernorm16(xln, gl, bl), n=5)
+    print(f"LayerNorm 590848x768: {t * 1e3:.0f} us ({xln.numel() * 4 / t / 1e9:.2f} TB/s)")
+    del xln
     cfg = trocr.trocr_base()
     t0 = time.time()
     sd = trocr.synth_trocr_state(cfg, 0, round_to=dt)
