@@ -21,13 +21,16 @@ int mb_encode_2d_map(mb_ctx* ctx, CUtensorMap* m, const void* base, long long co
 namespace {
 
 constexpr int AT_THREADS = 192;
-constexpr int TILE = 128;                 // query rows per CTA and keys per step
+constexpr int TILE = 128;                 // query rows per CTA
+constexpr int KT = 64;                    // keys per step: 64 -> 65 KB smem, 128 TMEM columns, three CTAs per SM
 constexpr int HD = 64;                    // head dim
 constexpr int TILE_BYTES = TILE * HD * 2; // 16 KB: one [128 x 64] 16-bit operand tile (128-byte rows, SW128)
-constexpr int P_BYTES = TILE * TILE * 2;  // 32 KB: P as two [128 x 64] K-major atoms
-constexpr int AT_SMEM = 1024 + TILE_BYTES * 5 + P_BYTES;   // 115,712 B: two CTAs + 2 x 1 KB reserved = 228 KB
-constexpr int TMEM_COLS_AT = 256;         // S: columns 0..127, O: columns 128..191
-constexpr int O_COL = 128;
+constexpr int KV_BYTES = KT * HD * 2;     // 8 KB: one K or V tile
+constexpr int P_BYTES = TILE * KT * 2;    // 16 KB: P as KT/64 [128 x 64] K-major atoms
+constexpr int AT_SMEM = 1024 + TILE_BYTES + 4 * KV_BYTES + P_BYTES;
+constexpr int TMEM_COLS_AT = (KT + HD) <= 128 ? 128 : 256;   // S: columns 0..KT-1, O: columns KT..KT+63
+constexpr int O_COL = KT;
+constexpr int AT_CTAS = KT == 64 ? 3 : 2;
 
 struct AttnParams {
     int T, D, heads;
@@ -44,8 +47,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <bool F16>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+__global__ void __launch_bounds__(AT_THREADS, AT_CTAS)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // layout: [mbarriers, 1 KB] [Q] [K x2] [V x2] [P]; the dynamic segment must itself be 1024-byte aligned (128-byte
     // swizzle) — two CTAs of 114 KB fill the SM exactly, there is no room for an alignment pad
@@ -56,8 +59,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     uint8_t* smem = smem_raw + 1024;
     uint8_t* sQ = smem;
     uint8_t* sK = smem + TILE_BYTES;              // 2 stages
-    uint8_t* sV = smem + 3 * TILE_BYTES;          // 2 stages
-    uint8_t* sP = smem + 5 * TILE_BYTES;
+    uint8_t* sV = sK + 2 * KV_BYTES;              // 2 stages
+    uint8_t* sP = sV + 2 * KV_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;                 // [2]
@@ -71,7 +74,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const int q0 = blockIdx.x * TILE, head = blockIdx.y;
     const long long img = blockIdx.z;
     const int T = p.T;
-    const int n_tiles = (T + TILE - 1) / TILE;
+    const int n_tiles = (T + KT - 1) / KT;
     const int row_base = (int)(img * T);
 
     if (warp == 0 && lane == 0) {
@@ -101,15 +104,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
                 const int st = j & 1;
                 mbar_wait(smem_u32(&kv_empty[st]), ((j >> 1) & 1) ^ 1, p.diag, 11);
                 const uint32_t fb = smem_u32(&kv_full[st]);
-                mbar_arrive_expect_tx(fb, 2 * TILE_BYTES);
-                tma_load_2d(smem_u32(sK + st * TILE_BYTES), &tmQKV, fb, p.D + head * HD, row_base + j * TILE);
-                tma_load_2d(smem_u32(sV + st * TILE_BYTES), &tmQKV, fb, 2 * p.D + head * HD, row_base + j * TILE);
+                mbar_arrive_expect_tx(fb, 2 * KV_BYTES);
+                tma_load_2d(smem_u32(sK + st * KV_BYTES), &tmKV, fb, p.D + head * HD, row_base + j * KT);
+                tma_load_2d(smem_u32(sV + st * KV_BYTES), &tmKV, fb, 2 * p.D + head * HD, row_base + j * KT);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t ab_fmt = F16 ? 0u : ((1u << 7) | (1u << 10));
-            const uint32_t idesc_qk = (1u << 4) | ab_fmt | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+            const uint32_t idesc_qk = (1u << 4) | ab_fmt | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
             // P V: B operand (V tile: keys x 64 contiguous head dims) is MN-major — bit 16
             const uint32_t idesc_pv = (1u << 4) | ab_fmt | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
             mbar_wait(smem_u32(q_full), 0, p.diag, 12);
@@ -118,17 +121,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
                 mbar_wait(smem_u32(&kv_full[st]), (j >> 1) & 1, p.diag, 13);
                 tcgen05_fence_after();
                 const uint64_t qd = make_smem_desc(smem_u32(sQ));
-                const uint64_t kd = make_smem_desc(smem_u32(sK + st * TILE_BYTES));
+                const uint64_t kd = make_smem_desc(smem_u32(sK + st * KV_BYTES));
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
                     umma_bf16(tmem_base, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
                 tcgen05_commit(smem_u32(s_full));
                 mbar_wait(smem_u32(p_full), j & 1, p.diag, 14);
                 tcgen05_fence_after();
-                const uint64_t vd = make_smem_desc(smem_u32(sV + st * TILE_BYTES));
+                const uint64_t vd = make_smem_desc(smem_u32(sV + st * KV_BYTES));
 #pragma unroll
-                for (int k = 0; k < TILE / 16; ++k) {
-                    // A = P: two K-major atoms of 64 keys (16 KB apart), 32 B per 16-key step inside an atom
+                for (int k = 0; k < KT / 16; ++k) {
+                    // A = P: KT/64 K-major atoms of 64 keys (16 KB apart), 32 B per 16-key step inside an atom
                     const uint64_t pd = make_smem_desc(smem_u32(sP + (k >> 2) * TILE_BYTES)) + (uint64_t)(2 * (k & 3));
                     // B = V tile, MN-major: 16 keys = two 8-row groups of 1024 B
                     umma_bf16(tmem_base + O_COL, pd, vd + (uint64_t)((k * 2048) >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
@@ -158,11 +161,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
             float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
             tmem_ld32(t_s, va);
 #pragma unroll
-            for (int ci = 0; ci < TILE / 32; ++ci) {
+            for (int ci = 0; ci < KT / 32; ++ci) {
                 uint32_t* cur = (ci & 1) ? vb : va;
                 uint32_t* nxt = (ci & 1) ? va : vb;
                 tmem_wait_ld();
-                if (ci + 1 < TILE / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
+                if (ci + 1 < KT / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
                 const int c = ci * 32;
                 float pr[32];
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -200,17 +203,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(smem_u32(s_full), j & 1, p.diag, 15);
             tcgen05_fence_after();
-            const int valid = T - j * TILE;                   // keys >= valid are beyond this image
+            const int valid = T - j * KT;                     // keys >= valid are beyond this image
             if (j == 0) {
                 // exact row maximum of the first tile = the row's reference
                 float mx = -INFINITY;
                 tmem_ld32(t_s, va);
 #pragma unroll
-                for (int ci = 0; ci < TILE / 32; ++ci) {
+                for (int ci = 0; ci < KT / 32; ++ci) {
                     uint32_t* cur = (ci & 1) ? vb : va;
                     uint32_t* nxt = (ci & 1) ? va : vb;
                     tmem_wait_ld();
-                    if (ci + 1 < TILE / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
+                    if (ci + 1 < KT / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
                     const int c = ci * 32;
                     float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
@@ -290,8 +293,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D, int heads, float scale_log2e,
                     cudaStream_t stream) {
     MB_REQUIRE(ctx, D == heads * HD && n > 0 && T > 0, "attention_tc: bad geometry");
-    CUtensorMap tm;
+    CUtensorMap tm, tmkv;
     int rc = mb_encode_2d_map(ctx, &tm, qkv, 3LL * D, (long long)n * T, 3LL * D, HD, TILE);
+    if (rc) return rc;
+    rc = mb_encode_2d_map(ctx, &tmkv, qkv, 3LL * D, (long long)n * T, 3LL * D, HD, KT);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -302,8 +307,8 @@ int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D
     AttnParams p;
     p.T = T; p.D = D; p.heads = heads; p.scale_log2e = scale_log2e; p.out = out; p.f16 = ctx->f16; p.diag = ctx->dev_diag;
     dim3 grid((T + TILE - 1) / TILE, heads, n);
-    if (ctx->f16) attn_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, p);
-    else attn_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, p);
+    if (ctx->f16) attn_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, tmkv, p);
+    else attn_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, tmkv, p);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
