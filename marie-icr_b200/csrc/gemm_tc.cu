@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -79,7 +80,11 @@ template <int ACT> __device__ __forceinline__ float apply_act(float x) {
 template <bool F16> __device__ __forceinline__ float2 unpack2t(uint32_t v) { return unpack2(v, F16 ? 1 : 0); }
 template <bool F16> __device__ __forceinline__ uint32_t pack2t(float a, float b) { return pack2(a, b, F16 ? 1 : 0); }
 
-template <int ACT, int OUT, bool RES, bool F16>
+// CG2 = true: clusters of two CTAs (neighbouring SMs) work on two M tiles of the same N tile with ONE shared B tile:
+// each CTA loads its own A tile and half of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256: rows
+// 0..127 accumulate in the leader's TMEM, 128..255 in the peer's), completions are multicast to both CTAs' mbarriers.
+// Per SM and k-block that is 32 KB through shared memory instead of 48 KB, and six pipeline stages instead of four.
+template <int ACT, int OUT, bool RES, bool F16, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const KParams p) {
@@ -89,7 +94,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                                                ~static_cast<uintptr_t>(1023));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+    const int b_stage_bytes = (CG2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
+    const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.stages * A_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage_bytes);
@@ -112,24 +119,33 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[i]), EPI_WARPS);   // one arrival per epilogue warp
+            mbar_init(smem_u32(&tmem_empty_bar[i]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(tmem_ptr_smem)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CG2) cluster_sync_all();      // the peer's mbarriers are initialised before anything is signalled remotely
     tcgen05_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
-    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+    // CG2: a "tile" index addresses a PAIR of M tiles (2*mp, 2*mp+1) of one N tile; this CTA takes M tile 2*mp + rank
+    const int m_units = CG2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    const int tiles_per_batch = m_units * p.n_tiles;
     const int total_tiles = tiles_per_batch * p.batches;
+    const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int kb_per_tap = p.kb0 + p.kb1;
     const int k_iters = p.taps * kb_per_tap;
 
@@ -139,31 +155,42 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int bt = tile / tiles_per_batch;
                 const int trem = tile - bt * tiles_per_batch;
                 const int nt = trem % p.n_tiles;
-                const int mt = trem / p.n_tiles;
+                int mt = trem / p.n_tiles;
+                if (CG2) mt = min(2 * mt + (int)crank, p.m_tiles - 1);   // a missing odd partner re-loads the last tile
                 const int wt = mt % p.w_tiles;
                 const int rest = mt / p.w_tiles;
                 const int hh = rest % p.h;
                 const int nn = rest / p.h;
                 const int w0 = wt * BLOCK_M;
-                const int acol = bt * p.a_col_stride, wrow = bt * p.w_row_stride;
+                const int acol = bt * p.a_col_stride, wrow = bt * p.w_row_stride + (CG2 ? (int)crank * (p.block_n / 2) : 0);
                 for (int tap = 0; tap < p.taps; ++tap) {
                     const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
                     const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
                     for (int kb = 0; kb < kb_per_tap; ++kb) {
                         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.diag, 1);
                         const uint32_t fb = smem_u32(&full_bar[stage]);
-                        mbar_arrive_expect_tx(fb, tx_bytes);
                         const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                         const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
+                        if (CG2) {
+                            // the leader's barrier collects the bytes of both CTAs
+                            if (leader) mbar_arrive_expect_tx(fb, 2 * tx_bytes);
+                            if (kb < p.kb0)
+                                tma_load_4d_cg2(sa, &tmA0, fb, kb * BLOCK_K + acol, w0 + dx, hh + dy, nn);
+                            else
+                                tma_load_4d_cg2(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 + dx, hh + dy, nn);
+                            tma_load_2d_cg2(sb, &tmB, fb, (tap * kb_per_tap + kb) * BLOCK_K, nt * p.block_n + wrow);
+                        } else {
+                        mbar_arrive_expect_tx(fb, tx_bytes);
                         if (kb < p.kb0)
                             tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K + acol, w0 + dx, hh + dy, nn);
                         else
                             tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 + dx, hh + dy, nn);
                         tma_load_2d(sb, &tmB, fb, (tap * kb_per_tap + kb) * BLOCK_K, nt * p.block_n + wrow);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -171,16 +198,16 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+        if (lane == 0 && leader) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
             const uint32_t ab_fmt = p.f16 ? 0u : ((1u << 7) | (1u << 10));   // a/b format: 0 = f16, 1 = bf16
             const uint32_t idesc = (1u << 4) | ab_fmt |
-                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)((CG2 ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1, p.diag, 2);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
@@ -192,11 +219,20 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 elements = 32 B along K inside the swizzle row: +2 in 16 B units
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                  (it > 0 || k > 0) ? 1u : 0u);
+                        if (CG2)
+                            umma_bf16_cg2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                          (it > 0 || k > 0) ? 1u : 0u);
+                        else
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                      (it > 0 || k > 0) ? 1u : 0u);
                     }
+                    if (CG2) {
+                        tcgen05_commit_cg2_mc(smem_u32(&empty_bar[stage]));   // frees the slot in BOTH CTAs
+                        if (it == k_iters - 1) tcgen05_commit_cg2_mc(smem_u32(&tmem_full_bar[as]));
+                    } else {
                     tcgen05_commit(smem_u32(&empty_bar[stage]));     // frees the smem slot when MMAs retire
                     if (it == k_iters - 1) tcgen05_commit(smem_u32(&tmem_full_bar[as]));
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 as ^= 1;
@@ -220,11 +256,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const bool vec_res = !RES || ((p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 7) == 0);
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int bt = tile / tiles_per_batch;
             const int trem = tile - bt * tiles_per_batch;
             const int nt = trem % p.n_tiles;
-            const int mt = trem / p.n_tiles;
+            int mt = trem / p.n_tiles;
+            bool tile_exists = true;
+            if (CG2) { mt = 2 * mt + (int)crank; tile_exists = mt < p.m_tiles; mt = min(mt, p.m_tiles - 1); }
             const int wt = mt % p.w_tiles;
             const int rest = mt / p.w_tiles;
             const int hh = rest % p.h;
@@ -232,7 +270,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int nbase = bt * p.out_col_stride;                // output / bias / residual column of this batch
             const int row0 = wt * BLOCK_M + q * 32;                 // first tile row (pixel) of this warp
             const long long pix0 = ((long long)nn * p.h + hh) * p.w + row0;
-            const int rows_valid = min(32, p.w - row0);             // may be <= 0 for a ragged last tile
+            const int rows_valid = tile_exists ? min(32, p.w - row0) : 0;   // <= 0: ragged last tile / missing partner
 
             const int n_chunks = (p.block_n + 31) >> 5;
             // residual tile rows are prefetched one chunk ahead (the first chunk before the accumulator is even ready)
@@ -335,7 +373,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+            if (lane == 0) {
+                if (CG2) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[as]), 0);   // the leader's barrier
+                else mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
@@ -343,11 +384,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
     tcgen05_fence_before();
     __syncthreads();
+    if (CG2) cluster_sync_all();      // no CTA leaves (or frees TMEM) while its peer may still signal / read it
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(TMEM_COLS)
-                     : "memory");
+        if (CG2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -478,7 +521,12 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.kb0 = g.c0 / BLOCK_K; p.kb1 = g.c1 / BLOCK_K;
     p.block_n = block_n;
     p.n_out = g.n_out;
-    const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+    // two-CTA mode (cta_group::2): big 16-bit-output problems with full 256-wide N tiles; MB_GEMM2=0 disables it
+    static int gemm2_env = -1;
+    if (gemm2_env < 0) { const char* e = getenv("MB_GEMM2"); gemm2_env = (e && e[0] == '1') ? 1 : 0; }
+    const bool cg2 = gemm2_env == 1 && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
+                     (g.batches <= 1);
+    const int stage_bytes = A_STAGE_BYTES + (cg2 ? block_n / 2 : block_n) * BLOCK_K * 2;
     const int bar_bytes = BAR_BYTES + EPI_WARPS * STAGE_TILE_BYTES;
     int stages = (SMEM_LIMIT - 1024 - bar_bytes) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -501,7 +549,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     } else {
         tmA1 = tmA0;
     }
-    rc = encode_wgt_map(ctx, &tmB, g.wgt, g.taps * (g.c0 + g.c1), g.n_rows_w, block_n, ctx->f16);
+    rc = encode_wgt_map(ctx, &tmB, g.wgt, g.taps * (g.c0 + g.c1), g.n_rows_w, cg2 ? block_n / 2 : block_n, ctx->f16);
     if (rc) return rc;
 
     const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
@@ -511,13 +559,19 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     const bool h = ctx->f16 != 0;
 #define MB_PICK(A, O, R)                                                                               \
     if (g.act == (A) && g.out_mode == (O) && res == (R))                                               \
-        fn = h ? (KernelFn)tap_gemm_kernel<A, O, R, true> : (KernelFn)tap_gemm_kernel<A, O, R, false>;
+        fn = h ? (KernelFn)tap_gemm_kernel<A, O, R, true, false> : (KernelFn)tap_gemm_kernel<A, O, R, false, false>;
+#define MB_PICK2(A, R)                                                                                 \
+    if (cg2 && g.act == (A) && res == (R))                                                             \
+        fn = h ? (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, true, true> : (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, false, true>;
     MB_PICK(MB_ACT_NONE, MB_OUT_BF16, false) MB_PICK(MB_ACT_NONE, MB_OUT_BF16, true)
     MB_PICK(MB_ACT_RELU, MB_OUT_BF16, false) MB_PICK(MB_ACT_RELU, MB_OUT_BF16, true)
     MB_PICK(MB_ACT_GELU, MB_OUT_BF16, false) MB_PICK(MB_ACT_GELU, MB_OUT_BF16, true)
     MB_PICK(MB_ACT_NONE, MB_OUT_F32, false) MB_PICK(MB_ACT_RELU, MB_OUT_F32, false)
     MB_PICK(MB_ACT_NONE, MB_OUT_F32_PLANAR, false) MB_PICK(MB_ACT_RELU, MB_OUT_F32_PLANAR, false)
+    MB_PICK2(MB_ACT_NONE, false) MB_PICK2(MB_ACT_NONE, true) MB_PICK2(MB_ACT_RELU, false) MB_PICK2(MB_ACT_RELU, true)
+    MB_PICK2(MB_ACT_GELU, false) MB_PICK2(MB_ACT_GELU, true)
 #undef MB_PICK
+#undef MB_PICK2
     if (!fn)
         return mb_set_err(ctx, MB_ERR_ARG, "tap_gemm: unsupported epilogue (act %d, out_mode %d, residual %d)", g.act,
                           g.out_mode, (int)res);
@@ -530,7 +584,23 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         cudaEventCreate(&ev1);
         cudaEventRecord(ev0, stream);
     }
-    fn<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
+    if (cg2) {
+        const long long pairs = (long long)((p.m_tiles + 1) / 2) * p.n_tiles * p.batches;
+        const int clusters = (int)(pairs < ctx->num_sms / 2 ? pairs : ctx->num_sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters, 1, 1);
+        cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MB_CUDA(ctx, cudaLaunchKernelEx(&cfg, fn, tmA0, tmA1, tmB, p));
+    } else {
+        fn<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
+    }
     if (ctx->profile) {
         cudaEventRecord(ev1, stream);
         ctx->prof_events.push_back(ev0);
