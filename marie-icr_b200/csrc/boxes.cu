@@ -1,8 +1,12 @@
 // NVCC_FLAGS: -fmad=false
-// K6/K7: per-component box extraction, batched over pages.  One CTA per (image, candidate box):
-//   phase 1 (all warps)  per-row extremes of {label == k and text > low_text} inside the component's bbox
-//   phase 2 (one thread)  analytic (1+niter)^2 dilation, convex hull, rotating calipers, boxPoints, diamond fix,
-//                         roll, coordinate adjustment and the +4 px crop rect  (csrc/boxgeom.cuh)
+// K6/K7: per-component box extraction, batched over pages.
+//   phase 1  per-row extremes of {label == k and text > low_text} inside the component's bbox
+//   phase 2  analytic (1+niter)^2 dilation, convex hull, rotating calipers, boxPoints, diamond fix, roll, coordinate
+//            adjustment and the +4 px crop rect  (csrc/boxgeom.cuh)
+// Phase 2 is a sequential algorithm (OpenCV's operation order is part of the contract), so the parallelism is across
+// components: one THREAD per component with a compact workspace in local memory (box_extract_small_kernel, word-sized
+// components: <= 64 rows, <= 40 hull vertices per chain); taller or vertex-rich components are queued for the
+// warp-per-component kernel with the full-size workspace (box_extract_kernel).
 // Reference: marie/models/craft/craft_utils.py:47-98,268-274; marie/boxes/craft_box_processor.py:499-521.
 // The reference builds four full-image boolean masks per label (O(N*H*W)); here each component touches only its
 // bounding box (O(sum of bbox areas)).
@@ -10,8 +14,8 @@
 #include "boxgeom.cuh"
 
 int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int h, int w, float low_text,
-               float link_thr, int* parent, int* rowcount, int* rowbase, int* labels, int* n_labels, int* stats,
-               int max_labels, int* overflow, cudaStream_t stream);
+               float link_thr, int* parent, int* rowcount, int* rowbase, unsigned* fg, unsigned* tx, int* labels,
+               int* n_labels, int* stats, int max_labels, int* overflow, cudaStream_t stream);
 
 namespace {
 
@@ -112,32 +116,120 @@ struct BoxSmem {
     short rowmax[MAX_ROWS];
 };
 
-// One WARP per box, 32 CTAs per SM: the per-box geometry (hull + rotating calipers) is a long single-thread dependency
-// chain (~40 us), so throughput comes from how many boxes are in flight.  The hull workspace lives in a per-CTA slice of
-// global scratch (the few dozen vertices actually touched stay in L1) instead of 64 KB of shared memory, which had
-// limited the first version to 3 CTAs/SM (ncu: 14 % warps active, 422 us for 4116 boxes).
+constexpr int SMALL_ROWS = 64;
+constexpr int BOX_LANE_STRIDE = 4;
+typedef MbHullWorkT<40, MbPtS, short> SmallHull;
+
+__device__ __forceinline__ void box_write(const float* box, long long o, int img, const double* __restrict__ ratios,
+                                          const int* __restrict__ page_hw, float* __restrict__ det,
+                                          float* __restrict__ adj, int* __restrict__ rects) {
+    float a[8];
+    int rect[4];
+    const double rw = ratios ? ratios[2 * img] : 1.0, rh = ratios ? ratios[2 * img + 1] : 1.0;
+    const int ph = page_hw ? page_hw[2 * img] : 0x7fffffff, pw = page_hw ? page_hw[2 * img + 1] : 0x7fffffff;
+    mb_adjust_and_rect(box, rw, rh, pw, ph, a, rect);
+    for (int i = 0; i < 8; ++i) { det[o * 8 + i] = box[i]; adj[o * 8 + i] = a[i]; }
+    for (int i = 0; i < 4; ++i) rects[o * 4 + i] = rect[i];
+}
+
+// One thread per (image, slot).  A run of consecutive `text > low_text` bits lies inside one foreground run, hence
+// inside one component: one label fetch per bit group decides the whole group.
 __global__ void __launch_bounds__(32)
-box_extract_kernel(const int* __restrict__ labels, const float* __restrict__ text, const BoxPlan* __restrict__ plans,
-                   const int* __restrict__ n_boxes, float* __restrict__ det, float* __restrict__ adj,
-                   int* __restrict__ rects, int* __restrict__ overflow, int n_img, int max_boxes, int img_h,
-                   int img_w, float low_text, const double* __restrict__ ratios, const int* __restrict__ page_hw,
-                   BoxSmem* __restrict__ workspace) {
-    BoxSmem* sm = workspace + blockIdx.x;
-    const int lane = threadIdx.x & 31, wid = 0, nw = 1;
-    // persistent CTAs stride over the (image, slot) pairs; empty slots cost one compare
-    for (int id = blockIdx.x; id < n_img * max_boxes; id += gridDim.x) {
+box_extract_small_kernel(const int* __restrict__ labels, const unsigned* __restrict__ tx, int wd,
+                         const BoxPlan* __restrict__ plans, const int* __restrict__ n_boxes, float* __restrict__ det,
+                         float* __restrict__ adj, int* __restrict__ rects, int* __restrict__ big_list,
+                         int* __restrict__ big_count, int n_img, int max_boxes, int img_h, int img_w,
+                         const double* __restrict__ ratios, const int* __restrict__ page_hw) {
+    // every BOX_LANE_STRIDE-th lane owns a box: 8 boxes per warp diverge far less than 32 and there are four times
+    // as many warps to hide the dependent-load latency (ncu: 3 % of the warp slots active with 32 boxes per warp)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid % BOX_LANE_STRIDE) return;
+    const int id = tid / BOX_LANE_STRIDE;
+    if (id >= n_img * max_boxes) return;
     const int img = id / max_boxes;
     const int b = id - img * max_boxes;
-    if (b >= n_boxes[img]) continue;
-    __syncwarp();                    // the previous box's single-thread phase is done with the row buffers
-    const BoxPlan p = plans[(long long)img * max_boxes + b];
+    if (b >= n_boxes[img]) return;
+    const BoxPlan p = plans[id];
+    if (p.h > SMALL_ROWS) {
+        big_list[atomicAdd(big_count, 1)] = id;
+        return;
+    }
     const int* lab = labels + (long long)img * img_h * img_w;
-    const float* txt = text + (long long)img * img_h * img_w;
-    for (int r = wid; r < p.h; r += nw) {
+    const unsigned* txi = tx + (long long)img * img_h * wd;
+    short rowmin[SMALL_ROWS], rowmax[SMALL_ROWS];
+    const int w0 = p.x >> 5, w1 = (p.x + p.w - 1) >> 5;
+    for (int r = 0; r < p.h; ++r) {
         const long long row = (long long)(p.y + r) * img_w;
+        const unsigned* trow = txi + (long long)(p.y + r) * wd;
         int mn = 0x7fff, mx = -1;
-        for (int x = p.x + lane; x < p.x + p.w; x += 32) {
-            if (lab[row + x] == p.label && txt[row + x] > low_text) {
+        for (int wx = w0; wx <= w1; ++wx) {
+            unsigned t = trow[wx];
+            const int lo = p.x - wx * 32, hi = p.x + p.w - 1 - wx * 32;
+            if (lo > 0) t &= 0xffffffffu << lo;
+            if (hi < 31) t &= 0xffffffffu >> (31 - hi);
+            while (t) {
+                const int bit = __ffs(t) - 1;
+                const unsigned inv = ~(t >> bit);
+                const int len = inv ? (__ffs(inv) - 1) : 32;
+                const int x0 = wx * 32 + bit;
+                if (lab[row + x0] == p.label) {
+                    mn = x0 < mn ? x0 : mn;
+                    mx = x0 + len - 1 > mx ? x0 + len - 1 : mx;
+                }
+                t = (bit + len >= 32) ? 0u : (t & (0xffffffffu << (bit + len)));
+            }
+        }
+        rowmin[r] = (short)mn; rowmax[r] = (short)mx;
+    }
+    SmallHull hw;
+    float box[8];
+    const int rc = mb_component_box(&hw, rowmin, rowmax, p.y, p.h, p.sx, p.ex, p.sy, p.ey, p.niter, box);
+    if (rc < 0) {                    // more hull vertices than the compact workspace holds
+        big_list[atomicAdd(big_count, 1)] = id;
+        return;
+    }
+    if (rc == 0)
+        for (int i = 0; i < 8; ++i) box[i] = 0.f;       // cannot happen for components that passed the filters
+    box_write(box, id, img, ratios, page_hw, det, adj, rects);
+}
+
+// One WARP per box, two warps per CTA, 32 CTAs per SM (all 64 warp slots): the per-box geometry (hull + rotating
+// calipers) is a long single-thread dependency chain (~40 us), so throughput comes from how many boxes are in flight.
+// The hull workspace lives in a per-warp slice of global scratch (the few dozen vertices actually touched stay in L1)
+// instead of 64 KB of shared memory, which had limited the first version to 3 CTAs/SM (ncu: 14 % warps active).
+// Phase 1 reads the `text > low_text` bit plane written by the labelling pass (32 pixels per word; label words are only
+// fetched where a bit is set) instead of the fp32 text map.
+constexpr int BOX_WARPS = 2;
+
+__global__ void __launch_bounds__(32 * BOX_WARPS)
+box_extract_kernel(const int* __restrict__ labels, const unsigned* __restrict__ tx, int wd,
+                   const BoxPlan* __restrict__ plans, const int* __restrict__ big_list,
+                   const int* __restrict__ big_count, float* __restrict__ det, float* __restrict__ adj,
+                   int* __restrict__ rects, int* __restrict__ overflow, int max_boxes, int img_h, int img_w,
+                   const double* __restrict__ ratios, const int* __restrict__ page_hw,
+                   BoxSmem* __restrict__ workspace) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * BOX_WARPS + (threadIdx.x >> 5), ngw = gridDim.x * BOX_WARPS;
+    BoxSmem* sm = workspace + gw;
+    const int n_big = *big_count;
+    // persistent warps stride over the queued (image, slot) pairs
+    for (int qi = gw; qi < n_big; qi += ngw) {
+    const int id = big_list[qi];
+    const int img = id / max_boxes;
+    __syncwarp();                    // the previous box's single-thread phase is done with the row buffers
+    const BoxPlan p = plans[id];
+    const int* lab = labels + (long long)img * img_h * img_w;
+    const unsigned* txi = tx + (long long)img * img_h * wd;
+    const int w0 = p.x >> 5, w1 = (p.x + p.w - 1) >> 5;
+    for (int r = 0; r < p.h; ++r) {
+        const long long row = (long long)(p.y + r) * img_w;
+        const unsigned* trow = txi + (long long)(p.y + r) * wd;
+        int mn = 0x7fff, mx = -1;
+        for (int wx = w0; wx <= w1; ++wx) {
+            const unsigned t = trow[wx];
+            if (!t) continue;
+            const int x = wx * 32 + lane;
+            if (((t >> lane) & 1u) && x >= p.x && x < p.x + p.w && lab[row + x] == p.label) {
                 mn = x < mn ? x : mn;
                 mx = x > mx ? x : mx;
             }
@@ -147,7 +239,7 @@ box_extract_kernel(const int* __restrict__ labels, const float* __restrict__ tex
         if (lane == 0) { sm->rowmin[r] = (short)mn; sm->rowmax[r] = (short)mx; }
     }
     __syncwarp();
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
         float box[8];
         const int rc = mb_component_box(&sm->hull, sm->rowmin, sm->rowmax, p.y, p.h, p.sx, p.ex, p.sy, p.ey, p.niter,
                                         box);
@@ -155,14 +247,7 @@ box_extract_kernel(const int* __restrict__ labels, const float* __restrict__ tex
             if (rc < 0) atomicExch(overflow, 2);
             for (int i = 0; i < 8; ++i) box[i] = 0.f;   // cannot happen for components that passed the filters
         }
-        const long long o = (long long)img * max_boxes + b;
-        float a[8];
-        int rect[4];
-        const double rw = ratios ? ratios[2 * img] : 1.0, rh = ratios ? ratios[2 * img + 1] : 1.0;
-        const int ph = page_hw ? page_hw[2 * img] : 0x7fffffff, pw = page_hw ? page_hw[2 * img + 1] : 0x7fffffff;
-        mb_adjust_and_rect(box, rw, rh, pw, ph, a, rect);
-        for (int i = 0; i < 8; ++i) { det[o * 8 + i] = box[i]; adj[o * 8 + i] = a[i]; }
-        for (int i = 0; i < 4; ++i) rects[o * 4 + i] = rect[i];
+        box_write(box, id, img, ratios, page_hw, det, adj, rects);
     }
     }
 }
@@ -192,8 +277,14 @@ extern "C" int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* li
     const size_t o_plans = off; off += mb_align_up((size_t)n_img * max_boxes * sizeof(BoxPlan), 256);
     const size_t o_ovf = off; off += 256;
     const long long slots = (long long)n_img * max_boxes;
-    const int box_grid = (int)(slots < (long long)ctx->num_sms * 32 ? slots : (long long)ctx->num_sms * 32);
-    const size_t o_boxws = off; off += mb_align_up((size_t)box_grid * sizeof(BoxSmem), 256);
+    MB_REQUIRE(ctx, slots < 0x7fffffffLL, "craft_post: n_img * max_boxes too large");
+    const long long want = (slots + BOX_WARPS - 1) / BOX_WARPS;
+    const int box_grid = (int)(want < (long long)ctx->num_sms * 4 ? want : (long long)ctx->num_sms * 4);
+    const size_t o_boxws = off; off += mb_align_up((size_t)box_grid * BOX_WARPS * sizeof(BoxSmem), 256);
+    const size_t o_big = off; off += mb_align_up((size_t)slots * 4 + 256, 256);   // big_count | pad | big_list
+    const int wd = (w + 31) / 32;
+    const size_t o_fg = off; off += mb_align_up((size_t)n_img * h * wd * 4, 256);
+    const size_t o_tx = off; off += mb_align_up((size_t)n_img * h * wd * 4, 256);
     unsigned char* s = (unsigned char*)mb_scratch(ctx, off);
     if (!s) return MB_ERR_OOM;
     int* parent = (int*)(s + o_parent);
@@ -203,15 +294,24 @@ extern "C" int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* li
     BoxPlan* plans = (BoxPlan*)(s + o_plans);
     int* ovf = (int*)(s + o_ovf);
 
-    int rc = mb_ccl_run(ctx, text_dev, link_dev, n_img, h, w, low_text, link_threshold, parent, rowcount, rowbase,
+    unsigned* fg = (unsigned*)(s + o_fg);
+    unsigned* tx = (unsigned*)(s + o_tx);
+    int rc = mb_ccl_run(ctx, text_dev, link_dev, n_img, h, w, low_text, link_threshold, parent, rowcount, rowbase, fg, tx,
                         labels_dev, n_labels_dev, raw, max_labels, ovf, stream);
     if (rc) return rc;
     box_plan_kernel<<<n_img, 1024, 0, stream>>>(raw, n_labels_dev, stats_dev, plans, mapper_dev, n_boxes_dev, ovf,
                                                 max_labels, max_boxes, h, w, text_threshold);
     MB_LAUNCH_CHECK(ctx);
-    box_extract_kernel<<<box_grid, 32, 0, stream>>>(labels_dev, text_dev, plans, n_boxes_dev, det_dev, adj_dev, rects_dev,
-                                                    ovf, n_img, max_boxes, h, w, low_text, ratios_dev, page_hw_dev,
-                                                    (BoxSmem*)(s + o_boxws));
+    int* big_count = (int*)(s + o_big);
+    int* big_list = big_count + 64;
+    MB_CUDA(ctx, cudaMemsetAsync(big_count, 0, sizeof(int), stream));
+    box_extract_small_kernel<<<(int)((slots * BOX_LANE_STRIDE + 31) / 32), 32, 0, stream>>>(labels_dev, tx, wd, plans, n_boxes_dev, det_dev,
+                                                                          adj_dev, rects_dev, big_list, big_count, n_img,
+                                                                          max_boxes, h, w, ratios_dev, page_hw_dev);
+    MB_LAUNCH_CHECK(ctx);
+    box_extract_kernel<<<box_grid, 32 * BOX_WARPS, 0, stream>>>(labels_dev, tx, wd, plans, big_list, big_count, det_dev,
+                                                                adj_dev, rects_dev, ovf, max_boxes, h, w, ratios_dev,
+                                                                page_hw_dev, (BoxSmem*)(s + o_boxws));
     MB_LAUNCH_CHECK(ctx);
     int host_ovf = 0;
     MB_CUDA(ctx, cudaMemcpyAsync(&host_ovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -22,42 +22,58 @@
 #define MB_HULL_CAP 512    // per chain; convex lattice polygons in a 4096^2 grid have < 1000 vertices
 
 struct MbPt { int x, y; };
+struct MbPtS { short x, y; };   // compact form (heat maps are at most 32767 wide / high)
 
-struct MbHullWork {
-    MbPt left[MB_HULL_CAP];     // left chain (row minima), top to bottom
-    MbPt right[MB_HULL_CAP];    // right chain (row maxima)
+// Workspace of one component.  CAP bounds each chain; PT / IX are the point and index storage types (the
+// one-thread-per-box kernel keeps a small workspace in local memory: MbHullWorkT<40, MbPtS, short>).
+template <int CAP, class PT, class IX>
+struct MbHullWorkT {
+    typedef PT pt_t;
+    typedef IX ix_t;
+    static const int cap = CAP;
+    PT left[CAP];     // left chain (row minima), top to bottom
+    PT right[CAP];    // right chain (row maxima)
     int nleft, nright;
     // merged + sorted vertex set and OpenCV hull scratch
-    MbPt v[2 * MB_HULL_CAP];
+    PT v[2 * CAP];
     int nv;
-    int order[2 * MB_HULL_CAP];     // hull output: indices into v
-    int stack[2 * MB_HULL_CAP + 4];
-    int stack2[2 * MB_HULL_CAP + 4];
-    float vx[2 * MB_HULL_CAP], vy[2 * MB_HULL_CAP], inv[2 * MB_HULL_CAP];
-    float hx[2 * MB_HULL_CAP], hy[2 * MB_HULL_CAP];
+    IX order[2 * CAP];     // hull output: indices into v
+    IX stack[2 * CAP + 4];
+    IX stack2[2 * CAP + 4];
+    float vx[2 * CAP], vy[2 * CAP], inv[2 * CAP];
+    float hx[2 * CAP], hy[2 * CAP];
     int overflow;
 };
+typedef MbHullWorkT<MB_HULL_CAP, MbPt, int> MbHullWork;
+
+template <class PT>
+MB_HD MbPt mb_pt(PT p) { MbPt q; q.x = p.x; q.y = p.y; return q; }
 
 MB_HD long long mb_cross(MbPt o, MbPt a, MbPt b) {
     return (long long)(a.x - o.x) * (b.y - o.y) - (long long)(a.y - o.y) * (b.x - o.x);
 }
 
-MB_HD void mb_hull_begin(MbHullWork* w) { w->nleft = w->nright = 0; w->overflow = 0; }
+template <class W>
+MB_HD void mb_hull_begin(W* w) { w->nleft = w->nright = 0; w->overflow = 0; }
 
 // Feed rows in increasing y; (lo, hi) are the extreme x of the (dilated) set on that row.
-MB_HD void mb_hull_push_row(MbHullWork* w, int y, int lo, int hi) {
+template <class W>
+MB_HD void mb_hull_push_row(W* w, int y, int lo, int hi) {
     MbPt pl = {lo, y}, pr = {hi, y};
-    while (w->nleft >= 2 && mb_cross(w->left[w->nleft - 2], w->left[w->nleft - 1], pl) >= 0) w->nleft--;
-    if (w->nleft < MB_HULL_CAP) w->left[w->nleft++] = pl; else w->overflow = 1;
-    while (w->nright >= 2 && mb_cross(w->right[w->nright - 2], w->right[w->nright - 1], pr) <= 0) w->nright--;
-    if (w->nright < MB_HULL_CAP) w->right[w->nright++] = pr; else w->overflow = 1;
+    typename W::pt_t sl, sr;
+    sl.x = lo; sl.y = y; sr.x = hi; sr.y = y;
+    while (w->nleft >= 2 && mb_cross(mb_pt(w->left[w->nleft - 2]), mb_pt(w->left[w->nleft - 1]), pl) >= 0) w->nleft--;
+    if (w->nleft < W::cap) w->left[w->nleft++] = sl; else w->overflow = 1;
+    while (w->nright >= 2 && mb_cross(mb_pt(w->right[w->nright - 2]), mb_pt(w->right[w->nright - 1]), pr) <= 0) w->nright--;
+    if (w->nright < W::cap) w->right[w->nright++] = sr; else w->overflow = 1;
 }
 
 MB_HD int mb_sign_ll(long long v) { return (v > 0) - (v < 0); }
 MB_HD int mb_sign_i(int v) { return (v > 0) - (v < 0); }
 
 // OpenCV Sklansky_ over points sorted by (x, y).  Returns the stack size; stack holds indices into arr.
-MB_HD int mb_sklansky(const MbPt* arr, int start, int end, int* stack, int nsign, int sign2) {
+template <class PT, class IX>
+MB_HD int mb_sklansky(const PT* arr, int start, int end, IX* stack, int nsign, int sign2) {
     int incr = end > start ? 1 : -1;
     int pprev = start, pcur = pprev + incr, pnext = pcur + incr;
     int stacksize = 3;
@@ -94,16 +110,20 @@ MB_HD int mb_sklansky(const MbPt* arr, int start, int end, int* stack, int nsign
     return --stacksize;
 }
 
-MB_HD long long mb_key(MbPt p) { return ((long long)p.y << 20) + p.x; }   // raster rank of the pixel
+template <class PT>
+MB_HD long long mb_key(PT p) { return ((long long)p.y << 20) + p.x; }   // raster rank of the pixel
 
 // Builds the OpenCV convexHull(points, clockwise=false) vertex order from the two chains.
 // Result: w->order[0..n) indexes w->v; returns n.
-MB_HD int mb_hull_finish(MbHullWork* w) {
+template <class W>
+MB_HD int mb_hull_finish(W* w) {
+    typedef typename W::pt_t PT;
+    typedef typename W::ix_t IX;
     // merge chains, dropping duplicates (first/last rows may contribute the same point twice)
     int nv = 0;
     for (int i = 0; i < w->nleft; ++i) w->v[nv++] = w->left[i];
     for (int i = 0; i < w->nright; ++i) {
-        MbPt p = w->right[i];
+        PT p = w->right[i];
         bool dup = false;
         for (int j = 0; j < w->nleft; ++j)
             if (w->left[j].x == p.x && w->left[j].y == p.y) { dup = true; break; }
@@ -111,13 +131,13 @@ MB_HD int mb_hull_finish(MbHullWork* w) {
     }
     // insertion sort by (x, y)
     for (int i = 1; i < nv; ++i) {
-        MbPt p = w->v[i];
+        PT p = w->v[i];
         int j = i - 1;
         while (j >= 0 && (w->v[j].x > p.x || (w->v[j].x == p.x && w->v[j].y > p.y))) { w->v[j + 1] = w->v[j]; --j; }
         w->v[j + 1] = p;
     }
     w->nv = nv;
-    const MbPt* arr = w->v;
+    const PT* arr = w->v;
     int total = nv;
     if (total == 0) return 0;
     int miny_ind = 0, maxy_ind = 0;
@@ -126,28 +146,28 @@ MB_HD int mb_hull_finish(MbHullWork* w) {
         if (arr[miny_ind].y > y) miny_ind = i;
         if (arr[maxy_ind].y < y) maxy_ind = i;
     }
-    int* hull = w->order;
+    IX* hull = w->order;
     int nout = 0;
     if (arr[0].x == arr[total - 1].x && arr[0].y == arr[total - 1].y) {
         hull[nout++] = 0;
         return nout;
     }
-    int* stack = w->stack;
-    int* tl_stack = stack;
+    IX* stack = w->stack;
+    IX* tl_stack = stack;
     int tl_count = mb_sklansky(arr, 0, maxy_ind, tl_stack, -1, 1);
-    int* tr_stack = stack + tl_count;
+    IX* tr_stack = stack + tl_count;
     int tr_count = mb_sklansky(arr, total - 1, maxy_ind, tr_stack, -1, -1);
     {   // clockwise == false: swap
-        int* t = tl_stack; tl_stack = tr_stack; tr_stack = t;
+        IX* t = tl_stack; tl_stack = tr_stack; tr_stack = t;
         int c = tl_count; tl_count = tr_count; tr_count = c;
     }
     for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = tl_stack[i];
     for (int i = tr_count - 1; i > 0; --i) hull[nout++] = tr_stack[i];
     int stop_idx = tr_count > 2 ? tr_stack[1] : tl_count > 2 ? tl_stack[tl_count - 2] : -1;
 
-    int* bl_stack = w->stack2;
+    IX* bl_stack = w->stack2;
     int bl_count = mb_sklansky(arr, 0, miny_ind, bl_stack, 1, -1);
-    int* br_stack = w->stack2 + bl_count;
+    IX* br_stack = w->stack2 + bl_count;
     int br_count = mb_sklansky(arr, total - 1, miny_ind, br_stack, 1, 1);
     if (stop_idx >= 0) {
         int check_idx = bl_count > 2 ? bl_stack[1] : bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1;
@@ -176,7 +196,7 @@ MB_HD int mb_hull_finish(MbHullWork* w) {
             int ascending = (max_idx + 1) % nout == min_idx;
             int i0 = ascending ? min_idx : max_idx, j = i0;
             if (i0 > 0) {
-                int* tmp = w->stack;
+                IX* tmp = w->stack;
                 for (i = 0; i < nout; ++i) {
                     int curr = hull[j];
                     tmp[i] = curr;
@@ -194,7 +214,8 @@ MB_HD int mb_hull_finish(MbHullWork* w) {
 }
 
 // OpenCV rotatingCalipers(CALIPERS_MINAREARECT). px/py: hull points (float). out[6].
-MB_HD void mb_rotating_calipers(MbHullWork* w, int n, float* out) {
+template <class W>
+MB_HD void mb_rotating_calipers(W* w, int n, float* out) {
     const float* px = w->hx; const float* py = w->hy;
     float* vx = w->vx; float* vy = w->vy; float* inv = w->inv;
     float minarea = 3.402823466e+38f;
@@ -276,7 +297,8 @@ MB_HD void mb_rotating_calipers(MbHullWork* w, int n, float* out) {
 }
 
 // cv2.minAreaRect (4.13: angle in [-90,0)) + cv2.boxPoints on the finished hull; box[8] = 4 x (x,y).
-MB_HD void mb_min_area_box(MbHullWork* w, int nh, float* box) {
+template <class W>
+MB_HD void mb_min_area_box(W* w, int nh, float* box) {
     for (int i = 0; i < nh; ++i) { w->hx[i] = (float)w->v[w->order[i]].x; w->hy[i] = (float)w->v[w->order[i]].y; }
     float cx, cy, bw, bh;
     double deg;
@@ -367,7 +389,8 @@ MB_HD void mb_adjust_and_rect(const float* box, double sx, double sy, int img_w,
 
 // One component: rowmin/rowmax hold the undilated segmap extremes for bbox rows [y0, y0+h) (empty row: min > max).
 // ROI [sx,ex) x [sy,ey), dilation (1+niter)^2 with OpenCV's anchor.  Writes det box (heat-map coords).
-MB_HD int mb_component_box(MbHullWork* w, const short* rowmin, const short* rowmax, int y0, int h, int sx, int ex,
+template <class W>
+MB_HD int mb_component_box(W* w, const short* rowmin, const short* rowmax, int y0, int h, int sx, int ex,
                            int sy, int ey, int niter, float* box) {
     const int anchor = (1 + niter) / 2;
     const int back = niter - anchor;

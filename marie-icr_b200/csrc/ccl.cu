@@ -3,11 +3,20 @@
 // Reference: marie/models/craft/craft_utils.py:32-38
 //   text_score = text > low_text; link_score = link > link_threshold (strict, float32)
 //   comb = clip(text_score + link_score, 0, 1); cv2.connectedComponentsWithStats(comb, connectivity=4)
-// OpenCV numbers components in raster order of their first pixel.  Here: union-find with min-index roots
-// (atomicMin label equivalence), then rank of each root among the roots of its image in raster order
-// (row counts -> exclusive scan -> in-row prefix), which reproduces cv2's numbering exactly.
+// OpenCV numbers components in raster order of their first pixel.
 //
-// All work is integer/byte traffic bound by HBM; kernels are grid-stride over n_img*H*W pixels.
+// The score maps are read ONCE (8 B/px) and reduced to two bit planes (1 bit/px each): fg = text|link and
+// tx = text > low_text.  Everything between that pass and the final label write works on the bit planes, 32 pixels per
+// word, with the maximal horizontal RUN as the union-find node (node id = pixel index of the run's first pixel; the
+// parent array is only ever touched at run starts):
+//   mask      text, link -> fg, tx bit words; parent[run start] = itself                     (streams 8 B/px)
+//   merge     runs that overlap a run of the row above are united (atomicMin: the root is the smallest node id,
+//             i.e. the component's first pixel in raster order)
+//   flatten   parent[run start] <- root; roots counted per image row
+//   rowscan   exclusive scan of the per-row root counts (one block per image)
+//   assign    roots get their final id = raster rank + 1 (cv2's numbering), encoded in place as -(id) - 2
+//   finalize  labels i32 written for every pixel (streams 4 B/px), per-label statistics by warp-aggregated atomics
+// Page text is sparse, so the middle passes move a few bytes per 32 pixels.
 #include "common.cuh"
 
 namespace {
@@ -39,47 +48,122 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     } while (!done);
 }
 
-// parent[i] = i (pixel index inside its image) for foreground, -1 for background
-__global__ void ccl_init_kernel(const float* __restrict__ text, const float* __restrict__ link,
-                                int* __restrict__ parent, long long total, int hw, float low_text,
-                                float link_thr) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        const bool fg = (text[i] > low_text) || (link[i] > link_thr);
-        parent[i] = fg ? (int)(i % hw) : -1;
+// first pixel (x) of the run of `row` (bit words) that contains bit `b` of word `wx`
+__device__ __forceinline__ int run_start(const unsigned* __restrict__ row, int wx, int b, unsigned m) {
+    const unsigned inv = ~m & ((b == 0) ? 0u : (0xffffffffu >> (32 - b)));   // clear bits below b
+    if (inv) return wx * 32 + (32 - __clz(inv));
+    for (int j = wx - 1; j >= 0; --j) {
+        const unsigned iv = ~row[j];
+        if (iv) return j * 32 + (32 - __clz(iv));      // one past the highest clear bit (32 -> next word's bit 0)
+    }
+    return 0;
+}
+
+// one warp per image row (grid-stride over n_img * h rows), 32 pixels = one bit word per step; words of a row:
+// wd = ceil(w / 32).  No 64-bit division anywhere on the per-word path.
+__global__ void __launch_bounds__(256)
+ccl_mask_kernel(const float* __restrict__ text, const float* __restrict__ link, unsigned* __restrict__ fg,
+                unsigned* __restrict__ tx, int* __restrict__ parent, int rows, int h, int w, int wd, float low_text,
+                float link_thr) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;                                  // words in flight per warp (loads issued before any ballot)
+    for (int rowi = warp0; rowi < rows; rowi += nwarps) {
+        const int y = rowi % h;
+        const float* trow = text + (long long)rowi * w;
+        const float* lrow = link + (long long)rowi * w;
+        int* prow = parent + (long long)rowi * w;
+        unsigned* frow = fg + (long long)rowi * wd;
+        unsigned* xrow = tx + (long long)rowi * wd;
+        unsigned prev = 0;                                // bit 31 of the previous word
+        for (int wx0 = 0; wx0 < wd; wx0 += U) {
+            float t[U], l[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = (wx0 + u) * 32 + lane;
+                t[u] = l[u] = -INFINITY;
+                if (x < w) { t[u] = __ldcs(trow + x); l[u] = __ldcs(lrow + x); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int wx = wx0 + u;
+                if (wx >= wd) break;
+                const bool tb = t[u] > low_text;
+                const unsigned mt = __ballot_sync(0xffffffffu, tb);
+                const unsigned m = __ballot_sync(0xffffffffu, tb || (l[u] > link_thr));
+                if (lane == 0) { frow[wx] = m; xrow[wx] = mt; }
+                const unsigned starts = m & ~((m << 1) | prev);
+                if ((starts >> lane) & 1u) prow[wx * 32 + lane] = y * w + wx * 32 + lane;
+                prev = m >> 31;
+            }
+        }
     }
 }
 
-__global__ void ccl_merge_kernel(int* __restrict__ parent, long long total, int hw, int w) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        if (parent[i] < 0) continue;
-        const int li = (int)(i % hw);
-        int* L = parent + (i - li);
-        const int x = li % w;
-        const bool left = (x > 0) && (L[li - 1] >= 0);
-        const bool up = (li >= w) && (L[li - w] >= 0);
-        if (left) uf_union(L, li, li - 1);
-        // the up-link is redundant when left and up-left are both foreground and already chained through the row above
-        if (up && !(left && L[li - w - 1] >= 0)) uf_union(L, li, li - w);
+// one thread per word: unite every run segment of this word with the run of the row above it touches
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(const unsigned* __restrict__ fg, int* __restrict__ parent, int n_words, int h, int w, int wd) {
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (; wi < n_words; wi += stride) {
+        const unsigned cur = fg[wi];
+        if (!cur || wi < wd) continue;
+        const unsigned up = fg[wi - wd];                 // for y == 0 this is another image's last row: rejected below
+        unsigned both = cur & up;
+        if (!both) continue;
+        const int rowi = wi / wd;
+        const int y = rowi % h;
+        if (y == 0) continue;
+        const int wx = wi - rowi * wd;
+        const unsigned* crow = fg + (long long)rowi * wd;
+        const unsigned* urow = crow - wd;
+        int* L = parent + (rowi - y) * (long long)w;     // this image's parent plane
+        // a segment that starts at bit 0 and continues the same pair of runs from the previous word is redundant
+        if ((both & 1u) && wx > 0 && (crow[wx - 1] & urow[wx - 1] & 0x80000000u)) {
+            const unsigned rest = ~both;                  // drop the leading group
+            both = rest ? (both & ~((rest & (0u - rest)) - 1u)) : 0u;
+        }
+        while (both) {
+            const int b = __ffs(both) - 1;
+            const int cs = run_start(crow, wx, b, cur);
+            const int us = run_start(urow, wx, b, up);
+            uf_union(L, y * w + cs, (y - 1) * w + us);
+            // clear this group of consecutive bits
+            const unsigned shifted = both >> b;
+            const unsigned inv = ~shifted;
+            const int len = inv ? (__ffs(inv) - 1) : 32;
+            both = (b + len >= 32) ? 0u : (both & (0xffffffffu << (b + len)));
+        }
     }
 }
 
-// parent[i] <- root; counts roots per image row
-__global__ void ccl_flatten_kernel(int* __restrict__ parent, int* __restrict__ rowcount, long long total, int hw,
-                                   int w, int h) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        if (parent[i] < 0) continue;
-        const int li = (int)(i % hw);
-        const long long img = i / hw;
-        int* L = parent + (i - li);
-        const int r = uf_find(L, li);
-        if (r != li) L[li] = r;
-        else atomicAdd(rowcount + img * h + li / w, 1);
+// one thread per word: parent[run start] <- root; counts roots per image row
+__global__ void __launch_bounds__(256)
+ccl_flatten_kernel(const unsigned* __restrict__ fg, int* __restrict__ parent, int* __restrict__ rowcount,
+                   int n_words, int h, int w, int wd) {
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (; wi < n_words; wi += stride) {
+        const unsigned m = fg[wi];
+        if (!m) continue;
+        const int rowi = wi / wd;
+        const int wx = wi - rowi * wd;
+        const unsigned prev = wx > 0 ? (fg[wi - 1] >> 31) : 0u;
+        unsigned starts = m & ~((m << 1) | prev);
+        if (!starts) continue;
+        const int y = rowi % h;
+        int* L = parent + (rowi - y) * (long long)w;
+        int roots = 0;
+        while (starts) {
+            const int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int li = y * w + wx * 32 + b;
+            const int r = uf_find(L, li);
+            if (r != li) L[li] = r;
+            else ++roots;
+        }
+        if (roots) atomicAdd(rowcount + rowi, roots);
     }
 }
 
@@ -112,7 +196,6 @@ __global__ void ccl_rowscan_kernel(const int* __restrict__ rowcount, int* __rest
                 if (lane >= o) ti += u;
             }
             warp_tot[lane] = ti - t;   // exclusive warp offsets
-            if (lane == 31) warp_tot[31] = ti - t;
         }
         __syncthreads();
         const int excl = carry + warp_tot[wid] + inc - v;
@@ -124,25 +207,49 @@ __global__ void ccl_rowscan_kernel(const int* __restrict__ rowcount, int* __rest
     if (threadIdx.x == 0) n_labels[img] = carry + 1;
 }
 
-// one warp per image row: roots get their final id, encoded in place as -(id) - 2
-__global__ void ccl_assign_kernel(int* __restrict__ parent, const int* __restrict__ rowbase, int n_img, int h,
-                                  int w) {
+// one warp per image row that holds a root: roots get their final id, encoded in place as -(id) - 2
+__global__ void ccl_assign_kernel(const unsigned* __restrict__ fg, int* __restrict__ parent,
+                                  const int* __restrict__ rowcount, const int* __restrict__ rowbase, long long rows,
+                                  int h, int w, int wd) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const long long rows = (long long)n_img * h;
     const long long rstride = (long long)gridDim.x * warps_per_block;
     for (; row < rows; row += rstride) {
+        if (rowcount[row] == 0) continue;
         const int y = (int)(row % h);
-        int* L = parent + (row / h) * (long long)h * w;
+        int* L = parent + (row - y) * (long long)w;
+        const unsigned* mrow = fg + row * wd;
         int running = rowbase[row];
-        for (int x0 = 0; x0 < w; x0 += 32) {
-            const int x = x0 + lane;
-            const int li = y * w + x;
-            const bool is_root = (x < w) && (L[li] == li);
-            const unsigned m = __ballot_sync(0xffffffffu, is_root);
-            if (is_root) L[li] = -(running + __popc(m & ((1u << lane) - 1)) + 1) - 2;
-            running += __popc(m);
+        for (int w0 = 0; w0 < wd; w0 += 32) {
+            const int wx = w0 + lane;
+            unsigned rootbits = 0;
+            if (wx < wd) {
+                const unsigned m = mrow[wx];
+                const unsigned prev = wx > 0 ? (mrow[wx - 1] >> 31) : 0u;
+                unsigned starts = m & ~((m << 1) | prev);
+                while (starts) {
+                    const int b = __ffs(starts) - 1;
+                    starts &= starts - 1;
+                    const int li = y * w + wx * 32 + b;
+                    if (L[li] == li) rootbits |= 1u << b;
+                }
+            }
+            const int cnt = __popc(rootbits);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int id = running + inc - cnt;                 // ids before this lane's first root
+            while (rootbits) {
+                const int b = __ffs(rootbits) - 1;
+                rootbits &= rootbits - 1;
+                ++id;
+                L[y * w + wx * 32 + b] = -id - 2;
+            }
+            running += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
 }
@@ -152,45 +259,74 @@ __device__ __forceinline__ int float_to_ordered(float f) {
     return i ^ ((i >> 31) & 0x7fffffff);
 }
 
-// labels[i] = final id; per-label stats via warp-aggregated atomics.
+// one warp per image row: labels for 32 pixels per step + per-(word, run) statistics.
 // stats layout per label: [area, minx, miny, maxx, maxy, max_text(ordered int), 0, 0]
-__global__ void ccl_finalize_kernel(const int* __restrict__ parent, const float* __restrict__ text,
-                                    int* __restrict__ labels, int* __restrict__ stats, int* __restrict__ overflow,
-                                    long long total, int hw, int w, int max_labels) {
-    long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(256)
+ccl_finalize_kernel(const unsigned* __restrict__ fg, const int* __restrict__ parent, const float* __restrict__ text,
+                    int* __restrict__ labels, int* __restrict__ stats, int* __restrict__ overflow, int rows, int h,
+                    int w, int wd, int max_labels) {
     const int lane = threadIdx.x & 31;
-    const long long total_up = (total + 31) / 32 * 32;   // keep warps converged for the match/reduce intrinsics
-    for (long long i = i0; i < total_up; i += stride) {
-        int id = 0;
-        int li = 0;
-        long long img = 0;
-        if (i < total) {
-            li = (int)(i % hw);
-            img = i / hw;
-            const int p = parent[i];
-            if (p < -1) id = -p - 2;
-            else if (p >= 0) id = -parent[(i - li) + p] - 2;
-            labels[i] = id;
-        }
-        const unsigned fgmask = __ballot_sync(0xffffffffu, id > 0);
-        if (id > 0) {
-            // lanes of a warp may straddle two images only when hw % 32 != 0; fold the image into the key
-            const long long key = img * (long long)max_labels + id;
-            const unsigned m = __match_any_sync(fgmask, key);
-            const int x = li % w, y = li / w;
-            const int mnx = __reduce_min_sync(m, x), mxx = __reduce_max_sync(m, x);
-            const int mny = __reduce_min_sync(m, y), mxy = __reduce_max_sync(m, y);
-            const int mt = __reduce_max_sync(m, float_to_ordered(text[i]));
-            if (lane == __ffs(m) - 1) {
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int rowi = warp0; rowi < rows; rowi += nwarps) {
+        const int y = rowi % h;
+        const int img = rowi / h;
+        const int* L = parent + (long long)(rowi - y) * w;
+        const unsigned* mrow = fg + (long long)rowi * wd;
+        int* lrow = labels + (long long)rowi * w;
+        const float* trow = text + (long long)rowi * w;
+        const unsigned mine = (lane < wd) ? mrow[lane] : 0u;      // the row's first 32 words, one per lane
+        const unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);  // which of the first 32 words hold foreground
+        const bool vec_ok = (w & 3) == 0;                         // rows are 16-byte aligned
+        int carry_id = 0;                                         // id of the run that reaches the previous word's bit 31
+        for (int wx = 0; wx < wd; ++wx) {
+            // four empty words at once: 128 zero labels as one 16-byte store per lane
+            if (vec_ok && (wx & 3) == 0 && wx + 4 <= 32 && (wx + 4) * 32 <= w && ((nz >> wx) & 0xFu) == 0u) {
+                __stcs(reinterpret_cast<int4*>(lrow + wx * 32) + lane, make_int4(0, 0, 0, 0));
+                carry_id = 0;
+                wx += 3;
+                continue;
+            }
+            const unsigned m = (wx < 32) ? __shfl_sync(0xffffffffu, mine, wx) : mrow[wx];
+            const int x = wx * 32 + lane;
+            if (m == 0) {
+                if (x < w) __stcs(lrow + x, 0);
+                carry_id = 0;
+                continue;
+            }
+            // leader of a group of consecutive bits = its lowest lane; it resolves the run's final id.  A group that
+            // starts at bit 0 and continues the previous word's run inherits that run's id.
+            const unsigned gstarts = m & ~(m << 1);
+            int id = 0;
+            if ((gstarts >> lane) & 1u) {
+                if (lane == 0 && carry_id) {
+                    id = carry_id;
+                } else {
+                    const int p = L[y * w + x];
+                    id = (p < -1) ? (-p - 2) : (-L[p] - 2);
+                }
+            }
+            const bool on = (m >> lane) & 1u;
+            const unsigned below = gstarts & (0xffffffffu >> (31 - lane));   // group starts at or below this lane
+            const int leader = on ? (31 - __clz(below)) : lane;
+            id = __shfl_sync(0xffffffffu, id, leader);
+            if (!on) id = 0;
+            if (x < w) __stcs(lrow + x, id);
+            carry_id = __shfl_sync(0xffffffffu, id, 31);
+            // statistics: one lane per group
+            const int tmax = on ? float_to_ordered(trow[x]) : (int)0x80000000;
+            const unsigned gm = __match_any_sync(0xffffffffu, on ? leader : 32 + lane);
+            const int gmax = __reduce_max_sync(gm, tmax);
+            if (on && leader == lane) {
                 if (id < max_labels) {
-                    int* s = stats + (img * max_labels + id) * 8;
-                    atomicAdd(s + 0, __popc(m));
-                    atomicMin(s + 1, mnx);
-                    atomicMin(s + 2, mny);
-                    atomicMax(s + 3, mxx);
-                    atomicMax(s + 4, mxy);
-                    atomicMax(s + 5, mt);
+                    const int len = __popc(gm);
+                    int* s = stats + ((long long)img * max_labels + id) * 8;
+                    atomicAdd(s + 0, len);
+                    atomicMin(s + 1, x);
+                    atomicMin(s + 2, y);
+                    atomicMax(s + 3, x + len - 1);
+                    atomicMax(s + 4, y);
+                    atomicMax(s + 5, gmax);
                 } else {
                     atomicExch(overflow, 1);
                 }
@@ -214,39 +350,41 @@ __global__ void ccl_stats_init_kernel(int* __restrict__ stats, long long n) {
 
 }  // namespace
 
-// Internal entry: labels + raw stats.  parent/rowcount/rowbase are caller-provided scratch.
+// Internal entry: labels + raw stats + the two bit planes.  parent / rowcount / rowbase / fg / tx are caller-provided
+// scratch (fg, tx: n_img * h * ceil(w / 32) words each; tx is consumed by the box extraction).
 int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int h, int w, float low_text,
-               float link_thr, int* parent, int* rowcount, int* rowbase, int* labels, int* n_labels, int* stats,
-               int max_labels, int* overflow, cudaStream_t stream) {
-    const long long total = (long long)n_img * h * w;
-    const int hw = h * w;
+               float link_thr, int* parent, int* rowcount, int* rowbase, unsigned* fg, unsigned* tx, int* labels,
+               int* n_labels, int* stats, int max_labels, int* overflow, cudaStream_t stream) {
+    const int wd = (w + 31) / 32;
+    const long long n_words_ll = (long long)n_img * h * wd;
+    const long long rows_ll = (long long)n_img * h;
+    MB_REQUIRE(ctx, n_words_ll < 0x7fffffffLL, "ccl: batch too large (n_img * h * ceil(w / 32) must fit 31 bits)");
+    const int n_words = (int)n_words_ll, rows = (int)rows_ll;
     const int threads = 256;
-    const int grid = (int)((total + threads - 1) / threads < (long long)ctx->num_sms * 16
-                               ? (total + threads - 1) / threads
-                               : (long long)ctx->num_sms * 16);
-    MB_CUDA(ctx, cudaMemsetAsync(rowcount, 0, sizeof(int) * (size_t)n_img * h, stream));
+    auto grid_for = [&](long long items, int per_sm) {
+        const long long want = (items + threads - 1) / threads;
+        const long long cap = (long long)ctx->num_sms * per_sm;
+        return (int)(want < cap ? want : cap);
+    };
+    MB_CUDA(ctx, cudaMemsetAsync(rowcount, 0, sizeof(int) * (size_t)rows, stream));
     MB_CUDA(ctx, cudaMemsetAsync(overflow, 0, sizeof(int), stream));
     const long long nstats = (long long)n_img * max_labels * 8;
-    ccl_stats_init_kernel<<<(int)((nstats + 255) / 256 < 4096 ? (nstats + 255) / 256 : 4096), 256, 0, stream>>>(stats, nstats);
+    ccl_stats_init_kernel<<<grid_for(nstats, 8), threads, 0, stream>>>(stats, nstats);
     MB_LAUNCH_CHECK(ctx);
-    ccl_init_kernel<<<grid, threads, 0, stream>>>(text, link, parent, total, hw, low_text, link_thr);
+    ccl_mask_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(text, link, fg, tx, parent, rows, h, w, wd,
+                                                                               low_text, link_thr);
     MB_LAUNCH_CHECK(ctx);
-    ccl_merge_kernel<<<grid, threads, 0, stream>>>(parent, total, hw, w);
+    ccl_merge_kernel<<<grid_for(n_words, 8), threads, 0, stream>>>(fg, parent, n_words, h, w, wd);
     MB_LAUNCH_CHECK(ctx);
-    ccl_flatten_kernel<<<grid, threads, 0, stream>>>(parent, rowcount, total, hw, w, h);
+    ccl_flatten_kernel<<<grid_for(n_words, 8), threads, 0, stream>>>(fg, parent, rowcount, n_words, h, w, wd);
     MB_LAUNCH_CHECK(ctx);
     ccl_rowscan_kernel<<<n_img, 1024, 0, stream>>>(rowcount, rowbase, n_labels, h);
     MB_LAUNCH_CHECK(ctx);
-    {
-        const long long rows = (long long)n_img * h;
-        const int wpb = 8;
-        const int g = (int)((rows + wpb - 1) / wpb < (long long)ctx->num_sms * 8 ? (rows + wpb - 1) / wpb
-                                                                               : (long long)ctx->num_sms * 8);
-        ccl_assign_kernel<<<g, wpb * 32, 0, stream>>>(parent, rowbase, n_img, h, w);
-        MB_LAUNCH_CHECK(ctx);
-    }
-    ccl_finalize_kernel<<<grid, threads, 0, stream>>>(parent, text, labels, stats, overflow, total, hw, w,
-                                                      max_labels);
+    ccl_assign_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(fg, parent, rowcount, rowbase, rows, h, w,
+                                                                                 wd);
+    MB_LAUNCH_CHECK(ctx);
+    ccl_finalize_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(fg, parent, text, labels, stats,
+                                                                                   overflow, rows, h, w, wd, max_labels);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }

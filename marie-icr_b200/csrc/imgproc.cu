@@ -35,38 +35,131 @@ __global__ void lin_coef_kernel(LinCoef* __restrict__ tab, int ssize, int dsize)
     tab[d] = c;
 }
 
-__global__ void page_preprocess_kernel(const uint8_t* __restrict__ pages, long long page_stride, int sh, int sw,
-                                       const LinCoef* __restrict__ xtab, const LinCoef* __restrict__ ytab, int th,
-                                       int tw, int oh, int ow, bf16* __restrict__ out, int f16) {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((float)i - 127.5f) / 127.5f;
-    __syncthreads();
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy = blockIdx.y;
-    const int page = blockIdx.z;
-    if (ox >= ow) return;
-    float v0 = -1.0f, v1 = -1.0f, v2 = -1.0f;   // zero canvas after (0 - 127.5) / 127.5
-    if (oy < th && ox < tw) {
-        const LinCoef cx = xtab[ox], cy = ytab[oy];
-        const int x0 = cx.ofs, x1 = min(cx.ofs + 1, sw - 1);
-        const int y0 = cy.ofs, y1 = min(cy.ofs + 1, sh - 1);
-        const uint8_t* p = pages + (long long)page * page_stride;
-        const uint8_t* r0 = p + ((long long)y0 * sw) * 3;
-        const uint8_t* r1 = p + ((long long)y1 * sw) * 3;
-        int res[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int s0 = r0[x0 * 3 + c] * cx.a0 + r0[x1 * 3 + c] * cx.a1;
-            const int s1 = r1[x0 * 3 + c] * cx.a0 + r1[x1 * 3 + c] * cx.a1;
-            int v = (((cy.a0 * (s0 >> 4)) >> 16) + ((cy.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
-            res[c] = min(max(v, 0), 255);
-        }
-        v0 = lut[res[0]]; v1 = lut[res[1]]; v2 = lut[res[2]];
+// One CTA = K1_COLS output columns x K1_ROWS output rows.  The source rows under the tile are staged in shared memory
+// with 16-byte loads (rows of a packed u8 page are only byte aligned, so each row is fetched as the aligned 16-byte
+// chunks that cover it and indexed with its own sub-chunk offset); a thread then owns one output column and walks
+// down the tile, keeping the horizontal sums of the current source-row pair in registers (a source row shared by two
+// output rows is filtered once).
+constexpr int K1_COLS = 256;
+constexpr int K1_ROWS = 16;
+constexpr int K1_MAX_SRC_ROWS = 40;      // source rows under 16 output rows (down-scale factor <= 2.4)
+constexpr int K1_MAX_ROW_BYTES = 2048;   // staged bytes per source row (down-scale factor <= 2.6 at 256 columns)
+
+__global__ void __launch_bounds__(K1_COLS)
+page_preprocess_kernel(const uint8_t* __restrict__ pages, long long page_stride, long long total_bytes, int sh, int sw,
+                       const LinCoef* __restrict__ xtab, const LinCoef* __restrict__ ytab, int th, int tw, int oh,
+                       int ow, bf16* __restrict__ out, int f16, int K1_ROW_BYTES) {
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    __shared__ unsigned short lut[256];
+    __shared__ int row_off[K1_MAX_SRC_ROWS];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const float v = ((float)i - 127.5f) / 127.5f;
+        lut[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
-    uint2 o;
-    o.x = pack2(v0, v1, f16);
-    o.y = pack2(v2, 0.f, f16);
-    reinterpret_cast<uint2*>(out)[((long long)page * oh + oy) * ow + ox] = o;
+    const int ox0 = blockIdx.x * K1_COLS, oy0 = blockIdx.y * K1_ROWS;
+    const int page = blockIdx.z;
+    const int ox = ox0 + threadIdx.x;
+    const int oy_end = min(oy0 + K1_ROWS, oh);
+    const unsigned short neg1 = f16 ? (unsigned short)0xBC00 : (unsigned short)0xBF80;
+    uint2* orow = reinterpret_cast<uint2*>(out) + ((long long)page * oh + oy0) * ow + ox;
+    const bool tile_has_src = (oy0 < th) && (ox0 < tw);
+    int ys0 = 0, nsrc = 0, xs0 = 0;
+    if (tile_has_src) {
+        const int oy_last = min(oy_end, th) - 1, ox_last = min(ox0 + K1_COLS, tw) - 1;
+        ys0 = ytab[oy0].ofs;
+        nsrc = min(ytab[oy_last].ofs + 1, sh - 1) - ys0 + 1;
+        xs0 = xtab[ox0].ofs;
+        const int xs1 = min(xtab[ox_last].ofs + 1, sw - 1);
+        const int nbytes = (xs1 - xs0 + 1) * 3;
+        const uint8_t* pbase = pages + (long long)page * page_stride;
+        // nsrc / nbytes exceed the staging area only for down-scale factors the launcher rejects.
+        // All (row, chunk) pairs form one flat index space so that every thread has several independent 16-byte
+        // loads in flight (a row-by-row loop serialises ~20 global-memory round trips per tile).
+        const int cpr = (nbytes + 30) >> 4;                 // chunks per row, enough for any sub-chunk offset
+        const int total = nsrc * cpr;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (i < total) {
+                    const int r = i / cpr, c = i - r * cpr;
+                    const uint8_t* g = pbase + ((long long)(ys0 + r) * sw + xs0) * 3;
+                    const uint8_t* src = g - ((uintptr_t)g & 15) + c * 16;
+                    if (src >= pages && (src + 16) <= pages + total_bytes) {
+                        v[u] = *reinterpret_cast<const uint4*>(src);
+                    } else {                               // first / last chunk of the whole buffer
+                        unsigned char b[16];
+                        for (int k = 0; k < 16; ++k)
+                            b[k] = (src + k >= pages && src + k < pages + total_bytes) ? src[k] : 0;
+                        v[u] = *reinterpret_cast<uint4*>(b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const int r = i / cpr, c = i - r * cpr;
+                    *reinterpret_cast<uint4*>(k1_smem + r * K1_ROW_BYTES + c * 16) = v[u];
+                }
+            }
+        }
+        for (int r = threadIdx.x; r < nsrc; r += blockDim.x) {
+            const uint8_t* g = pbase + ((long long)(ys0 + r) * sw + xs0) * 3;
+            row_off[r] = (int)((uintptr_t)g & 15);
+        }
+    }
+    __syncthreads();
+    if (ox >= ow) return;
+    const uint2 pad = make_uint2((unsigned)neg1 | ((unsigned)neg1 << 16), (unsigned)neg1);   // (-1, -1, -1, 0)
+    if (!tile_has_src || ox >= tw) {
+        for (int oy = oy0; oy < oy_end; ++oy) orow[(long long)(oy - oy0) * ow] = pad;
+        return;
+    }
+    const LinCoef cx = xtab[ox];
+    const int bx0 = (cx.ofs - xs0) * 3, bx1 = (min(cx.ofs + 1, sw - 1) - xs0) * 3;
+    const int a0 = cx.a0, a1 = cx.a1;
+    int ya = -1, yb = -1;                 // source rows whose horizontal sums are held in sa / sb
+    int sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
+    auto hsum = [&](int y, int* s3) {
+        const unsigned char* row = k1_smem + (y - ys0) * K1_ROW_BYTES + row_off[y - ys0];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s3[c] = row[bx0 + c] * a0 + row[bx1 + c] * a1;
+    };
+    for (int oy = oy0; oy < oy_end; ++oy) {
+        uint2 o = pad;
+        if (oy < th) {
+            const LinCoef cy = ytab[oy];
+            const int y0 = cy.ofs, y1 = min(cy.ofs + 1, sh - 1);
+            if (y0 == yb) {               // previous bottom row becomes the top row
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sa[c] = sb[c];
+                ya = yb;
+            } else if (y0 != ya) {
+                hsum(y0, sa);
+                ya = y0;
+            }
+            if (y1 == ya) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sb[c] = sa[c];
+            } else if (y1 != yb) {
+                hsum(y1, sb);
+            }
+            yb = y1;
+            unsigned short r3[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                // every term is non-negative: only the upper side of cv2's saturate_cast can trigger
+                const int v = (((cy.a0 * (sa[c] >> 4)) >> 16) + ((cy.a1 * (sb[c] >> 4)) >> 16) + 2) >> 2;
+                r3[c] = lut[min(v, 255)];
+            }
+            o.x = (unsigned)r3[0] | ((unsigned)r3[1] << 16);
+            o.y = (unsigned)r3[2];
+        }
+        orow[(long long)(oy - oy0) * ow] = o;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K9
@@ -114,6 +207,34 @@ __device__ __forceinline__ void pil_coef(int in_size, int xx, int ksize, int* xm
     *n_out = xmax;
 }
 
+// pil_coef for in_size <= OUT (filterscale = 1, support = 2, at most 5 taps): every weight evaluated once and kept in
+// registers; same operations in the same order as the generic routine.
+__device__ __forceinline__ void pil_coef_up(int in_size, int xx, int* xmin_out, int* n_out, int kk[5]) {
+    const double scale = (double)((float)in_size - 0.0f) / OUT;
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - 2.0 + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + 2.0 + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double wv[5];
+    double ww = 0.0;
+#pragma unroll
+    for (int x = 0; x < 5; ++x) {
+        wv[x] = bicubic((x + xmin - center + 0.5) * 1.0);
+        if (x < xmax) ww += wv[x];
+    }
+#pragma unroll
+    for (int x = 0; x < 5; ++x) {
+        double w = wv[x];
+        if (ww != 0.0) w /= ww;
+        const int k = (w < 0) ? (int)(-0.5 + w * (double)(1 << PREC_BITS)) : (int)(0.5 + w * (double)(1 << PREC_BITS));
+        kk[x] = x < xmax ? k : 0;
+    }
+    *xmin_out = xmin;
+    *n_out = xmax;
+}
+
 __device__ __forceinline__ int pil_ksize(int in_size) {
     const double scale = (double)((float)in_size) / OUT;
     const double filterscale = scale < 1.0 ? 1.0 : scale;
@@ -128,19 +249,21 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 // grid = (OUT / TILE_ROWS, n_crops).  layout 0: [N,3,384,384] (RGB planes); layout 1: patch rows
 // [N*576, 768] with k = c*256 + py*16 + px (the A operand of the ViT patch-embedding GEMM).
 __global__ void __launch_bounds__(K9_THREADS)
-crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, int layout, int* __restrict__ err,
-                   int f16, int smem_limit, int small_only, int tiles_per_cta) {
+crop_resize_kernel(const CropDesc* __restrict__ crops, const int* __restrict__ list, const int* __restrict__ count,
+                   bf16* __restrict__ out, int layout, int* __restrict__ err, int f16, int smem_limit,
+                   int tiles_per_cta) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ float lut[256];
     __shared__ int s_r0, s_r1;
-    const CropDesc cd = crops[blockIdx.y];
-    const int w = cd.w, h = cd.h;
-    if (w <= 0 || h <= 0) return;
-    // two launches share this kernel: the common one with a small shared-memory budget (5 CTAs/SM) takes the crops
-    // that fit it, the second one (200 KB, 1 CTA/SM) takes only the large ones
-    const bool fits_small = k9_smem_need(w, h) <= (size_t)K9_SMEM_SMALL;
-    if (small_only != (int)fits_small) return;
+    // two launches share this kernel, each walking its own work list (crop_classify_kernel): the one with a small
+    // shared-memory budget (5 CTAs/SM) and the one for large crops (200 KB, 1 CTA/SM)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (((float)i / 255.0f) - 0.5f) / 0.5f;
+    const int n_list = *count;
+    for (int li = blockIdx.y; li < n_list; li += gridDim.y) {
+    const int crop_id = list[li];
+    const CropDesc cd = crops[crop_id];
+    const int w = cd.w, h = cd.h;
+    __syncthreads();                  // previous crop is done with the tables
 
     const int ks_v = pil_ksize(h), ks_h = pil_ksize(w);
     const size_t table_bytes = (size_t)(TILE_ROWS * 2 + TILE_ROWS * ks_v + OUT * 2 + OUT * ks_h) * 4;
@@ -223,7 +346,7 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
             pg[px] = lut[clip8(acc[3 * px + 1])];
             pr[px] = lut[clip8(acc[3 * px + 2])];
         }
-        const long long n_img = blockIdx.y;
+        const long long n_img = crop_id;
         bf16* o;
         long long plane;
         if (layout == 0) {
@@ -242,6 +365,7 @@ crop_resize_kernel(const CropDesc* __restrict__ crops, bf16* __restrict__ out, i
                                                               pack2(pb[4], pb[5], f16), pack2(pb[6], pb[7], f16));
     }
 }   // tile loop
+    }   // crop loop
 }
 
 __host__ __device__ inline size_t k9_smem_need(int w, int h) {
@@ -251,6 +375,231 @@ __host__ __device__ inline size_t k9_smem_need(int w, int h) {
     const size_t tables = (size_t)(TILE_ROWS * 2 + TILE_ROWS * ks_v + OUT * 2 + OUT * ks_h) * 4;
     const size_t band = (size_t)(TILE_ROWS * sv + 2.0 * (2.0 * fv) + 4.0);    // source rows under 16 output rows + support
     return tables + (band > (size_t)(ks_v + 2) ? band : (size_t)(ks_v + 2)) * OUT * 3 + 64;
+}
+
+// ------------------------------------------------------------------------------------------------ K9, common case
+// Word crops are small (h <= ~60 rows) and are scaled UP vertically, so Pillow's vertical filter has at most five
+// taps.  One CTA owns one crop: coefficient tables once, the horizontal pass once over all source rows (the tiled
+// kernel above recomputes both per 64-row band), then the vertical pass as packed integer dot products:
+//   * the u8 intermediate is stored row-PAIR interleaved, tmp[pair][x*3+c][2], so a 32-bit word holds two vertically
+//     adjacent samples of two neighbouring values;
+//   * every 22-bit coefficient k is split exactly as k = kh * 2^11 + kl (kl = k & 2047, kh = k >> 11, both fit s16),
+//     and dp2a.{lo,hi}.s32.u32 accumulates kh- and kl-sums for two taps at once: sum k*v = (sum kh*v << 11) + sum kl*v.
+// Results are bit-identical to the tap-by-tap form.  Crops that do not fit (tall / very wide) take the tiled kernel.
+constexpr int UP_THREADS = 384;
+constexpr int UP_SMEM = 112 * 1024;      // two CTAs per SM
+constexpr int UP_MIN_PAIRS = 12;         // smallest row-pair band worth running (wide crops have large tables)
+constexpr int UP_VROW_INTS = 8;          // p0, pairs, kh[3], kl[3]
+constexpr int UP_PAIR_BYTES = OUT * 3 * 2;
+
+__host__ __device__ inline int k9_ksize(int in_size) {
+    const double scale = (double)((float)in_size) / OUT;
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    return (int)ceil(2.0 * filterscale) * 2 + 1;
+}
+
+__host__ __device__ inline size_t k9_up_tables(int w) {
+    return (size_t)OUT * UP_VROW_INTS * 4 + (size_t)OUT * 2 * 4 + (size_t)OUT * k9_ksize(w) * 4 + 512 * 2;
+}
+
+__host__ __device__ inline bool k9_fast_ok(int w, int h) {
+    if (h > OUT || h <= 0 || w <= 0) return false;
+    return k9_up_tables(w) + (size_t)UP_MIN_PAIRS * UP_PAIR_BYTES <= (size_t)UP_SMEM;
+}
+
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// grid-stride over the list of eligible crops (list[0..*count))
+__global__ void __launch_bounds__(UP_THREADS, 2)
+crop_resize_up_kernel(const CropDesc* __restrict__ crops, const int* __restrict__ list, const int* __restrict__ count,
+                      bf16* __restrict__ out, int layout, int f16) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int* vrow = reinterpret_cast<int*>(smem);                       // [OUT][8]
+    int* hb = vrow + OUT * UP_VROW_INTS;                            // [OUT][2]
+    unsigned short* lut = reinterpret_cast<unsigned short*>(hb + OUT * 2);   // [512]: index (v >> 22) + 128, clamped
+    int* hk = reinterpret_cast<int*>(lut + 512);                    // [OUT][ks_h]
+    const int n_list = *count;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+    const int crop = list[li];
+    const CropDesc cd = crops[crop];
+    const int w = cd.w, h = cd.h;
+    const int ks_h = k9_ksize(w);
+    unsigned char* tmp = reinterpret_cast<unsigned char*>(hk + OUT * ks_h);   // [pairs of a band][OUT*3][2]
+    __syncthreads();                                                // previous crop is done with the tables
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        int u = i - 128;
+        u = u < 0 ? 0 : (u > 255 ? 255 : u);
+        const float v = (((float)u / 255.0f) - 0.5f) / 0.5f;
+        lut[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+    for (int t = threadIdx.x; t < 2 * OUT; t += blockDim.x) {
+        if (t < OUT) {
+            if (w <= OUT) {
+                int kk[5], xmin, n;
+                pil_coef_up(w, t, &xmin, &n, kk);
+                hb[t * 2] = xmin; hb[t * 2 + 1] = n;
+#pragma unroll
+                for (int x = 0; x < 5; ++x) hk[t * 5 + x] = kk[x];
+            } else {
+                pil_coef(w, t, ks_h, &hb[t * 2], &hb[t * 2 + 1], hk + t * ks_h);
+            }
+        } else {
+            const int yy = t - OUT;
+            int kk[5], ymin, n;
+            pil_coef_up(h, yy, &ymin, &n, kk);
+            // taps ymin .. ymin+n-1 (n <= 5) -> row pairs p0 .. p0+pairs-1, slot s = row - 2*p0
+            const int odd = ymin & 1;
+            int k6[6];
+            k6[0] = odd ? 0 : kk[0];
+#pragma unroll
+            for (int x = 1; x < 5; ++x) k6[x] = odd ? kk[x - 1] : kk[x];
+            k6[5] = odd ? kk[4] : 0;
+            int* v = vrow + yy * UP_VROW_INTS;
+            v[0] = ymin >> 1;
+            v[1] = (odd + n + 1) >> 1;
+            for (int q = 0; q < 3; ++q) {
+                const int a = k6[2 * q], b = k6[2 * q + 1];
+                v[2 + q] = (int)(((unsigned)(a >> 11) & 0xFFFFu) | ((unsigned)(b >> 11) << 16));
+                v[5 + q] = (int)((unsigned)(a & 2047) | ((unsigned)(b & 2047) << 16));
+            }
+        }
+    }
+    __syncthreads();
+    // Output rows are processed in bands whose source row pairs fit the staging area (one band for h <= ~78).
+    const int npair = (h + 1) >> 1;
+    const int max_pairs = (int)((UP_SMEM - k9_up_tables(w)) / UP_PAIR_BYTES);
+    const int xg = threadIdx.x % (OUT / 8), slot = threadIdx.x / (OUT / 8);
+    const int xx0 = xg * 8;
+    constexpr int SLOTS = UP_THREADS / (OUT / 8);          // output rows in flight
+    for (int yb0 = 0; yb0 < OUT;) {
+        const int pf = vrow[yb0 * UP_VROW_INTS];           // first source pair of the band
+        int yb1 = yb0 + SLOTS;
+        while (yb1 < OUT) {                                 // uniform across the CTA: same table, same arithmetic
+            const int* vl = vrow + (yb1 + SLOTS - 1) * UP_VROW_INTS;
+            if (vl[0] + vl[1] - pf > max_pairs) break;
+            yb1 += SLOTS;
+        }
+        const int* vlast = vrow + (yb1 - 1) * UP_VROW_INTS;
+        const int pl = min(vlast[0] + vlast[1], npair);    // pairs past the crop carry zero coefficients only
+    // horizontal pass, two source rows per item -> tmp[pair - pf][xx*3+c][row&1]
+    for (int idx = threadIdx.x; idx < (pl - pf) * OUT; idx += blockDim.x) {
+        const int pr = pf + idx / OUT, xx = idx % OUT;
+        const int r0 = 2 * pr, r1 = (2 * pr + 1 < h) ? 2 * pr + 1 : r0;     // the odd tail row is never referenced
+        const uint8_t* s0 = cd.base + (long long)r0 * cd.pitch + hb[xx * 2] * 3;
+        const uint8_t* s1 = cd.base + (long long)r1 * cd.pitch + hb[xx * 2] * 3;
+        const int n = hb[xx * 2 + 1];
+        const int* k = hk + xx * ks_h;
+        int a0 = 1 << (PREC_BITS - 1), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+        if (ks_h == 5) {
+            // up-scale: five coefficient slots (zero past n), taps clamped to the last tap so every load stays in the row
+#pragma unroll
+            for (int x = 0; x < 5; ++x) {
+                const int kv = k[x];
+                const int o = (x < n ? x : n - 1) * 3;
+                a0 += s0[o + 0] * kv; a1 += s0[o + 1] * kv; a2 += s0[o + 2] * kv;
+                b0 += s1[o + 0] * kv; b1 += s1[o + 1] * kv; b2 += s1[o + 2] * kv;
+            }
+        } else {
+            for (int x = 0; x < n; ++x) {
+                const int kv = k[x];
+                a0 += s0[x * 3 + 0] * kv; a1 += s0[x * 3 + 1] * kv; a2 += s0[x * 3 + 2] * kv;
+                b0 += s1[x * 3 + 0] * kv; b1 += s1[x * 3 + 1] * kv; b2 += s1[x * 3 + 2] * kv;
+            }
+        }
+        unsigned short* t = reinterpret_cast<unsigned short*>(tmp + (size_t)(pr - pf) * UP_PAIR_BYTES + xx * 6);
+        t[0] = (unsigned short)(clip8(a0) | (clip8(b0) << 8));
+        t[1] = (unsigned short)(clip8(a1) | (clip8(b1) << 8));
+        t[2] = (unsigned short)(clip8(a2) | (clip8(b2) << 8));
+    }
+    __syncthreads();
+    // vertical pass: thread = 8 consecutive output pixels (24 values = 48 bytes of a pair row), SLOTS rows in flight
+    for (int yy = yb0 + slot; yy < yb1; yy += SLOTS) {
+        const int4 va = *reinterpret_cast<const int4*>(vrow + yy * UP_VROW_INTS);
+        const int4 vb4 = *reinterpret_cast<const int4*>(vrow + yy * UP_VROW_INTS + 4);
+        const int p0 = va.x - pf, pairs = va.y;
+        const int kh[3] = {va.z, va.w, vb4.x};
+        const int kl[3] = {vb4.y, vb4.z, vb4.w};
+        int ah[24], al[24];
+        const unsigned char* tb = tmp + (size_t)p0 * UP_PAIR_BYTES + xg * 48;
+        {   // first pair: always present
+            const uint4* t4 = reinterpret_cast<const uint4*>(tb);
+            const uint4 w0 = t4[0], w1 = t4[1], w2 = t4[2];
+            const unsigned wd[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                ah[2 * j] = dp2a_lo_su(kh[0], wd[j], 0);
+                ah[2 * j + 1] = dp2a_hi_su(kh[0], wd[j], 0);
+                al[2 * j] = dp2a_lo_su(kl[0], wd[j], 1 << (PREC_BITS - 1));
+                al[2 * j + 1] = dp2a_hi_su(kl[0], wd[j], 1 << (PREC_BITS - 1));
+            }
+        }
+#pragma unroll
+        for (int q = 1; q < 3; ++q) {
+            if (q < pairs) {
+                const uint4* t4 = reinterpret_cast<const uint4*>(tb + (size_t)q * UP_PAIR_BYTES);
+                const uint4 w0 = t4[0], w1 = t4[1], w2 = t4[2];
+                const unsigned wd[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    ah[2 * j] = dp2a_lo_su(kh[q], wd[j], ah[2 * j]);
+                    ah[2 * j + 1] = dp2a_hi_su(kh[q], wd[j], ah[2 * j + 1]);
+                    al[2 * j] = dp2a_lo_su(kl[q], wd[j], al[2 * j]);
+                    al[2 * j + 1] = dp2a_hi_su(kl[q], wd[j], al[2 * j + 1]);
+                }
+            }
+        }
+        unsigned short hv[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            const int tot = ah[j] * 2048 + al[j];
+            hv[j] = lut[(tot >> PREC_BITS) + 128];     // |tot >> 22| < 128 beyond [0, 255]: the table clamps
+        }
+        bf16* o;
+        long long plane;
+        if (layout == 0) {
+            o = out + (long long)crop * 3 * OUT * OUT + (long long)yy * OUT + xx0;
+            plane = (long long)OUT * OUT;
+        } else {
+            const int patch = (yy >> 4) * 24 + (xx0 >> 4);
+            o = out + ((long long)crop * 576 + patch) * 768 + (yy & 15) * 16 + (xx0 & 15);
+            plane = 256;
+        }
+        // source order is B, G, R (value j = px*3 + c): plane 0 = R (c = 2), plane 1 = G, plane 2 = B
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int sc = 2 - c;
+            uint4 q;
+            q.x = (unsigned)hv[0 * 3 + sc] | ((unsigned)hv[1 * 3 + sc] << 16);
+            q.y = (unsigned)hv[2 * 3 + sc] | ((unsigned)hv[3 * 3 + sc] << 16);
+            q.z = (unsigned)hv[4 * 3 + sc] | ((unsigned)hv[5 * 3 + sc] << 16);
+            q.w = (unsigned)hv[6 * 3 + sc] | ((unsigned)hv[7 * 3 + sc] << 16);
+            *reinterpret_cast<uint4*>(o + c * plane) = q;
+        }
+    }
+        yb0 = yb1;
+        if (yb0 < OUT) __syncthreads();                     // the next band overwrites tmp
+    }   // band loop
+    }   // crop loop
+}
+
+// crops -> three work lists: [0] fast (crop_resize_up_kernel), [1] tiled / small smem, [2] tiled / large smem
+__global__ void crop_classify_kernel(const CropDesc* __restrict__ crops, int n, int* __restrict__ counts,
+                                     int* __restrict__ lists) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int w = crops[i].w, h = crops[i].h;
+    if (w <= 0 || h <= 0) return;
+    const int cls = k9_fast_ok(w, h) ? 0 : (k9_smem_need(w, h) <= (size_t)K9_SMEM_SMALL ? 1 : 2);
+    lists[(long long)cls * n + atomicAdd(counts + cls, 1)] = i;
 }
 
 // rect (x, y, w, h) on a page -> crop descriptor of page[y:y+h+1, x:x+w+1] (numpy-style clipping), the
@@ -281,21 +630,37 @@ __global__ void crop_desc_packed_kernel(const uint8_t* __restrict__ buf, const l
     out[i] = d;
 }
 
-int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int layout, int* err, cudaStream_t stream) {
+// scratch layout behind the descriptors: counts[4] | lists[3][n]
+static size_t k9_list_bytes(int n) { return 64 + sizeof(int) * 3 * (size_t)n; }
+
+int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int layout, int* err, int* lists_scratch,
+                       cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           K9_SMEM_BYTES));
+        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM));
         attr_set = true;
     }
+    int* counts = lists_scratch;
+    int* lists = lists_scratch + 16;
     MB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), stream));
-    constexpr int TPC = 4;            // row tiles per CTA in the common launch
-    crop_resize_kernel<<<dim3(OUT / TILE_ROWS / TPC, n), K9_THREADS, K9_SMEM_SMALL, stream>>>(descs, out, layout, err, ctx->f16,
-                                                                                              K9_SMEM_SMALL, 1, TPC);
+    MB_CUDA(ctx, cudaMemsetAsync(counts, 0, 4 * sizeof(int), stream));
+    crop_classify_kernel<<<mb_cdiv(n, 256), 256, 0, stream>>>(descs, n, counts, lists);
     MB_LAUNCH_CHECK(ctx);
-    // large crops: one CTA per crop walks all 24 tiles (an empty launch then costs n CTAs, not 24 n)
-    crop_resize_kernel<<<dim3(1, n), K9_THREADS, K9_SMEM_BYTES, stream>>>(descs, out, layout, err, ctx->f16, K9_SMEM_BYTES, 0,
-                                                                          OUT / TILE_ROWS);
+    const int sms = ctx->num_sms;
+    // common case: one CTA per crop, two resident per SM
+    crop_resize_up_kernel<<<n < 2 * sms * 8 ? n : 2 * sms * 8, UP_THREADS, UP_SMEM, stream>>>(descs, lists, counts, out,
+                                                                                              layout, ctx->f16);
+    MB_LAUNCH_CHECK(ctx);
+    constexpr int TPC = 4;            // row tiles per CTA in the small-smem tiled launch
+    const int gy = n < sms * 4 ? n : sms * 4;
+    crop_resize_kernel<<<dim3(OUT / TILE_ROWS / TPC, gy), K9_THREADS, K9_SMEM_SMALL, stream>>>(
+        descs, lists + n, counts + 1, out, layout, err, ctx->f16, K9_SMEM_SMALL, TPC);
+    MB_LAUNCH_CHECK(ctx);
+    // large crops: one CTA per crop walks all 24 tiles
+    crop_resize_kernel<<<dim3(1, n < sms ? n : sms), K9_THREADS, K9_SMEM_BYTES, stream>>>(
+        descs, lists + 2 * (size_t)n, counts + 2, out, layout, err, ctx->f16, K9_SMEM_BYTES, OUT / TILE_ROWS);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -307,10 +672,12 @@ int mb_crops_from_rects(mb_ctx* ctx, const uint8_t* pages, long long page_stride
                         const int* rects, const int* page_idx, int n, bf16* out, int layout, void* desc_scratch,
                         int* err_flag, cudaStream_t stream) {
     if (n == 0) return 0;
+    // desc_scratch: descriptors [n] | work lists (k9_list_bytes)
     CropDesc* descs = (CropDesc*)desc_scratch;
+    int* lists = (int*)((unsigned char*)desc_scratch + mb_align_up(sizeof(CropDesc) * (size_t)n, 256));
     crop_desc_kernel<<<mb_cdiv(n, 128), 128, 0, stream>>>(pages, page_stride, page_h, page_w, rects, page_idx, n, descs);
     MB_LAUNCH_CHECK(ctx);
-    return launch_crop_resize(ctx, descs, n, out, layout, err_flag, stream);
+    return launch_crop_resize(ctx, descs, n, out, layout, err_flag, lists, stream);
 }
 
 extern "C" int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_pages, int page_h, int page_w,
@@ -328,9 +695,23 @@ extern "C" int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_p
     MB_LAUNCH_CHECK(ctx);
     lin_coef_kernel<<<mb_cdiv(target_h, 256), 256, 0, stream>>>(ytab, page_h, target_h);
     MB_LAUNCH_CHECK(ctx);
-    dim3 grid(mb_cdiv(out_w, 256), out_h, n_pages);
-    page_preprocess_kernel<<<grid, 256, 0, stream>>>(pages_dev, (long long)page_h * page_w * 3, page_h, page_w, xtab,
-                                                     ytab, target_h, target_w, out_h, out_w, (bf16*)out_dev, ctx->f16);
+    // staging area limits (see page_preprocess_kernel): source rows / bytes under one 256 x 16 output tile
+    MB_REQUIRE(ctx, (double)page_h / target_h * K1_ROWS + 3 <= K1_MAX_SRC_ROWS &&
+                        ((double)page_w / target_w * K1_COLS + 3) * 3 + 32 <= K1_MAX_ROW_BYTES,
+               "page_preprocess: down-scale factor above 2.4 is not supported");
+    static bool k1_attr = false;
+    if (!k1_attr) {
+        MB_CUDA(ctx, cudaFuncSetAttribute(page_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          K1_MAX_SRC_ROWS * K1_MAX_ROW_BYTES));
+        k1_attr = true;
+    }
+    const int src_rows = (int)((double)page_h / target_h * K1_ROWS) + 3;
+    dim3 grid(mb_cdiv(out_w, K1_COLS), mb_cdiv(out_h, K1_ROWS), n_pages);
+    const long long pstride = (long long)page_h * page_w * 3;
+    const int row_bytes = ((int)(((double)page_w / target_w * K1_COLS + 3) * 3) + 32 + 15) & ~15;
+    page_preprocess_kernel<<<grid, K1_COLS, (size_t)src_rows * row_bytes, stream>>>(
+        pages_dev, pstride, pstride * n_pages, page_h, page_w, xtab, ytab, target_h, target_w, out_h, out_w,
+        (bf16*)out_dev, ctx->f16, row_bytes);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -342,7 +723,8 @@ extern "C" int mb_pack_crops(mb_ctx* ctx, const uint8_t* pages_dev, int page_h, 
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_crops == 0) return 0;
     MB_REQUIRE(ctx, n_crops > 0 && (layout == 0 || layout == 1), "pack_crops: bad arguments");
-    unsigned char* s = (unsigned char*)mb_scratch(ctx, sizeof(CropDesc) * (size_t)n_crops + 512);
+    unsigned char* s = (unsigned char*)mb_scratch(ctx, mb_align_up(sizeof(CropDesc) * (size_t)n_crops, 256) + 512 +
+                                                           k9_list_bytes(n_crops));
     if (!s) return MB_ERR_OOM;
     int* err = (int*)s;
     int rc = mb_crops_from_rects(ctx, pages_dev, (long long)page_h * page_w * 3, page_h, page_w, rects_dev,
@@ -361,13 +743,15 @@ extern "C" int mb_pack_fragments(mb_ctx* ctx, const uint8_t* buf_dev, const long
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_crops == 0) return 0;
     MB_REQUIRE(ctx, n_crops > 0 && (layout == 0 || layout == 1), "pack_fragments: bad arguments");
-    unsigned char* s = (unsigned char*)mb_scratch(ctx, sizeof(CropDesc) * (size_t)n_crops + 512);
+    unsigned char* s = (unsigned char*)mb_scratch(ctx, mb_align_up(sizeof(CropDesc) * (size_t)n_crops, 256) + 512 +
+                                                           k9_list_bytes(n_crops));
     if (!s) return MB_ERR_OOM;
     int* err = (int*)s;
     CropDesc* descs = (CropDesc*)(s + 256);
+    int* lists = (int*)(s + 256 + mb_align_up(sizeof(CropDesc) * (size_t)n_crops, 256));
     crop_desc_packed_kernel<<<mb_cdiv(n_crops, 128), 128, 0, stream>>>(buf_dev, offsets_dev, hw_dev, n_crops, descs);
     MB_LAUNCH_CHECK(ctx);
-    int rc = launch_crop_resize(ctx, descs, n_crops, (bf16*)out_dev, layout, err, stream);
+    int rc = launch_crop_resize(ctx, descs, n_crops, (bf16*)out_dev, layout, err, lists, stream);
     if (rc) return rc;
     int host_err = 0;
     MB_CUDA(ctx, cudaMemcpyAsync(&host_err, err, sizeof(int), cudaMemcpyDeviceToHost, stream));

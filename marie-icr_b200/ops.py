@@ -74,10 +74,10 @@ def craft_post(text, link, text_threshold, link_threshold, low_text, ratios=None
         labels=torch.empty((n, h, w), dtype=torch.int32, device=dev),
         n_labels=torch.zeros((n,), dtype=torch.int32, device=dev),
         stats=torch.zeros((n, max_labels, 5), dtype=torch.int32, device=dev),
-        det=torch.zeros((n, max_boxes, 4, 2), dtype=torch.float32, device=dev),
-        adj=torch.zeros((n, max_boxes, 4, 2), dtype=torch.float32, device=dev),
-        rects=torch.zeros((n, max_boxes, 4), dtype=torch.int32, device=dev),
-        mapper=torch.zeros((n, max_boxes), dtype=torch.int32, device=dev),
+        det=torch.empty((n, max_boxes, 4, 2), dtype=torch.float32, device=dev),
+        adj=torch.empty((n, max_boxes, 4, 2), dtype=torch.float32, device=dev),
+        rects=torch.empty((n, max_boxes, 4), dtype=torch.int32, device=dev),
+        mapper=torch.empty((n, max_boxes), dtype=torch.int32, device=dev),
         n_boxes=torch.zeros((n,), dtype=torch.int32, device=dev),
     )
     if ratios is not None:

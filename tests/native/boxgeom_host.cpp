@@ -12,3 +12,9 @@ extern "C" void host_adjust_and_rect(const float* box, double sx, double sy, int
                                      int* rect) {
     mb_adjust_and_rect(box, sx, sy, img_w, img_h, adj, rect);
 }
+// the compact workspace of the one-thread-per-box kernel (boxes.cu box_extract_small_kernel); -1 = overflow
+extern "C" int host_component_box_small(const short* rowmin, const short* rowmax, int y0, int h, int sx, int ex, int sy,
+                                        int ey, int niter, float* box) {
+    MbHullWorkT<40, MbPtS, short> w;
+    return mb_component_box(&w, rowmin, rowmax, y0, h, sx, ex, sy, ey, niter, box);
+}

@@ -69,7 +69,7 @@ def test_host_build_of_device_geometry():
     text, link = synth.random_score_maps(5, 120, 200, n_blobs=30)
     it = craft_post.iter_components(text, link, 0.7, 0.45, 0.3)
     next(it)
-    n = 0
+    n = n_small = 0
     for k, rows, (x, y, w, h, size), (sx, ex, sy, ey), niter in it:
         ref = craft_post.component_box_restated(rows, sx, ex, sy, ey, niter)
         rmin = np.full(h, 32767, np.int16)
@@ -83,5 +83,15 @@ def test_host_build_of_device_geometry():
                                     box.ctypes.data_as(ctypes.c_void_p))
         assert rc == 1          # 1 = box written, 0 = empty component, -1 = hull workspace overflow
         assert np.array_equal(box.reshape(4, 2), ref), (k, box.reshape(4, 2), ref)
+        # the compact workspace of the one-thread-per-box kernel gives the same box (or reports overflow)
+        box2 = np.zeros(8, np.float32)
+        rc2 = lib.host_component_box_small(rmin.ctypes.data_as(ctypes.c_void_p), rmax.ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.c_int(y), ctypes.c_int(h), ctypes.c_int(sx), ctypes.c_int(ex),
+                                           ctypes.c_int(sy), ctypes.c_int(ey), ctypes.c_int(niter),
+                                           box2.ctypes.data_as(ctypes.c_void_p))
+        assert rc2 in (1, -1)
+        if rc2 == 1:
+            assert np.array_equal(box2, box), (k, box2, box)
+            n_small += 1
         n += 1
-    assert n > 5
+    assert n > 5 and n_small > 5
