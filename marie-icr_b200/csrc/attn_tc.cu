@@ -3,10 +3,14 @@
 // 105-146).  Replaces the mma.sync flash kernel (trocr.cu attention_kernel) for the encoder: ncu showed that kernel
 // pinned at the legacy HMMA pipe's rate (~255 TFLOP/s with the pipe 92 % busy, profiles/r01_attention_decode_cross.md).
 //
-// One CTA = 128 query rows of one (image, head); two CTAs per SM (112 KB smem, 256 of 512 TMEM columns each), so one
-// CTA's softmax overlaps the other's MMAs.  Per 128-key tile:
-//   warp 0      TMA: Q once; K and V tiles (two stages) straight out of the qkv activation buffer [rows, 3D]
-//   warp 1      tcgen05.mma  S[128x128] = Q K^T  (A, B K-major);  O[128x64] += P V  (B = V tile as loaded, MN-major)
+// One CTA = 128 query rows of one (image, head); two CTAs per SM (98 KB smem, 256 of 512 TMEM columns each).
+// The kernel is bound by the MUFU pipe (one ex2 per score), so the schedule keeps the softmax warps fed: S is DOUBLE
+// BUFFERED in TMEM and P in shared memory, and the MMA warp issues S(j+1) = Q K(j+1)^T before it waits for P(j) — while
+// the softmax warps work on tile j the tensor pipe already produces tile j+1, and P V of tile j runs under the softmax
+// of tile j+1.  (The first version serialised S -> softmax -> P V inside a CTA and relied on three resident CTAs to
+// overlap: ncu 331 TFLOP/s, MUFU a third busy.)  Per 64-key tile:
+//   warp 0      TMA: Q once; K and V tiles (three stages) straight out of the qkv activation buffer [rows, 3D]
+//   warp 1      tcgen05.mma  S[128x64] = Q K^T  (A, B K-major);  O[128x64] += P V  (B = V tile as loaded, MN-major)
 //   warps 2..5  one thread per query row (TMEM lane): P = exp2((S - ref) / 8 * log2 e) -> 16-bit -> shared memory in
 //               the swizzled K-major operand layout, one pass over S per tile (fixed per-row reference, re-based
 //               with an in-TMEM rescale of O only on fp16 head-room overflow); after the last tile O / l -> global
@@ -22,19 +26,23 @@ namespace {
 
 constexpr int AT_THREADS = 192;
 constexpr int TILE = 128;                 // query rows per CTA
-constexpr int KT = 64;                    // keys per step: 64 -> 65 KB smem, 128 TMEM columns, three CTAs per SM
+constexpr int KT = 64;                    // keys per step
 constexpr int HD = 64;                    // head dim
+constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = TILE * HD * 2; // 16 KB: one [128 x 64] 16-bit operand tile (128-byte rows, SW128)
 constexpr int KV_BYTES = KT * HD * 2;     // 8 KB: one K or V tile
-constexpr int P_BYTES = TILE * KT * 2;    // 16 KB: P as KT/64 [128 x 64] K-major atoms
-constexpr int AT_SMEM = 1024 + TILE_BYTES + 4 * KV_BYTES + P_BYTES;
-constexpr int TMEM_COLS_AT = (KT + HD) <= 128 ? 128 : 256;   // S: columns 0..KT-1, O: columns KT..KT+63
-constexpr int O_COL = KT;
-constexpr int AT_CTAS = KT == 64 ? 3 : 2;
+constexpr int P_BYTES = TILE * KT * 2;    // 16 KB: P as one [128 x 64] K-major atom
+constexpr int AT_SMEM = 1024 + TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES;
+constexpr int TMEM_COLS_AT = 256;         // S0: columns 0..63, S1: 64..127, O: 128..191
+constexpr int O_COL = 2 * KT;
+constexpr int AT_CTAS = 2;
+constexpr int MAX_TAIL = 2;                 // tail K / V rows are staged in the barrier page: MAX_TAIL * 256 B at +512
+static_assert(KT == 64, "P is one 64-key K-major atom per buffer");
 
 struct AttnParams {
     int T, D, heads;
     float scale_log2e;
+    const bf16* qkv;
     bf16* out;
     int f16;
     unsigned int* diag;
@@ -46,44 +54,110 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// 16-bit pack WITHOUT saturation: P of a tile that overflows the fp16 range is never consumed (the row is re-based and
+// the tile recomputed before the MMA is released), and two FMNMX per score are what made the loop issue-bound.
+template <bool F16> __device__ __forceinline__ uint32_t pack2_raw(float lo, float hi) {
+    if (F16) {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    return pack_bf16x2(lo, hi);
+}
+
+// One pass over a 64-key S tile of this thread's row: P = exp2(S * sc + ms) -> 16-bit -> shared memory (swizzled K-major
+// atom); returns the row's sum of P.  RAGGED masks keys >= valid (a partial last tile only).  TMEM loads are
+// software-pipelined: chunk c+1 is in flight while chunk c is processed.  Per score: FFMA, MUFU.EX2, FADD, half a pack.
+template <bool F16, bool RAGGED>
+__device__ __forceinline__ float attn_pass_p(uint32_t t_s, uint8_t* pbuf, int row, int valid, float ms_, float sc,
+                                             uint32_t* va, uint32_t* vb) {
+    float lsum = 0.f;
+    tmem_ld32(t_s, va);
+#pragma unroll
+    for (int ci = 0; ci < KT / 32; ++ci) {
+        uint32_t* cur = (ci & 1) ? vb : va;
+        uint32_t* nxt = (ci & 1) ? va : vb;
+        tmem_wait_ld();
+        if (ci + 1 < KT / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
+        const int c = ci * 32;
+        float pr[32];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            pr[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), sc, ms_));
+            pr[i + 1] = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), sc, ms_));
+            pr[i + 2] = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), sc, ms_));
+            pr[i + 3] = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), sc, ms_));
+            if (RAGGED) {
+                if (c + i >= valid) pr[i] = 0.f;
+                if (c + i + 1 >= valid) pr[i + 1] = 0.f;
+                if (c + i + 2 >= valid) pr[i + 2] = 0.f;
+                if (c + i + 3 >= valid) pr[i + 3] = 0.f;
+            }
+            s0 += pr[i]; s1 += pr[i + 1]; s2 += pr[i + 2]; s3 += pr[i + 3];
+        }
+        lsum += (s0 + s1) + (s2 + s3);
+        uint8_t* prow = pbuf + row * 128;
+        const int chunk0 = c >> 3;                    // first 16-byte chunk of these 32 columns inside the atom row
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack2_raw<F16>(pr[8 * q + 0], pr[8 * q + 1]);
+            w.y = pack2_raw<F16>(pr[8 * q + 2], pr[8 * q + 3]);
+            w.z = pack2_raw<F16>(pr[8 * q + 4], pr[8 * q + 5]);
+            w.w = pack2_raw<F16>(pr[8 * q + 6], pr[8 * q + 7]);
+            *reinterpret_cast<uint4*>(prow + (((chunk0 + q) ^ (row & 7)) << 4)) = w;
+        }
+    }
+    return lsum;
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // layout: [mbarriers, 1 KB] [Q] [K x2] [V x2] [P]; the dynamic segment must itself be 1024-byte aligned (128-byte
-    // swizzle) — two CTAs of 114 KB fill the SM exactly, there is no room for an alignment pad
+    // layout: [mbarriers, 1 KB] [Q] [K x3] [V x3] [P x2]; the dynamic segment must itself be 1024-byte aligned (128-byte
+    // swizzle)
     if ((smem_u32(smem_raw) & 1023u) != 0) {
         if (threadIdx.x == 0 && p.diag) atomicExch(p.diag, 0xA11C0000u);
         __trap();
     }
     uint8_t* smem = smem_raw + 1024;
     uint8_t* sQ = smem;
-    uint8_t* sK = smem + TILE_BYTES;              // 2 stages
-    uint8_t* sV = sK + 2 * KV_BYTES;              // 2 stages
-    uint8_t* sP = sV + 2 * KV_BYTES;
+    uint8_t* sK = smem + TILE_BYTES;
+    uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+    uint8_t* sP = sV + KV_STAGES * KV_BYTES;      // 2 buffers
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                 // [2]
-    uint64_t* kv_empty = bars + 3;                // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* o_full = bars + 7;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* kv_full = bars + 1;                 // [3]  TMA -> MMA
+    uint64_t* kv_empty = bars + 4;                // [3]  P V (j) retired -> TMA
+    uint64_t* s_full = bars + 7;                  // [2]  S(j) complete -> softmax
+    uint64_t* p_full = bars + 9;                  // [2]  P(j) written and S(j) consumed -> MMA (128 arrivals)
+    uint64_t* pv_done = bars + 11;                // [2]  P V (j) retired: P buffer reusable, O up to tile j complete
+    uint64_t* tail_full = bars + 13;              //      tail K / V rows landed in shared memory (cp.async, warp 0)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint8_t* sTail = smem_raw + 512;              // [MAX_TAIL][K row 128 B | V row 128 B]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * TILE, head = blockIdx.y;
     const long long img = blockIdx.z;
     const int T = p.T;
-    const int n_tiles = (T + KT - 1) / KT;
+    // T = 577 is nine 64-key tiles plus ONE key: a remainder of up to MAX_TAIL keys is folded into the epilogue on the
+    // CUDA cores (two 64-long dot products per key and row) instead of costing a whole masked tile of MUFU / MMA work
+    const int tail = (T >= KT && (T % KT) <= MAX_TAIL) ? (T % KT) : 0;
+    const int n_tiles = tail ? T / KT : (T + KT - 1) / KT;
     const int row_base = (int)(img * T);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
         mbar_init(smem_u32(q_full), 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&kv_full[i]), 1); mbar_init(smem_u32(&kv_empty[i]), 1); }
-        mbar_init(smem_u32(s_full), 1);
-        mbar_init(smem_u32(p_full), 128);
-        mbar_init(smem_u32(o_full), 1);
+        for (int i = 0; i < KV_STAGES; ++i) { mbar_init(smem_u32(&kv_full[i]), 1); mbar_init(smem_u32(&kv_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&s_full[i]), 1);
+            mbar_init(smem_u32(&p_full[i]), 128);
+            mbar_init(smem_u32(&pv_done[i]), 1);
+        }
+        mbar_init(smem_u32(tail_full), 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -97,16 +171,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
     if (warp == 0) {
+        // tail K / V rows (16 B per lane) go to shared memory asynchronously; the epilogue picks them up a few
+        // microseconds later without a global-memory round trip on its critical path
+        if (lane < 16 * tail) {
+            const int t = lane >> 4, part = lane & 15;        // part 0..7: K row, 8..15: V row
+            const bf16* g = p.qkv + ((long long)row_base + n_tiles * KT + t) * (3LL * p.D) + (part < 8 ? p.D : 2 * p.D) +
+                            head * HD + (part & 7) * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sTail + t * 256 + part * 16)), "l"(g)
+                         : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(tail_full)) : "memory");
         if (lane == 0) {
             mbar_arrive_expect_tx(smem_u32(q_full), TILE_BYTES);
             tma_load_2d(smem_u32(sQ), &tmQKV, smem_u32(q_full), head * HD, row_base + q0);
+            int st = 0, use = 0;                  // stage of tile j, number of times the ring wrapped
             for (int j = 0; j < n_tiles; ++j) {
-                const int st = j & 1;
-                mbar_wait(smem_u32(&kv_empty[st]), ((j >> 1) & 1) ^ 1, p.diag, 11);
+                mbar_wait(smem_u32(&kv_empty[st]), (use & 1) ^ 1, p.diag, 11);
                 const uint32_t fb = smem_u32(&kv_full[st]);
                 mbar_arrive_expect_tx(fb, 2 * KV_BYTES);
                 tma_load_2d(smem_u32(sK + st * KV_BYTES), &tmKV, fb, p.D + head * HD, row_base + j * KT);
                 tma_load_2d(smem_u32(sV + st * KV_BYTES), &tmKV, fb, 2 * p.D + head * HD, row_base + j * KT);
+                if (++st == KV_STAGES) { st = 0; ++use; }
             }
         }
     } else if (warp == 1) {
@@ -115,50 +200,61 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
             const uint32_t idesc_qk = (1u << 4) | ab_fmt | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
             // P V: B operand (V tile: keys x 64 contiguous head dims) is MN-major — bit 16
             const uint32_t idesc_pv = (1u << 4) | ab_fmt | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-            mbar_wait(smem_u32(q_full), 0, p.diag, 12);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j & 1;
-                mbar_wait(smem_u32(&kv_full[st]), (j >> 1) & 1, p.diag, 13);
+            const uint64_t qd = make_smem_desc(smem_u32(sQ));
+            auto issue_s = [&](int j, int st, int use) {
+                mbar_wait(smem_u32(&kv_full[st]), use & 1, p.diag, 13);
                 tcgen05_fence_after();
-                const uint64_t qd = make_smem_desc(smem_u32(sQ));
                 const uint64_t kd = make_smem_desc(smem_u32(sK + st * KV_BYTES));
+                const uint32_t d = tmem_base + (uint32_t)((j & 1) * KT);
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(tmem_base, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-                tcgen05_commit(smem_u32(s_full));
-                mbar_wait(smem_u32(p_full), j & 1, p.diag, 14);
+                    umma_bf16(d, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+                tcgen05_commit(smem_u32(&s_full[j & 1]));
+            };
+            mbar_wait(smem_u32(q_full), 0, p.diag, 12);
+            issue_s(0, 0, 0);
+            int st = 0, use = 0;                  // stage / wrap count of tile j
+            for (int j = 0; j < n_tiles; ++j) {
+                int st1 = st + 1, use1 = use;
+                if (st1 == KV_STAGES) { st1 = 0; ++use1; }
+                // S(j+1) goes to the tensor pipe before P(j) is awaited: its buffer was released by p_full(j-1), which
+                // this thread observed before issuing P V (j-1)
+                if (j + 1 < n_tiles) issue_s(j + 1, st1, use1);
+                mbar_wait(smem_u32(&p_full[j & 1]), (j >> 1) & 1, p.diag, 14);
                 tcgen05_fence_after();
                 const uint64_t vd = make_smem_desc(smem_u32(sV + st * KV_BYTES));
+                const uint64_t pd0 = make_smem_desc(smem_u32(sP + (j & 1) * P_BYTES));
 #pragma unroll
                 for (int k = 0; k < KT / 16; ++k) {
-                    // A = P: KT/64 K-major atoms of 64 keys (16 KB apart), 32 B per 16-key step inside an atom
-                    const uint64_t pd = make_smem_desc(smem_u32(sP + (k >> 2) * TILE_BYTES)) + (uint64_t)(2 * (k & 3));
-                    // B = V tile, MN-major: 16 keys = two 8-row groups of 1024 B
-                    umma_bf16(tmem_base + O_COL, pd, vd + (uint64_t)((k * 2048) >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    // A = P: 32 B per 16-key step inside the K-major atom; B = V tile, MN-major: 16 keys = two 8-row
+                    // groups of 1024 B
+                    umma_bf16(tmem_base + O_COL, pd0 + (uint64_t)(2 * k), vd + (uint64_t)((k * 2048) >> 4), idesc_pv,
+                              (j > 0 || k > 0) ? 1u : 0u);
                 }
                 tcgen05_commit(smem_u32(&kv_empty[st]));
-                tcgen05_commit(smem_u32(o_full));
+                tcgen05_commit(smem_u32(&pv_done[j & 1]));
+                st = st1; use = use1;
             }
         }
     } else {
         // ------------------------------------------------------------ softmax / correction / epilogue: one row per thread
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;                  // query row inside the tile == TMEM lane
-        const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t t_o = t_s + O_COL;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t t_o = t_lane + O_COL;
         float l_run = 0.f;
         float ms = 0.f;                                       // -(reference score) * scale * log2(e) of this row
         const float sc = p.scale_log2e;
         uint32_t va[32], vb[32];
         // The softmax is shift invariant, so instead of the running row maximum (which costs a second pass over S in
         // TMEM per tile) the row keeps ONE reference: the exact maximum of its first key tile.  Later tiles are read
-        // once; probabilities may exceed 1 and only when one passes 2^11 (fp16 operand head-room) the row is re-based:
-        // O and l are scaled in place and the tile's P is recomputed.  The reference never exceeds the true maximum,
-        // so the largest probability of a row is >= 1 and nothing underflows as a whole.
-        // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed.
-        auto pass_p = [&](int valid, float ms_, float& pmax) -> float {
-            float lsum = 0.f;
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+        // once; probabilities may exceed 1 and only when a row's tile sum passes 2^11 (fp16 operand head-room; the sum
+        // bounds every probability) the row is re-based: O and l are scaled in place and the tile's P is recomputed.
+        // The reference never exceeds the true maximum, so the largest probability of a row is >= 1 and nothing
+        // underflows as a whole.  TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed.
+        // exact maximum of the valid scores of a tile (first tile: the reference; re-basing: the new reference)
+        auto pass_max = [&](uint32_t t_s, int valid) -> float {
+            float mx = -INFINITY;
             tmem_ld32(t_s, va);
 #pragma unroll
             for (int ci = 0; ci < KT / 32; ++ci) {
@@ -167,75 +263,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
                 tmem_wait_ld();
                 if (ci + 1 < KT / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
                 const int c = ci * 32;
-                float pr[32];
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    pr[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), sc, ms_));
-                    pr[i + 1] = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), sc, ms_));
-                    pr[i + 2] = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), sc, ms_));
-                    pr[i + 3] = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), sc, ms_));
-                    if (c + 32 > valid) {                      // ragged last tile only
-                        if (c + i >= valid) pr[i] = 0.f;
-                        if (c + i + 1 >= valid) pr[i + 1] = 0.f;
-                        if (c + i + 2 >= valid) pr[i + 2] = 0.f;
-                        if (c + i + 3 >= valid) pr[i + 3] = 0.f;
-                    }
-                    s0 += pr[i]; s1 += pr[i + 1]; s2 += pr[i + 2]; s3 += pr[i + 3];
-                    m0 = fmaxf(m0, pr[i]); m1 = fmaxf(m1, pr[i + 1]); m2 = fmaxf(m2, pr[i + 2]); m3 = fmaxf(m3, pr[i + 3]);
+                    if (c + i < valid) a0 = fmaxf(a0, __uint_as_float(cur[i]));
+                    if (c + i + 1 < valid) a1 = fmaxf(a1, __uint_as_float(cur[i + 1]));
+                    if (c + i + 2 < valid) a2 = fmaxf(a2, __uint_as_float(cur[i + 2]));
+                    if (c + i + 3 < valid) a3 = fmaxf(a3, __uint_as_float(cur[i + 3]));
                 }
-                lsum += (s0 + s1) + (s2 + s3);
-                uint8_t* prow = sP + (c >> 6) * TILE_BYTES + row * 128;
-                const int chunk0 = (c & 63) >> 3;             // first 16-byte chunk of these 32 columns inside the atom row
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 w;
-                    w.x = pack2(pr[8 * q + 0], pr[8 * q + 1], F16 ? 1 : 0);
-                    w.y = pack2(pr[8 * q + 2], pr[8 * q + 3], F16 ? 1 : 0);
-                    w.z = pack2(pr[8 * q + 4], pr[8 * q + 5], F16 ? 1 : 0);
-                    w.w = pack2(pr[8 * q + 6], pr[8 * q + 7], F16 ? 1 : 0);
-                    *reinterpret_cast<uint4*>(prow + (((chunk0 + q) ^ (row & 7)) << 4)) = w;
-                }
+                mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
             }
-            pmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            return lsum;
+            return mx;
         };
         for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(smem_u32(s_full), j & 1, p.diag, 15);
+            const int b = j & 1;
+            const uint32_t t_s = t_lane + (uint32_t)(b * KT);
+            uint8_t* pbuf = sP + b * P_BYTES;
+            mbar_wait(smem_u32(&s_full[b]), (j >> 1) & 1, p.diag, 15);
+            // P buffer b was last read by P V (j-2)
+            if (j >= 2) mbar_wait(smem_u32(&pv_done[b]), ((j >> 1) - 1) & 1, p.diag, 17);
             tcgen05_fence_after();
             const int valid = T - j * KT;                     // keys >= valid are beyond this image
-            if (j == 0) {
-                // exact row maximum of the first tile = the row's reference
-                float mx = -INFINITY;
-                tmem_ld32(t_s, va);
-#pragma unroll
-                for (int ci = 0; ci < KT / 32; ++ci) {
-                    uint32_t* cur = (ci & 1) ? vb : va;
-                    uint32_t* nxt = (ci & 1) ? va : vb;
-                    tmem_wait_ld();
-                    if (ci + 1 < KT / 32) tmem_ld32(t_s + (uint32_t)((ci + 1) * 32), nxt);
-                    const int c = ci * 32;
-                    float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (c + i < valid) a0 = fmaxf(a0, __uint_as_float(cur[i]));
-                        if (c + i + 1 < valid) a1 = fmaxf(a1, __uint_as_float(cur[i + 1]));
-                        if (c + i + 2 < valid) a2 = fmaxf(a2, __uint_as_float(cur[i + 2]));
-                        if (c + i + 3 < valid) a3 = fmaxf(a3, __uint_as_float(cur[i + 3]));
-                    }
-                    mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+            const bool ragged = valid < KT;                   // CTA-uniform: a partial last tile only
+            if (j == 0) ms = -pass_max(t_s, valid) * sc;      // the row's reference
+            float lt = ragged ? attn_pass_p<F16, true>(t_s, pbuf, row, valid, ms, sc, va, vb)
+                              : attn_pass_p<F16, false>(t_s, pbuf, row, valid, ms, sc, va, vb);
+            if (__any_sync(0xffffffffu, !(lt <= 2048.f))) {
+                // re-base the rows that grew: the tile's maximum becomes the new reference (their largest probability
+                // of this tile becomes 1); everything accumulated so far shrinks by the same factor
+                const float ms_new = -pass_max(t_s, valid) * sc;   // all lanes: tcgen05.ld is warp-collective
+                float f = 1.f;
+                if (!(lt <= 2048.f)) {
+                    f = ex2_approx(ms_new - ms);              // 2^-(shift), shift > 0
+                    ms = ms_new;
                 }
-                ms = -mx * sc;
-            }
-            float pmax;
-            float lt = pass_p(valid, ms, pmax);
-            if (__any_sync(0xffffffffu, pmax > 2048.f)) {
-                // re-base the rows that grew: shift by log2(pmax) so their largest probability becomes 1
-                const float lg = pmax > 1.f ? log2f(pmax) : 0.f;
-                const float f = ex2_approx(-lg);
-                ms -= lg;
                 l_run *= f;
-                if (j > 0) {                                  // s_full(j) was committed after P V (j-1): O is complete
+                if (j > 0) {
+                    // O must hold tiles 0..j-1 completely and no P V may be in flight: P V (j) is not issued before this
+                    // thread's p_full arrival below
+                    mbar_wait(smem_u32(&pv_done[(j - 1) & 1]), ((j - 1) >> 1) & 1, p.diag, 18);
+                    tcgen05_fence_after();
 #pragma unroll 1
                     for (int c = 0; c < HD; c += 32) {
                         tmem_ld32(t_o + (uint32_t)c, vb);
@@ -246,15 +313,57 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
                     }
                     tmem_wait_st();
                 }
-                lt = pass_p(valid, ms, pmax);
+                lt = attn_pass_p<F16, true>(t_s, pbuf, row, valid, ms, sc, va, vb);
             }
             l_run += lt;
             fence_proxy_async_smem();                         // generic-proxy writes of P -> visible to the MMA (async proxy)
             tcgen05_fence_before();
-            mbar_arrive(smem_u32(p_full));
+            mbar_arrive(smem_u32(&p_full[b]));
+        }
+        // tail keys on the CUDA cores: s = q . k, p = exp2(s * sc + ms) (re-basing the row if p would leave the fp32
+        // comfort zone), folded into l and O below
+        float pt[MAX_TAIL];
+        float fo = 1.f;                                       // factor applied to the tensor-core part of O
+        if (tail) {
+            mbar_wait(smem_u32(tail_full), 0, p.diag, 19);
+            uint4 qv[8];
+            const uint8_t* qrow = sQ + row * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qv[i] = *reinterpret_cast<const uint4*>(qrow + ((i ^ (row & 7)) << 4));
+#pragma unroll
+            for (int t = 0; t < MAX_TAIL; ++t) {
+                pt[t] = 0.f;
+                if (t < tail) {
+                    const uint4* kg = reinterpret_cast<const uint4*>(sTail + t * 256);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 kk = kg[i];
+                        const uint32_t qa[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+                        const uint32_t ka[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = unpack2(qa[e], F16 ? 1 : 0), b = unpack2(ka[e], F16 ? 1 : 0);
+                            acc = fmaf(a.x, b.x, acc);
+                            acc = fmaf(a.y, b.y, acc);
+                        }
+                    }
+                    float x = fmaf(acc, sc, ms);
+                    if (x > 16.f) {                           // re-base: this key becomes the row's reference
+                        const float f = ex2_approx(-x);
+                        l_run *= f; fo *= f; ms -= x;
+#pragma unroll
+                        for (int u = 0; u < MAX_TAIL; ++u)
+                            if (u < t) pt[u] *= f;
+                        x = 0.f;
+                    }
+                    pt[t] = ex2_approx(x);
+                    l_run += pt[t];
+                }
+            }
         }
         // epilogue: O / l -> 16-bit -> global (one 128-byte row per thread)
-        mbar_wait(smem_u32(o_full), (n_tiles - 1) & 1, p.diag, 16);
+        mbar_wait(smem_u32(&pv_done[(n_tiles - 1) & 1]), ((n_tiles - 1) >> 1) & 1, p.diag, 16);
         tcgen05_fence_after();
         const float inv = 1.0f / l_run;
         const bool store = q0 + row < T;
@@ -264,14 +373,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
             uint32_t v[32];
             tmem_ld32(t_o + (uint32_t)c, v);
             tmem_wait_ld();
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]) * fo;
+            if (tail) {
+#pragma unroll
+                for (int t = 0; t < MAX_TAIL; ++t) {
+                    if (t < tail) {
+                        const uint4* vg = reinterpret_cast<const uint4*>(sTail + t * 256 + 128 + c * 2);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 vv = vg[i];
+                            const uint32_t a4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = unpack2(a4[e], F16 ? 1 : 0);
+                                o[8 * i + 2 * e] = fmaf(pt[t], a.x, o[8 * i + 2 * e]);
+                                o[8 * i + 2 * e + 1] = fmaf(pt[t], a.y, o[8 * i + 2 * e + 1]);
+                            }
+                        }
+                    }
+                }
+            }
             if (store) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint4 w;
-                    w.x = pack2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv, F16 ? 1 : 0);
-                    w.y = pack2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv, F16 ? 1 : 0);
-                    w.z = pack2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv, F16 ? 1 : 0);
-                    w.w = pack2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv, F16 ? 1 : 0);
+                    w.x = pack2(o[8 * q + 0] * inv, o[8 * q + 1] * inv, F16 ? 1 : 0);
+                    w.y = pack2(o[8 * q + 2] * inv, o[8 * q + 3] * inv, F16 ? 1 : 0);
+                    w.z = pack2(o[8 * q + 4] * inv, o[8 * q + 5] * inv, F16 ? 1 : 0);
+                    w.w = pack2(o[8 * q + 6] * inv, o[8 * q + 7] * inv, F16 ? 1 : 0);
                     *reinterpret_cast<uint4*>(orow + c + 8 * q) = w;
                 }
             }
@@ -305,7 +436,7 @@ int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D
         attr_set = true;
     }
     AttnParams p;
-    p.T = T; p.D = D; p.heads = heads; p.scale_log2e = scale_log2e; p.out = out; p.f16 = ctx->f16; p.diag = ctx->dev_diag;
+    p.T = T; p.D = D; p.heads = heads; p.scale_log2e = scale_log2e; p.qkv = qkv; p.out = out; p.f16 = ctx->f16; p.diag = ctx->dev_diag;
     dim3 grid((T + TILE - 1) / TILE, heads, n);
     if (ctx->f16) attn_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, tmkv, p);
     else attn_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, tmkv, p);
