@@ -97,6 +97,11 @@ struct TapGemm {
     // block-diagonal batches (per-head projections): batch b reads A columns [b*a_col_stride, +c0), weight rows
     // [b*w_row_stride, +n_out) and writes output / bias / residual columns [b*out_col_stride, +n_out)
     int batches = 1, a_col_stride = 0, w_row_stride = 0, out_col_stride = 0;
+    // LayerNorm folded into the GEMM (encoder qkv / fc1): A is the RAW residual stream, wgt holds W * gamma, and the
+    // epilogue computes rstd_r * (acc - mean_r * ln_c[n]) + bias[n] with ln_c[n] = sum_k wgt[n, k] and
+    // bias[n] = b[n] + sum_k beta_k W[n, k].  ln_stats: per row (-mean, rstd) pairs (trocr.cu ln_stats_kernel).
+    const float* ln_stats = nullptr;
+    const float* ln_c = nullptr;
 };
 int mb_tap_gemm(mb_ctx* ctx, const TapGemm& p, cudaStream_t stream);
 void mb_profile_drain(mb_ctx* ctx);

@@ -52,6 +52,8 @@ struct KParams {
     long long out_plane;
     int f16;               // operand / 16-bit output element type: 0 = bf16, 1 = fp16
     int batches, a_col_stride, w_row_stride, out_col_stride;   // block-diagonal (per-head) GEMMs
+    const float2* ln_stats;   // LNF: per row (-mean, rstd)
+    const float* ln_c;        // LNF: per column sum_k W'[n, k]
     unsigned int* diag;
 };
 
@@ -84,7 +86,7 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2t(float a, float b)
 // each CTA loads its own A tile and half of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256: rows
 // 0..127 accumulate in the leader's TMEM, 128..255 in the peer's), completions are multicast to both CTAs' mbarriers.
 // Per SM and k-block that is 32 KB through shared memory instead of 48 KB, and six pipeline stages instead of four.
-template <int ACT, int OUT, bool RES, bool F16, bool CG2>
+template <int ACT, int OUT, bool RES, bool F16, bool CG2, bool LNF = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const KParams p) {
@@ -272,6 +274,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const long long pix0 = ((long long)nn * p.h + hh) * p.w + row0;
             const int rows_valid = tile_exists ? min(32, p.w - row0) : 0;   // <= 0: ragged last tile / missing partner
 
+            // LNF: the (-mean, rstd) pairs of this lane's eight read-back rows, once per tile
+            float2 lst[8];
+            if (LNF) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    lst[i] = (i * 4 + rr < rows_valid) ? __ldg(p.ln_stats + pix0 + i * 4 + rr) : make_float2(0.f, 0.f);
+            }
             const int n_chunks = (p.block_n + 31) >> 5;
             // residual tile rows are prefetched one chunk ahead (the first chunk before the accumulator is even ready)
             uint2 rres[8];
@@ -328,13 +337,24 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         // activation, residual, pack, coalesced store
                         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + n0) + kk);
+                        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (LNF) c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c + nbase + n0) + kk);
                         float4 xs[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = i * 4 + rr;
                             float4 x = *reinterpret_cast<const float4*>(stage + r * 32 + ((kk ^ (r & 7)) << 2));
+                            if (LNF) {   // rstd * (acc - mean * c) + b'
+                                x.x = fmaf(fmaf(lst[i].x, c4.x, x.x), lst[i].y, b4.x);
+                                x.y = fmaf(fmaf(lst[i].x, c4.y, x.y), lst[i].y, b4.y);
+                                x.z = fmaf(fmaf(lst[i].x, c4.z, x.z), lst[i].y, b4.z);
+                                x.w = fmaf(fmaf(lst[i].x, c4.w, x.w), lst[i].y, b4.w);
+                                x.x = apply_act<ACT>(x.x); x.y = apply_act<ACT>(x.y);
+                                x.z = apply_act<ACT>(x.z); x.w = apply_act<ACT>(x.w);
+                            } else {
                             x.x = apply_act<ACT>(x.x + b4.x); x.y = apply_act<ACT>(x.y + b4.y);
                             x.z = apply_act<ACT>(x.z + b4.z); x.w = apply_act<ACT>(x.w + b4.w);
+                            }
                             if (RES) {
                                 const float2 r0 = unpack2t<F16>(rres[i].x), r1 = unpack2t<F16>(rres[i].y);
                                 x.x += r0.x; x.y += r0.y; x.z += r1.x; x.w += r1.y;
@@ -355,10 +375,17 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     } else {
                         // ragged chunk (last rows / last columns / unaligned pitch): one element per lane and row
                         const float bl = (p.bias != nullptr && lane < ncols) ? __ldg(p.bias + nbase + n0 + lane) : 0.f;
+                        const float cl = (LNF && lane < ncols) ? __ldg(p.ln_c + nbase + n0 + lane) : 0.f;
 #pragma unroll 1
                         for (int r = 0; r < rows_valid; ++r) {
                             if (lane < ncols) {
-                                float x = apply_act<ACT>(stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))] + bl);
+                                float x = stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+                                if (LNF) {
+                                    const float2 st = __ldg(p.ln_stats + pix0 + r);
+                                    x = apply_act<ACT>(fmaf(fmaf(st.x, cl, x), st.y, bl));
+                                } else {
+                                    x = apply_act<ACT>(x + bl);
+                                }
                                 if (RES) x += load16(p.residual + (pix0 + r) * p.res_ld + nbase + n0 + lane, F16);
                                 if (OUT == MB_OUT_BF16)
                                     store16(reinterpret_cast<bf16*>(p.out) + (pix0 + r) * p.out_ld + nbase + n0 + lane, x, F16);
@@ -524,7 +551,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     // two-CTA mode (cta_group::2): big 16-bit-output problems with full 256-wide N tiles; MB_GEMM2=0 disables it
     static int gemm2_env = -1;
     if (gemm2_env < 0) { const char* e = getenv("MB_GEMM2"); gemm2_env = (e && e[0] == '1') ? 1 : 0; }
-    const bool cg2 = gemm2_env == 1 && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
+    const bool cg2 = gemm2_env == 1 && g.ln_stats == nullptr && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
                      (g.batches <= 1);
     const int stage_bytes = A_STAGE_BYTES + (cg2 ? block_n / 2 : block_n) * BLOCK_K * 2;
     const int bar_bytes = BAR_BYTES + EPI_WARPS * STAGE_TILE_BYTES;
@@ -537,7 +564,11 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.f16 = ctx->f16;
     p.batches = g.batches > 0 ? g.batches : 1;
     p.a_col_stride = g.a_col_stride; p.w_row_stride = g.w_row_stride; p.out_col_stride = g.out_col_stride;
+    p.ln_stats = reinterpret_cast<const float2*>(g.ln_stats); p.ln_c = g.ln_c;
     p.diag = ctx->dev_diag;
+    const bool lnf = g.ln_stats != nullptr;
+    MB_REQUIRE(ctx, !lnf || (g.ln_c && g.out_mode == MB_OUT_BF16 && !g.residual && g.taps == 1 && g.n == 1 && g.h == 1),
+               "tap_gemm: the LayerNorm fold needs a plain 16-bit-output GEMM without residual");
 
     CUtensorMap tmA0, tmA1, tmB;
     int rc = encode_act_map(ctx, &tmA0, g.a0, g.batches > 1 ? g.a0_ld : g.c0, g.a0_ld, g.n, g.h, g.w, ctx->f16);
@@ -570,6 +601,13 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     MB_PICK(MB_ACT_NONE, MB_OUT_F32_PLANAR, false) MB_PICK(MB_ACT_RELU, MB_OUT_F32_PLANAR, false)
     MB_PICK2(MB_ACT_NONE, false) MB_PICK2(MB_ACT_NONE, true) MB_PICK2(MB_ACT_RELU, false) MB_PICK2(MB_ACT_RELU, true)
     MB_PICK2(MB_ACT_GELU, false) MB_PICK2(MB_ACT_GELU, true)
+#define MB_PICKL(A)                                                                                    \
+    if (lnf && g.act == (A))                                                                           \
+        fn = h ? (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, false, true, false, true>                  \
+               : (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, false, false, false, true>;
+    MB_PICKL(MB_ACT_NONE) MB_PICKL(MB_ACT_GELU)
+    if (lnf && g.act == MB_ACT_RELU) fn = nullptr;
+#undef MB_PICKL
 #undef MB_PICK
 #undef MB_PICK2
     if (!fn)

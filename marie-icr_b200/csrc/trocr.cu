@@ -33,6 +33,9 @@ constexpr int TOK_PAD = 1, TOK_EOS = 2;
 struct EncLayer {
     const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *proj_b, *fc1_b, *fc2_b;
     const bf16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+    // LayerNorm folded into the following GEMM (weights.py pack_trocr): W * gamma, its row sums, b + W beta
+    const bf16 *qkv_wf = nullptr, *fc1_wf = nullptr;
+    const float *qkv_c = nullptr, *qkv_bf = nullptr, *fc1_c = nullptr, *fc1_bf = nullptr;
 };
 struct DecLayer {
     const bf16 *sqkv_w, *sout_w, *cq_w, *ckv_w, *ckT_w, *cout_w, *fc1_w, *fc2_w;
@@ -54,6 +57,7 @@ struct TrocrModel {
     const bf16* embed = nullptr; const float* pe = nullptr; const bf16* out_w = nullptr;
     void* arena = nullptr; size_t arena_bytes = 0;
     unsigned long long decode_calls = 0, decode_steps = 0, decode_rows = 0;
+    bool ln_fold = true;          // encoder LayerNorms folded into qkv / fc1 when the blob carries the folded tensors (MB_LNFOLD=0 disables)
 };
 
 namespace {
@@ -822,6 +826,60 @@ bool attention_legacy() {
     return v == 1;
 }
 
+// Row statistics only: (-mean, rstd) per row, same two-pass arithmetic as layernorm_kernel.  With the LayerNorm folded
+// into the next GEMM (TapGemm::ln_stats) the normalised activations are never written: 2 B/element read instead of
+// 2 B read + 2 B written + 2 B read again by the GEMM.
+__global__ void __launch_bounds__(256) ln_stats_kernel(const bf16* __restrict__ in, float2* __restrict__ stats,
+                                                       long long rows, int D, float eps, int f16) {
+    const int lane = threadIdx.x & 31;
+    const int nv = D >> 3;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint4 nxt[LN_MAXV];
+    if (row < rows) {
+        const uint4* src = reinterpret_cast<const uint4*>(in + row * D);
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i)
+            if (lane + 32 * i < nv) nxt[i] = src[lane + 32 * i];
+    }
+    for (; row < rows; row += wstride) {
+        uint4 cur[LN_MAXV];
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) cur[i] = nxt[i];
+        if (row + wstride < rows) {
+            const uint4* src = reinterpret_cast<const uint4*>(in + (row + wstride) * D);
+#pragma unroll
+            for (int i = 0; i < LN_MAXV; ++i)
+                if (lane + 32 * i < nv) nxt[i] = src[lane + 32 * i];
+        }
+        float v[LN_MAXV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            if (lane + 32 * i < nv) {
+                const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack2(w[k], f16);
+                    v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+                    sum += f.x + f.y;
+                }
+            }
+        }
+        const float mean = warp_sum(sum) / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            if (lane + 32 * i < nv) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; sq += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+        if (lane == 0) stats[row] = make_float2(-mean, rstd);
+    }
+}
+
 int attention_setup(mb_ctx* ctx) {
     static bool done = false;
     if (done) return 0;
@@ -855,6 +913,29 @@ int layernorm(mb_ctx* ctx, const bf16* in, bf16* out, const float* g, const floa
     return 0;
 }
 
+int ln_stats(mb_ctx* ctx, const bf16* in, float* stats, long long rows, int D, float eps, cudaStream_t s) {
+    if (D % 8 != 0 || D > 256 * LN_MAXV) return mb_set_err(ctx, MB_ERR_ARG, "ln_stats: unsupported width %d", D);
+    const long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)ctx->num_sms * 8;
+    ln_stats_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(in, reinterpret_cast<float2*>(stats), rows, D, eps,
+                                                                            ctx->f16);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// GEMM over the raw residual stream with the LayerNorm folded in (see TapGemm::ln_stats)
+int gemm_ln(mb_ctx* ctx, const bf16* a, int K, const bf16* wf, long long M, int N, const float* bias_f, const float* c,
+            const float* stats, int act, void* out, cudaStream_t s) {
+    TapGemm g;
+    g.a0 = a; g.c0 = K; g.a0_ld = K;
+    g.n = 1; g.h = 1; g.w = (int)M;
+    g.wgt = wf; g.n_rows_w = N; g.n_out = N;
+    g.bias = bias_f; g.act = act;
+    g.out = out; g.out_ld = N; g.out_mode = MB_OUT_BF16;
+    g.ln_stats = stats; g.ln_c = c;
+    return mb_tap_gemm(ctx, g, s);
+}
+
 int grid1d(mb_ctx* ctx, long long total, int threads) {
     long long g = (total + threads - 1) / threads;
     const long long cap = (long long)ctx->num_sms * 16;
@@ -865,7 +946,7 @@ int grid1d(mb_ctx* ctx, long long total, int threads) {
 
 // patches [n*576, 768] -> enc_out [n*577, D]; ws must hold x, y [n*577*D] and big [n*577*max(3D, ffn)]
 int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out, bf16* x, bf16* y, bf16* big,
-           cudaStream_t s) {
+           float* stats, cudaStream_t s) {
     const int D = m->enc_dim, T = m->tokens, F = m->enc_ffn;
     const long long M = (long long)n * T;
     // patch embedding (Conv2d k=s=16 == GEMM over patch rows) into `big`, then cls/pos assembly into x
@@ -876,11 +957,22 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
         MB_LAUNCH_CHECK(ctx);
     }
     const float scale_log2e = 0.125f * 1.4426950408889634f;
+    // timing aid (tools/gpu_probe_encoder.py): MB_PROBE_SKIP=attn|ln|qkv|proj|fc1|fc2 leaves that launch class out, so
+    // its in-situ cost (sustained clocks, warm L2) is the difference of two runs.  Results are garbage when set.
+    const char* skip_env = getenv("MB_PROBE_SKIP");
+    const std::string skip = skip_env ? skip_env : "";
     for (int l = 0; l < m->enc_layers; ++l) {
         const EncLayer& L = m->enc[l];
-        RC(layernorm(ctx, x, y, L.ln1_w, L.ln1_b, M, D, 1e-6f, s));
-        RC(gemm(ctx, y, D, L.qkv_w, 3 * D, M, 3 * D, nullptr, MB_ACT_NONE, nullptr, big, MB_OUT_BF16, s));
-        if (!attention_legacy()) {
+        const bool fold = m->ln_fold && L.qkv_wf && L.fc1_wf;
+        if (fold) {
+            if (skip != "ln") RC(ln_stats(ctx, x, stats, M, D, 1e-6f, s));
+            if (skip != "qkv") RC(gemm_ln(ctx, x, D, L.qkv_wf, M, 3 * D, L.qkv_bf, L.qkv_c, stats, MB_ACT_NONE, big, s));
+        } else {
+            RC(layernorm(ctx, x, y, L.ln1_w, L.ln1_b, M, D, 1e-6f, s));
+            RC(gemm(ctx, y, D, L.qkv_w, 3 * D, M, 3 * D, nullptr, MB_ACT_NONE, nullptr, big, MB_OUT_BF16, s));
+        }
+        if (skip == "attn") {
+        } else if (!attention_legacy()) {
             RC(mb_attention_tc(ctx, big, y, n, T, D, m->enc_heads, scale_log2e, s));
         } else {
             dim3 grid((T + 63) / 64, m->enc_heads, n);
@@ -889,10 +981,15 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
             else attention_kernel<false><<<grid, 128, ATT_SMEM, s>>>(big, 3LL * D, big + D, big + 2 * D, 3LL * D, y, D, T, T, scale_log2e);
             MB_LAUNCH_CHECK(ctx);
         }
-        RC(gemm(ctx, y, D, L.proj_w, D, M, D, L.proj_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
-        RC(layernorm(ctx, x, y, L.ln2_w, L.ln2_b, M, D, 1e-6f, s));
-        RC(gemm(ctx, y, D, L.fc1_w, F, M, F, L.fc1_b, MB_ACT_GELU, nullptr, big, MB_OUT_BF16, s));
-        RC(gemm(ctx, big, F, L.fc2_w, D, M, D, L.fc2_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
+        if (skip != "proj") RC(gemm(ctx, y, D, L.proj_w, D, M, D, L.proj_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
+        if (fold) {
+            if (skip != "ln") RC(ln_stats(ctx, x, stats, M, D, 1e-6f, s));
+            if (skip != "fc1") RC(gemm_ln(ctx, x, D, L.fc1_wf, M, F, L.fc1_bf, L.fc1_c, stats, MB_ACT_GELU, big, s));
+        } else {
+            RC(layernorm(ctx, x, y, L.ln2_w, L.ln2_b, M, D, 1e-6f, s));
+            RC(gemm(ctx, y, D, L.fc1_w, F, M, F, L.fc1_b, MB_ACT_GELU, nullptr, big, MB_OUT_BF16, s));
+        }
+        if (skip != "fc2") RC(gemm(ctx, big, F, L.fc2_w, D, M, D, L.fc2_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
     }
     RC(layernorm(ctx, x, enc_out, m->norm_w, m->norm_b, M, D, 1e-6f, s));
     return 0;
@@ -1094,6 +1191,14 @@ extern "C" int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes) 
         L.ln1_w = Fp(p + "ln1.w"); L.ln1_b = Fp(p + "ln1.b"); L.ln2_w = Fp(p + "ln2.w"); L.ln2_b = Fp(p + "ln2.b");
         L.qkv_w = W(p + "qkv.w"); L.proj_w = W(p + "proj.w"); L.proj_b = Fp(p + "proj.b");
         L.fc1_w = W(p + "fc1.w"); L.fc1_b = Fp(p + "fc1.b"); L.fc2_w = W(p + "fc2.w"); L.fc2_b = Fp(p + "fc2.b");
+        if (m->blob.get(p + "qkv.wf") && m->blob.get(p + "fc1.wf")) {      // optional: LayerNorm-folded set
+            L.qkv_wf = W(p + "qkv.wf"); L.qkv_c = Fp(p + "qkv.c"); L.qkv_bf = Fp(p + "qkv.bf");
+            L.fc1_wf = W(p + "fc1.wf"); L.fc1_c = Fp(p + "fc1.c"); L.fc1_bf = Fp(p + "fc1.bf");
+        }
+    }
+    {
+        const char* e = getenv("MB_LNFOLD");
+        m->ln_fold = !(e && e[0] == '0');
     }
     m->embed = W("dec.embed"); m->pe = Fp("dec.pe"); m->out_w = W("dec.out.w");
     m->dec.resize(m->dec_layers);
@@ -1162,13 +1267,14 @@ extern "C" int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void
     const int D = m->enc_dim, T = m->tokens;
     const size_t wide = (size_t)(3 * D > m->enc_ffn ? 3 * D : m->enc_ffn);
     const size_t M = (size_t)n * T;
-    const size_t bytes = (2 * M * D + M * wide) * 2 + 1024;
+    const size_t bytes = (2 * M * D + M * wide) * 2 + M * 8 + 2048;
     RC(ensure_arena(ctx, m, bytes));
     Arena a{(unsigned char*)m->arena, 0, 0};
     bf16* x = a.take<bf16>(M * D);
     bf16* y = a.take<bf16>(M * D);
     bf16* big = a.take<bf16>(M * wide);
-    return encode(ctx, m, (const bf16*)patches_dev, n, (bf16*)enc_out_dev, x, y, big, (cudaStream_t)stream);
+    float* stats = a.take<float>(M * 2);
+    return encode(ctx, m, (const bf16*)patches_dev, n, (bf16*)enc_out_dev, x, y, big, stats, (cudaStream_t)stream);
 }
 
 // Greedy (beam 1) / beam search over encoder states.  tokens_out [n, out_ld] i32 (hypothesis incl. the final EOS,

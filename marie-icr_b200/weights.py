@@ -137,6 +137,15 @@ def pack_trocr(state_dict, cfg, dtype=torch.float16):
         t[p + "proj.w"], t[p + "proj.b"] = sd[b + "attn.proj.weight"].to(dtype), sd[b + "attn.proj.bias"]
         t[p + "fc1.w"], t[p + "fc1.b"] = sd[b + "mlp.fc1.weight"].to(dtype), sd[b + "mlp.fc1.bias"]
         t[p + "fc2.w"], t[p + "fc2.b"] = sd[b + "mlp.fc2.weight"].to(dtype), sd[b + "mlp.fc2.bias"]
+        # pre-LN blocks: LN(x) W^T + b = rstd * (x (W * gamma)^T - mean * c) + (b + W beta), c = row sums of the ROUNDED
+        # folded weights — the GEMM then reads the raw residual stream and the LayerNorm kernels disappear
+        for name, ln, bias in (("qkv", "norm1", None), ("fc1", "norm2", sd[b + "mlp.fc1.bias"])):
+            w = sd[b + ("attn.qkv.weight" if name == "qkv" else "mlp.fc1.weight")]
+            wf = (w * sd[b + ln + ".weight"][None, :]).to(dtype)
+            t[p + name + ".wf"] = wf
+            t[p + name + ".c"] = wf.double().sum(1).float()
+            bf = (w.double() @ sd[b + ln + ".bias"].double()).float()
+            t[p + name + ".bf"] = bf if bias is None else bf + bias
     t["dec.embed"] = sd["decoder.embed_tokens.weight"].to(dtype)
     half = H // 2
     freq = torch.exp(torch.arange(half, dtype=torch.float) * -(math.log(10000) / (half - 1)))
