@@ -68,9 +68,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
     q = fmaf(q, z, -0.15032003819942474f);
     q = fmaf(q, z, -0.9179494380950928f);
     q = fmaf(q, z, -1.6279493570327759f);
-    const float e = 1.0f - exp2f(q * z);
+    float e2;                                           // q * z in [-26, 0]: no denormal range handling needed
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(q * z));
+    const float e = 1.0f - e2;
     const float hx = 0.5f * x;
-    return fmaf(hx, copysignf(e, x), hx);
+    return fmaf(fabsf(hx), e, hx);                      // hx * sign(x) * e == |hx| * e: the sign rides on the operand modifier
 }
 template <int ACT> __device__ __forceinline__ float apply_act(float x) {
     if (ACT == MB_ACT_RELU) return fmaxf(x, 0.0f);
