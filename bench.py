@@ -264,6 +264,17 @@ def run_ours(args, rank, world, local_rank):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json (sustained)" if peaks else "fallback"
     achieved = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
+    # DRAM traffic of the dominant tap-GEMM launch (encoder fc1) from the committed ncu --set full capture
+    traffic, traffic_detail = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_tap_gemm_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_detail = {"unit": "bytes per launch (dram read + write)", "launch": tj["kernel"],
+                          "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
+                          "source": "profiles/r01_tap_gemm_traffic.json"}
+    except Exception:
+        pass
     st_ms, st_units = stages["ms"], stages["units"]
     per_step = {k: v / args.steps for k, v in st_ms.items()}
     # algorithmic bytes per unit: K1 55.7 MB/page, K5-K7 20.3 MB/page, K9 ~0.9 MB/crop
@@ -286,8 +297,8 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(rec_h.numel() * 4 / max(world, 1)), "crops_per_s": crops_step / sec_e2e},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "tap_gemm_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
-                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
-                     "peak_source": peak_src, "launches": prof["launches"],
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
+                     "traffic_detail": traffic_detail, "peak_source": peak_src, "launches": prof["launches"],
                      "share_of_step": prof["ms"] / ms if ms else None},
         "stages_ms_per_step": per_step, "hbm_stages": hbm,
         "clocks": clocks,

@@ -14,8 +14,8 @@
 #include "boxgeom.cuh"
 
 int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int h, int w, float low_text,
-               float link_thr, int* parent, int* rowcount, int* rowbase, unsigned* fg, unsigned* tx, int* labels,
-               int* n_labels, int* stats, int max_labels, int* overflow, cudaStream_t stream);
+               float link_thr, int* parent, int* rowcount, int* rowbase, unsigned* fg, unsigned* tx, int* wmax,
+               int* labels, int* n_labels, int* stats, int max_labels, int* overflow, cudaStream_t stream);
 
 namespace {
 
@@ -285,6 +285,7 @@ extern "C" int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* li
     const int wd = (w + 31) / 32;
     const size_t o_fg = off; off += mb_align_up((size_t)n_img * h * wd * 4, 256);
     const size_t o_tx = off; off += mb_align_up((size_t)n_img * h * wd * 4, 256);
+    const size_t o_wmax = off; off += mb_align_up((size_t)n_img * h * wd * 4, 256);
     unsigned char* s = (unsigned char*)mb_scratch(ctx, off);
     if (!s) return MB_ERR_OOM;
     int* parent = (int*)(s + o_parent);
@@ -297,7 +298,7 @@ extern "C" int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* li
     unsigned* fg = (unsigned*)(s + o_fg);
     unsigned* tx = (unsigned*)(s + o_tx);
     int rc = mb_ccl_run(ctx, text_dev, link_dev, n_img, h, w, low_text, link_threshold, parent, rowcount, rowbase, fg, tx,
-                        labels_dev, n_labels_dev, raw, max_labels, ovf, stream);
+                        (int*)(s + o_wmax), labels_dev, n_labels_dev, raw, max_labels, ovf, stream);
     if (rc) return rc;
     box_plan_kernel<<<n_img, 1024, 0, stream>>>(raw, n_labels_dev, stats_dev, plans, mapper_dev, n_boxes_dev, ovf,
                                                 max_labels, max_boxes, h, w, text_threshold);

@@ -48,6 +48,11 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     } while (!done);
 }
 
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+
 // first pixel (x) of the run of `row` (bit words) that contains bit `b` of word `wx`
 __device__ __forceinline__ int run_start(const unsigned* __restrict__ row, int wx, int b, unsigned m) {
     const unsigned inv = ~m & ((b == 0) ? 0u : (0xffffffffu >> (32 - b)));   // clear bits below b
@@ -63,8 +68,8 @@ __device__ __forceinline__ int run_start(const unsigned* __restrict__ row, int w
 // wd = ceil(w / 32).  No 64-bit division anywhere on the per-word path.
 __global__ void __launch_bounds__(256)
 ccl_mask_kernel(const float* __restrict__ text, const float* __restrict__ link, unsigned* __restrict__ fg,
-                unsigned* __restrict__ tx, int* __restrict__ parent, int rows, int h, int w, int wd, float low_text,
-                float link_thr) {
+                unsigned* __restrict__ tx, int* __restrict__ wmax, int* __restrict__ parent, int rows, int h, int w,
+                int wd, float low_text, float link_thr) {
     const int lane = threadIdx.x & 31;
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -76,6 +81,7 @@ ccl_mask_kernel(const float* __restrict__ text, const float* __restrict__ link, 
         int* prow = parent + (long long)rowi * w;
         unsigned* frow = fg + (long long)rowi * wd;
         unsigned* xrow = tx + (long long)rowi * wd;
+        int* mxrow = wmax + (long long)rowi * wd;
         unsigned prev = 0;                                // bit 31 of the previous word
         for (int wx0 = 0; wx0 < wd; wx0 += U) {
             float t[U], l[U];
@@ -91,8 +97,12 @@ ccl_mask_kernel(const float* __restrict__ text, const float* __restrict__ link, 
                 if (wx >= wd) break;
                 const bool tb = t[u] > low_text;
                 const unsigned mt = __ballot_sync(0xffffffffu, tb);
-                const unsigned m = __ballot_sync(0xffffffffu, tb || (l[u] > link_thr));
-                if (lane == 0) { frow[wx] = m; xrow[wx] = mt; }
+                const bool fgb = tb || (l[u] > link_thr);
+                const unsigned m = __ballot_sync(0xffffffffu, fgb);
+                // max text score over the word's foreground pixels (ordered-int form): the statistics pass uses it for
+                // words that hold a single run, i.e. a single component
+                const int wm = m ? __reduce_max_sync(0xffffffffu, fgb ? float_to_ordered(t[u]) : (int)0x80000000) : (int)0x80000000;
+                if (lane == 0) { frow[wx] = m; xrow[wx] = mt; mxrow[wx] = wm; }
                 const unsigned starts = m & ~((m << 1) | prev);
                 if ((starts >> lane) & 1u) prow[wx * 32 + lane] = y * w + wx * 32 + lane;
                 prev = m >> 31;
@@ -254,17 +264,12 @@ __global__ void ccl_assign_kernel(const unsigned* __restrict__ fg, int* __restri
     }
 }
 
-__device__ __forceinline__ int float_to_ordered(float f) {
-    int i = __float_as_int(f);
-    return i ^ ((i >> 31) & 0x7fffffff);
-}
-
 // one warp per image row: labels for 32 pixels per step + per-(word, run) statistics.
 // stats layout per label: [area, minx, miny, maxx, maxy, max_text(ordered int), 0, 0]
 __global__ void __launch_bounds__(256)
-ccl_finalize_kernel(const unsigned* __restrict__ fg, const int* __restrict__ parent, const float* __restrict__ text,
-                    int* __restrict__ labels, int* __restrict__ stats, int* __restrict__ overflow, int rows, int h,
-                    int w, int wd, int max_labels) {
+ccl_finalize_kernel(const unsigned* __restrict__ fg, const int* __restrict__ wmax, const int* __restrict__ parent,
+                    const float* __restrict__ text, int* __restrict__ labels, int* __restrict__ stats,
+                    int* __restrict__ overflow, int rows, int h, int w, int wd, int max_labels) {
     const int lane = threadIdx.x & 31;
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -313,6 +318,24 @@ ccl_finalize_kernel(const unsigned* __restrict__ fg, const int* __restrict__ par
             if (!on) id = 0;
             if (x < w) __stcs(lrow + x, id);
             carry_id = __shfl_sync(0xffffffffu, id, 31);
+            if ((gstarts & (gstarts - 1)) == 0) {
+                // one run in this word (the common case): everything but the id comes from bit arithmetic and the
+                // per-word maximum written by the mask pass — no per-pixel text read, no match / reduce
+                if (on && leader == lane) {
+                    if (id < max_labels) {
+                        int* s = stats + ((long long)img * max_labels + id) * 8;
+                        atomicAdd(s + 0, __popc(m));
+                        atomicMin(s + 1, x);
+                        atomicMin(s + 2, y);
+                        atomicMax(s + 3, wx * 32 + 31 - __clz(m));
+                        atomicMax(s + 4, y);
+                        atomicMax(s + 5, wmax[(long long)rowi * wd + wx]);
+                    } else {
+                        atomicExch(overflow, 1);
+                    }
+                }
+                continue;
+            }
             // statistics: one lane per group
             const int tmax = on ? float_to_ordered(trow[x]) : (int)0x80000000;
             const unsigned gm = __match_any_sync(0xffffffffu, on ? leader : 32 + lane);
@@ -351,10 +374,10 @@ __global__ void ccl_stats_init_kernel(int* __restrict__ stats, long long n) {
 }  // namespace
 
 // Internal entry: labels + raw stats + the two bit planes.  parent / rowcount / rowbase / fg / tx are caller-provided
-// scratch (fg, tx: n_img * h * ceil(w / 32) words each; tx is consumed by the box extraction).
+// scratch (fg, tx, wmax: n_img * h * ceil(w / 32) words each; tx is consumed by the box extraction).
 int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int h, int w, float low_text,
-               float link_thr, int* parent, int* rowcount, int* rowbase, unsigned* fg, unsigned* tx, int* labels,
-               int* n_labels, int* stats, int max_labels, int* overflow, cudaStream_t stream) {
+               float link_thr, int* parent, int* rowcount, int* rowbase, unsigned* fg, unsigned* tx, int* wmax,
+               int* labels, int* n_labels, int* stats, int max_labels, int* overflow, cudaStream_t stream) {
     const int wd = (w + 31) / 32;
     const long long n_words_ll = (long long)n_img * h * wd;
     const long long rows_ll = (long long)n_img * h;
@@ -371,8 +394,8 @@ int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int
     const long long nstats = (long long)n_img * max_labels * 8;
     ccl_stats_init_kernel<<<grid_for(nstats, 8), threads, 0, stream>>>(stats, nstats);
     MB_LAUNCH_CHECK(ctx);
-    ccl_mask_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(text, link, fg, tx, parent, rows, h, w, wd,
-                                                                               low_text, link_thr);
+    ccl_mask_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(text, link, fg, tx, wmax, parent, rows, h,
+                                                                               w, wd, low_text, link_thr);
     MB_LAUNCH_CHECK(ctx);
     ccl_merge_kernel<<<grid_for(n_words, 8), threads, 0, stream>>>(fg, parent, n_words, h, w, wd);
     MB_LAUNCH_CHECK(ctx);
@@ -383,7 +406,7 @@ int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int
     ccl_assign_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(fg, parent, rowcount, rowbase, rows, h, w,
                                                                                  wd);
     MB_LAUNCH_CHECK(ctx);
-    ccl_finalize_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(fg, parent, text, labels, stats,
+    ccl_finalize_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(fg, wmax, parent, text, labels, stats,
                                                                                    overflow, rows, h, w, wd, max_labels);
     MB_LAUNCH_CHECK(ctx);
     return 0;

@@ -52,6 +52,7 @@ page_preprocess_kernel(const uint8_t* __restrict__ pages, long long page_stride,
     extern __shared__ __align__(16) unsigned char k1_smem[];
     __shared__ unsigned short lut[256];
     __shared__ int row_off[K1_MAX_SRC_ROWS];
+    __shared__ LinCoef ytile[K1_ROWS];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const float v = ((float)i - 127.5f) / 127.5f;
         lut[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -63,102 +64,81 @@ page_preprocess_kernel(const uint8_t* __restrict__ pages, long long page_stride,
     const unsigned short neg1 = f16 ? (unsigned short)0xBC00 : (unsigned short)0xBF80;
     uint2* orow = reinterpret_cast<uint2*>(out) + ((long long)page * oh + oy0) * ow + ox;
     const bool tile_has_src = (oy0 < th) && (ox0 < tw);
+    const int n_src_rows_out = tile_has_src ? min(oy_end, th) - oy0 : 0;   // output rows of the tile that have source
     int ys0 = 0, nsrc = 0, xs0 = 0;
     if (tile_has_src) {
-        const int oy_last = min(oy_end, th) - 1, ox_last = min(ox0 + K1_COLS, tw) - 1;
+        if (threadIdx.x < n_src_rows_out) ytile[threadIdx.x] = ytab[oy0 + threadIdx.x];
+        const int oy_last = oy0 + n_src_rows_out - 1, ox_last = min(ox0 + K1_COLS, tw) - 1;
         ys0 = ytab[oy0].ofs;
         nsrc = min(ytab[oy_last].ofs + 1, sh - 1) - ys0 + 1;
         xs0 = xtab[ox0].ofs;
         const int xs1 = min(xtab[ox_last].ofs + 1, sw - 1);
         const int nbytes = (xs1 - xs0 + 1) * 3;
         const uint8_t* pbase = pages + (long long)page * page_stride;
-        // nsrc / nbytes exceed the staging area only for down-scale factors the launcher rejects.
-        // All (row, chunk) pairs form one flat index space so that every thread has several independent 16-byte
-        // loads in flight (a row-by-row loop serialises ~20 global-memory round trips per tile).
+        // nsrc / nbytes exceed the staging area only for down-scale factors the launcher rejects.  Warp w stages rows
+        // w, w+8, ...; lanes take the row's aligned 16-byte chunks, so a thread has several independent loads in flight
+        // (a row-by-row loop over the whole CTA serialised ~20 global-memory round trips per tile).
         const int cpr = (nbytes + 30) >> 4;                 // chunks per row, enough for any sub-chunk offset
-        const int total = nsrc * cpr;
-        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-            uint4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (i < total) {
-                    const int r = i / cpr, c = i - r * cpr;
-                    const uint8_t* g = pbase + ((long long)(ys0 + r) * sw + xs0) * 3;
-                    const uint8_t* src = g - ((uintptr_t)g & 15) + c * 16;
-                    if (src >= pages && (src + 16) <= pages + total_bytes) {
-                        v[u] = *reinterpret_cast<const uint4*>(src);
-                    } else {                               // first / last chunk of the whole buffer
-                        unsigned char b[16];
-                        for (int k = 0; k < 16; ++k)
-                            b[k] = (src + k >= pages && src + k < pages + total_bytes) ? src[k] : 0;
-                        v[u] = *reinterpret_cast<uint4*>(b);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < total) {
-                    const int r = i / cpr, c = i - r * cpr;
-                    *reinterpret_cast<uint4*>(k1_smem + r * K1_ROW_BYTES + c * 16) = v[u];
-                }
-            }
-        }
-        for (int r = threadIdx.x; r < nsrc; r += blockDim.x) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < nsrc; r += K1_COLS / 32) {
             const uint8_t* g = pbase + ((long long)(ys0 + r) * sw + xs0) * 3;
-            row_off[r] = (int)((uintptr_t)g & 15);
+            const int sub = (int)((uintptr_t)g & 15);
+            if (lane == 0) row_off[r] = sub;
+            unsigned char* dst = k1_smem + r * K1_ROW_BYTES;
+#pragma unroll 3
+            for (int c = lane; c < cpr; c += 32) {
+                const uint8_t* src = g - sub + c * 16;
+                uint4 v;
+                if (src >= pages && (src + 16) <= pages + total_bytes) {
+                    v = *reinterpret_cast<const uint4*>(src);
+                } else {                                   // first / last chunk of the whole buffer
+                    unsigned char b[16];
+#pragma unroll 1
+                    for (int k = 0; k < 16; ++k) b[k] = (src + k >= pages && src + k < pages + total_bytes) ? src[k] : 0;
+                    v = *reinterpret_cast<uint4*>(b);
+                }
+                *reinterpret_cast<uint4*>(dst + c * 16) = v;
+            }
         }
     }
     __syncthreads();
     if (ox >= ow) return;
     const uint2 pad = make_uint2((unsigned)neg1 | ((unsigned)neg1 << 16), (unsigned)neg1);   // (-1, -1, -1, 0)
-    if (!tile_has_src || ox >= tw) {
-        for (int oy = oy0; oy < oy_end; ++oy) orow[(long long)(oy - oy0) * ow] = pad;
-        return;
-    }
-    const LinCoef cx = xtab[ox];
-    const int bx0 = (cx.ofs - xs0) * 3, bx1 = (min(cx.ofs + 1, sw - 1) - xs0) * 3;
-    const int a0 = cx.a0, a1 = cx.a1;
-    int ya = -1, yb = -1;                 // source rows whose horizontal sums are held in sa / sb
-    int sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
-    auto hsum = [&](int y, int* s3) {
-        const unsigned char* row = k1_smem + (y - ys0) * K1_ROW_BYTES + row_off[y - ys0];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) s3[c] = row[bx0 + c] * a0 + row[bx1 + c] * a1;
-    };
-    for (int oy = oy0; oy < oy_end; ++oy) {
-        uint2 o = pad;
-        if (oy < th) {
-            const LinCoef cy = ytab[oy];
-            const int y0 = cy.ofs, y1 = min(cy.ofs + 1, sh - 1);
-            if (y0 == yb) {               // previous bottom row becomes the top row
-#pragma unroll
-                for (int c = 0; c < 3; ++c) sa[c] = sb[c];
-                ya = yb;
-            } else if (y0 != ya) {
-                hsum(y0, sa);
-                ya = y0;
-            }
-            if (y1 == ya) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) sb[c] = sa[c];
-            } else if (y1 != yb) {
-                hsum(y1, sb);
-            }
-            yb = y1;
-            unsigned short r3[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
+    int k = 0;                                              // next output row of the tile
+    if (tile_has_src && ox < tw) {
+        const LinCoef cx = xtab[ox];
+        const int bx0 = (cx.ofs - xs0) * 3, bx1 = (min(cx.ofs + 1, sw - 1) - xs0) * 3;
+        const int a0 = cx.a0, a1 = cx.a1;
+        // walk the staged source rows once: row r is filtered horizontally (one code path), then every output row whose
+        // LOWER source row is r is emitted from (previous, current) — output rows are ordered by source row
+        int prev0 = 0, prev1 = 0, prev2 = 0;
+        for (int r = 0; r < nsrc; ++r) {
+            const unsigned char* row = k1_smem + r * K1_ROW_BYTES + row_off[r];
+            const int c0 = row[bx0] * a0 + row[bx1] * a1;
+            const int c1 = row[bx0 + 1] * a0 + row[bx1 + 1] * a1;
+            const int c2 = row[bx0 + 2] * a0 + row[bx1 + 2] * a1;
+            while (k < n_src_rows_out) {                    // CTA-uniform
+                const LinCoef cy = ytile[k];
+                if (min(cy.ofs + 1, sh - 1) - ys0 != r) break;
+                const bool same = cy.ofs - ys0 == r;        // clamped bottom edge: both source rows are r
+                const int t0 = same ? c0 : prev0, t1 = same ? c1 : prev1, t2 = same ? c2 : prev2;
                 // every term is non-negative: only the upper side of cv2's saturate_cast can trigger
-                const int v = (((cy.a0 * (sa[c] >> 4)) >> 16) + ((cy.a1 * (sb[c] >> 4)) >> 16) + 2) >> 2;
-                r3[c] = lut[min(v, 255)];
+                const int v0 = (((cy.a0 * (t0 >> 4)) >> 16) + ((cy.a1 * (c0 >> 4)) >> 16) + 2) >> 2;
+                const int v1 = (((cy.a0 * (t1 >> 4)) >> 16) + ((cy.a1 * (c1 >> 4)) >> 16) + 2) >> 2;
+                const int v2 = (((cy.a0 * (t2 >> 4)) >> 16) + ((cy.a1 * (c2 >> 4)) >> 16) + 2) >> 2;
+                uint2 o;
+                o.x = (unsigned)lut[min(v0, 255)] | ((unsigned)lut[min(v1, 255)] << 16);
+                o.y = (unsigned)lut[min(v2, 255)];
+                *orow = o;
+                orow += ow;
+                ++k;
             }
-            o.x = (unsigned)r3[0] | ((unsigned)r3[1] << 16);
-            o.y = (unsigned)r3[2];
+            prev0 = c0; prev1 = c1; prev2 = c2;
         }
-        orow[(long long)(oy - oy0) * ow] = o;
+    }
+    for (; oy0 + k < oy_end; ++k) {                         // canvas rows / columns beyond the resized page
+        *orow = pad;
+        orow += ow;
     }
 }
 
