@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
 constexpr int XE_KEYS = 32;
 template <bool F16, int ESLICE, int WARPS, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) dec_cross_enc_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ enc,
-                                                                bf16* __restrict__ ctxo, int T, int heads) {
+                                                                bf16* __restrict__ ctxo, int T, int heads,
+                                                                const unsigned char* __restrict__ finished) {
     constexpr int E = ESLICE * WARPS;
     constexpr int NT = WARPS * 32;
     constexpr int ROWB = E * 2;                       // bytes per smem row
@@ -398,6 +399,10 @@ __global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) d
     float* sS = reinterpret_cast<float*>(sE + STAGES * XE_KEYS * ROWB);   // [WARPS][16][32] partial scores
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long crop = blockIdx.x;
+    // a crop whose hypothesis has ended (EOS chosen in an earlier step) is dropped from the batch by the reference's
+    // generator (generator.py:266-303); here its row stays in place and simply stops reading its encoder states — the
+    // 0.9 MB per crop and layer that bound this kernel.  Its stale context row is never looked at again.
+    if (finished != nullptr && finished[crop]) return;
     const bf16* qbase = qp + crop * heads * E;     // heads <= 16 rows; the rest of the m16 tile is zero
     const bf16* ebase = enc + crop * T * E;
     const int n_tiles = (T + XE_KEYS - 1) / XE_KEYS;
@@ -1052,14 +1057,15 @@ size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* b
 
 // one decoder step for all R rows: tokens[:, step] -> logits [R, V]
 template <bool F16, int ESLICE, int WARPS, int STAGES>
-int launch_cross_enc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* ctxe, int n, int T, int heads, cudaStream_t s) {
+int launch_cross_enc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* ctxe, int n, int T, int heads,
+                     const unsigned char* finished, cudaStream_t s) {
     const size_t smem = (size_t)(STAGES * XE_KEYS) * ESLICE * WARPS * 2 + WARPS * 16 * 32 * sizeof(float);
     static bool done = false;
     if (!done) {
         MB_CUDA(ctx, cudaFuncSetAttribute(dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
-    dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES><<<n, WARPS * 32, smem, s>>>(qp, enc, ctxe, T, heads);
+    dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES><<<n, WARPS * 32, smem, s>>>(qp, enc, ctxe, T, heads, finished);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1074,9 +1080,9 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     g.batches = heads; g.a_col_stride = DH; g.w_row_stride = E; g.out_col_stride = E;
     RC(mb_tap_gemm(ctx, g, s));
     int rc;
-    if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
-    else if (E == 1024) rc = ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
-    else if (E == 128) rc = ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s) : launch_cross_enc<false, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, s);
+    if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    else if (E == 1024) rc = ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    else if (E == 128) rc = ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
     else return mb_set_err(ctx, MB_ERR_STATE, "cross_enc_attention: unsupported encoder width %d", E);
     if (rc) return rc;
     TapGemm v;                                    // att^h = Wv^h ctx^h + bv^h : [R, H]
@@ -1306,7 +1312,7 @@ extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int 
         MB_LAUNCH_CHECK(ctx);
         search_commit_kernel<<<mb_cdiv(R, 128), 128, 0, s>>>(w.st, n, beam, step, max_len);
         MB_LAUNCH_CHECK(ctx);
-        if ((step & 1) == 1 || step == max_len) {    // poll the "all finished" counter every other step
+        if (step >= 3 || (step & 1) == 1 || step == max_len) {   // poll the "all finished" counter (a 4-byte D2H + sync, ~1 % of a step)
             int left = 0;
             MB_CUDA(ctx, cudaMemcpyAsync(&left, w.st.n_unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
             MB_CUDA(ctx, cudaStreamSynchronize(s));

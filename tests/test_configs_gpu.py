@@ -28,8 +28,30 @@ def test_trocr_large_encoder_and_greedy(cuda_ctx):
     with torch.no_grad():
         hyps = trocr.generate(sd, cfg, enc.float().cpu(), beam=1, max_len_b=12)
     toks, lens, _, _ = ops.trocr_decode(enc, beam=1, max_len_b=12)
+    # token ids with the margin protocol of test_trocr_gpu.py: a hypothesis must match exactly when every oracle decision
+    # has a top-1 / top-2 log-prob margin above MARGIN; closer calls may flip under 16-bit rounding and are counted
+    from test_trocr_gpu import MARGIN
+    L = max(len(h[0]["tokens"]) for h in hyps)
+    forced = torch.full((len(hyps), L), trocr.PAD, dtype=torch.long)
     for i, h in enumerate(hyps):
-        assert toks[i, :int(lens[i])].cpu().tolist() == h[0]["tokens"].tolist()
+        forced[i, :len(h[0]["tokens"])] = h[0]["tokens"]
+    trace = []
+    with torch.no_grad():
+        trocr.generate(sd, cfg, enc.float().cpu(), beam=1, max_len_b=12, forced=forced, trace=trace)
+    exact = confident = 0
+    for i, h in enumerate(hyps):
+        want = h[0]["tokens"].tolist()
+        got = toks[i, :int(lens[i])].cpu().tolist()
+        margins = []
+        for step in range(len(want)):
+            top2 = trace[step][1][i].topk(2).values
+            margins.append(float(top2[0] - top2[1]))
+        if min(margins) > MARGIN:
+            confident += 1
+            assert got == want, f"crop {i}: {got} != {want} with min margin {min(margins):.3f}"
+        exact += got == want
+        assert got[-1] == 2 and len(got) <= 13
+    print(f"large greedy: {exact}/{len(hyps)} identical, {confident} with margin > {MARGIN}")
 
 
 def test_beam5_matches_oracle_tiny(cuda_ctx):
