@@ -139,6 +139,26 @@ int mb_load_craft(mb_ctx* ctx, const void* blob_host, size_t nbytes);
 int mb_craft_forward(mb_ctx* ctx, const void* x_dev, int n, int h, int w, float* scores_dev, void* feature_dev,
                      void* stream);
 
+/* ---- section 8f rank 2: the link refiner and its line branch ------------------------------------------------------
+ * mb_load_refine: flat blob of marie-icr_b200/weights.py:pack_refine from the reference's RefineNet state dict
+ * (marie/models/craft/refinenet.py:15-55; loading: marie/boxes/craft_box_processor.py:287-312).
+ * mb_refine_forward: replaces RefineNet.forward (refinenet.py:57-66) as called by get_prediction
+ * (craft_box_processor.py:116-120, 150-156).  feature_dev: [n, h, w, 64] 16-bit as written by mb_craft_forward — its
+ * unused channels 32 / 33 are OVERWRITTEN with the two score maps (the concatenated 34-channel input is never
+ * materialised).  scores_dev: [2, n, h, w] fp32 (mb_craft_forward output).  link_out_dev: [n, h, w] fp32 =
+ * y_refiner[..., 0].
+ * mb_line_components: replaces the threshold / MORPH_CLOSE / connectedComponentsWithStats block of the line branch
+ * (craft_box_processor.py:161-205): link > link_threshold (strict, float32), 3x3 closing, 4-connected labelling.
+ * labels_dev [n, h, w] i32 (optional, may be NULL); n_labels_dev [n] (background included); stats_dev
+ * [n, max_labels, 5] i32 = cv2's (left, top, width, height, area), rows >= n_labels and row 0 zero.  The boxes
+ * (left, top, width, height) of labels 1.. feed mb_line_merge; scaling to page coordinates is the caller's
+ * int(v * ratio * 2) (craft_box_processor.py:207-217).  Synchronises `stream`. */
+int mb_load_refine(mb_ctx* ctx, const void* blob_host, size_t nbytes);
+int mb_refine_forward(mb_ctx* ctx, void* feature_dev, const float* scores_dev, int n, int h, int w, float* link_out_dev,
+                      void* stream);
+int mb_line_components(mb_ctx* ctx, const float* link_dev, int n, int h, int w, float link_threshold,
+                       int32_t* labels_dev, int32_t* n_labels_dev, int32_t* stats_dev, int max_labels, void* stream);
+
 /* ---- K8: line grouping (host side: a few thousand boxes, O(n^2) integer work) -----------------------------------
  * mb_line_merge replaces line_merge / __line_merge (marie/boxes/line_processor.py:48-171): boxes [n,4] i32 (x,y,w,h) ->
  * lines [<= n, 4] i32 sorted by y.  mb_find_line_numbers replaces find_line_number (:15-45): 1-based line id per box,

@@ -16,9 +16,13 @@ from .plugin_api import BoxProcessor, PSMode
 
 class BoxProcessorCraftB200(BoxProcessor):
     def __init__(self, work_dir="/tmp/boxes", models_dir="./model_zoo", cuda=True, config=None, *, state_dict=None,
-                 pipeline=None, device=0):
+                 pipeline=None, device=0, line_refiner_state_dict=None):
         """state_dict: CRAFT weights (keys of marie/models/craft/craft.py); when omitted the reference's checkpoint
-        `<models_dir>/craft/craft_mlt_25k.pth` is loaded (craft_box_processor.py:260-277)."""
+        `<models_dir>/craft/craft_mlt_25k.pth` is loaded (craft_box_processor.py:260-277).
+        line_refiner_state_dict: RefineNet weights (marie/models/craft/refinenet.py) — enables the line branch of
+        get_prediction (craft_box_processor.py:150-217), which the reference keeps switched off (`:287-312`: the
+        refiner is never loaded, so `lines_bboxes` is always [] and every box gets line -1).  With it, `lines_bboxes`
+        and the per-box line numbers are produced exactly as that branch would."""
         super().__init__(work_dir, models_dir, cuda, config or {})
         if not cuda:
             raise RuntimeError("BoxProcessorCraftB200 has no CPU path: cuda=True and a B200 are required")
@@ -31,6 +35,10 @@ class BoxProcessorCraftB200(BoxProcessor):
         if state_dict is not None:
             self.pipeline.load_craft(_weights.pack_craft(state_dict, self.pipeline.dtype))
         self.device = f"cuda:{self.pipeline.device}"
+        self.line_refiner = line_refiner_state_dict is not None
+        if self.line_refiner:
+            from . import ops as _ops
+            _ops.load_refine(_weights.pack_refine(line_refiner_state_dict, self.pipeline.dtype), self.pipeline.device)
 
     def unload(self):
         from ._lib import Context
@@ -39,11 +47,11 @@ class BoxProcessorCraftB200(BoxProcessor):
     # ------------------------------------------------------------------ PSM presets (get_prediction, :76-146)
     def _predict(self, image, mode):
         pages = torch.from_numpy(np.ascontiguousarray(image[None])).to(self.device)
-        det = self.pipeline.detect(pages, PSM_PRESETS[mode])
+        det = self.pipeline.detect(pages, PSM_PRESETS[mode], line_refiner=self.line_refiner)
         bboxes = det["boxes"].cpu().numpy()
         polys = [b for b in bboxes]                      # poly=False: polys[k] = boxes[k] (:133-135)
         self._last_rects = det["rects"].cpu().numpy()
-        return bboxes, polys, None, []
+        return bboxes, polys, None, det.get("lines", [[]])[0]
 
     def psm_word(self, image):
         return self._predict(image, "word")

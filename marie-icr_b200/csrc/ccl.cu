@@ -337,7 +337,7 @@ ccl_finalize_kernel(const unsigned* __restrict__ fg, const int* __restrict__ wma
                 continue;
             }
             // statistics: one lane per group
-            const int tmax = on ? float_to_ordered(trow[x]) : (int)0x80000000;
+            const int tmax = (on && text != nullptr) ? float_to_ordered(trow[x]) : (int)0x80000000;
             const unsigned gm = __match_any_sync(0xffffffffu, on ? leader : 32 + lane);
             const int gmax = __reduce_max_sync(gm, tmax);
             if (on && leader == lane) {
@@ -354,6 +354,30 @@ ccl_finalize_kernel(const unsigned* __restrict__ fg, const int* __restrict__ wma
                     atomicExch(overflow, 1);
                 }
             }
+        }
+    }
+}
+
+// parent[run start] = itself for a foreground bit plane that already exists (line components: refine.cu); also fills
+// the per-word maximum with "no text statistics"
+__global__ void __launch_bounds__(256)
+ccl_init_runs_kernel(const unsigned* __restrict__ fg, int* __restrict__ wmax, int* __restrict__ parent, int n_words, int h,
+                     int w, int wd) {
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (; wi < n_words; wi += stride) {
+        wmax[wi] = (int)0x80000000;
+        const unsigned m = fg[wi];
+        if (!m) continue;
+        const int rowi = wi / wd;
+        const int wx = wi - rowi * wd;
+        const unsigned prev = wx > 0 ? (fg[wi - 1] >> 31) : 0u;
+        unsigned starts = m & ~((m << 1) | prev);
+        const int y = rowi % h;
+        while (starts) {
+            const int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            parent[(long long)rowi * w + wx * 32 + b] = y * w + wx * 32 + b;
         }
     }
 }
@@ -394,8 +418,13 @@ int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int
     const long long nstats = (long long)n_img * max_labels * 8;
     ccl_stats_init_kernel<<<grid_for(nstats, 8), threads, 0, stream>>>(stats, nstats);
     MB_LAUNCH_CHECK(ctx);
-    ccl_mask_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(text, link, fg, tx, wmax, parent, rows, h,
-                                                                               w, wd, low_text, link_thr);
+    if (text != nullptr && link != nullptr) {
+        ccl_mask_kernel<<<grid_for((long long)rows * 32, 8), threads, 0, stream>>>(text, link, fg, tx, wmax, parent, rows, h,
+                                                                                   w, wd, low_text, link_thr);
+    } else {
+        // the foreground plane is given (mb_ccl_run_planes): only the run nodes have to be created
+        ccl_init_runs_kernel<<<grid_for(n_words, 8), threads, 0, stream>>>(fg, wmax, parent, n_words, h, w, wd);
+    }
     MB_LAUNCH_CHECK(ctx);
     ccl_merge_kernel<<<grid_for(n_words, 8), threads, 0, stream>>>(fg, parent, n_words, h, w, wd);
     MB_LAUNCH_CHECK(ctx);
@@ -410,4 +439,12 @@ int mb_ccl_run(mb_ctx* ctx, const float* text, const float* link, int n_img, int
                                                                                    overflow, rows, h, w, wd, max_labels);
     MB_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// Labelling of a foreground bit plane that the caller has already built (fg: n_img * h * ceil(w / 32) words).
+int mb_ccl_run_planes(mb_ctx* ctx, int n_img, int h, int w, int* parent, int* rowcount, int* rowbase, unsigned* fg,
+                      int* wmax, int* labels, int* n_labels, int* stats, int max_labels, int* overflow,
+                      cudaStream_t stream) {
+    return mb_ccl_run(ctx, nullptr, nullptr, n_img, h, w, 0.f, 0.f, parent, rowcount, rowbase, fg, nullptr, wmax, labels,
+                      n_labels, stats, max_labels, overflow, stream);
 }

@@ -27,6 +27,7 @@ struct mb_ctx {
     // model state (opaque here; defined in craft.cu / trocr.cu)
     struct CraftModel* craft = nullptr;
     struct TrocrModel* trocr = nullptr;
+    struct RefineModel* refine = nullptr;   // refine.cu
     // device-side diagnostic word written by kernels before __trap()
     unsigned int* dev_diag = nullptr;
     // 16-bit element type of activations / weights: 0 = bf16, 1 = fp16 (default; mb_set_dtype)

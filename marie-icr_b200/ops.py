@@ -166,6 +166,52 @@ def craft_forward(x, want_feature=False):
     return (scores, feat) if want_feature else scores
 
 
+def load_refine(blob: bytes, device=0):
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    Context.get(device).call("mb_load_refine", buf, ctypes.c_size_t(len(blob)))
+
+
+def refine_forward(scores, feature):
+    """RefineNet.forward on the device: scores [2,n,h,w] fp32 + feature [n,h,w,64] 16-bit (craft_forward(want_feature=True);
+    its channels 32/33 are overwritten) -> refined link map [n,h,w] fp32."""
+    assert scores.is_cuda and scores.dtype == torch.float32 and scores.is_contiguous() and feature.is_contiguous()
+    _, n, h, w = scores.shape
+    assert tuple(feature.shape) == (n, h, w, 64) and feature.dtype == _ctx(scores).torch_dtype
+    out = torch.empty((n, h, w), dtype=torch.float32, device=scores.device)
+    _ctx(scores).call("mb_refine_forward", ptr(feature), ptr(scores), c_int(n), c_int(h), c_int(w), ptr(out), cur_stream())
+    return out
+
+
+def line_components(link, link_threshold, max_labels=8192, want_labels=False):
+    """Line branch of get_prediction up to the component list: link [n,h,w] fp32 -> dict(n_labels [n], stats
+    [n,max_labels,5] (left, top, width, height, area), labels [n,h,w] when asked)."""
+    assert link.is_cuda and link.dtype == torch.float32 and link.is_contiguous()
+    n, h, w = link.shape
+    dev = link.device
+    out = dict(n_labels=torch.zeros((n,), dtype=torch.int32, device=dev),
+               stats=torch.empty((n, max_labels, 5), dtype=torch.int32, device=dev),
+               labels=torch.empty((n, h, w), dtype=torch.int32, device=dev) if want_labels else None)
+    _ctx(link).call("mb_line_components", ptr(link), c_int(n), c_int(h), c_int(w), c_float(link_threshold),
+                    ptr(out["labels"]), ptr(out["n_labels"]), ptr(out["stats"]), c_int(max_labels), cur_stream())
+    return out
+
+
+def line_boxes(link, link_threshold, ratio_w, ratio_h, ratio_net=2, max_labels=8192):
+    """Refiner line boxes in page coordinates, per image: components -> line_merge (host) -> int() scaling
+    (marie/boxes/craft_box_processor.py:161-217)."""
+    from . import lines as _lines
+    comp = line_components(link, link_threshold, max_labels)
+    nl = comp["n_labels"].cpu().tolist()
+    stats = comp["stats"].cpu().numpy()
+    res = []
+    for i, k in enumerate(nl):
+        boxes = stats[i, 1:k, :4].tolist()
+        merged = _lines.line_merge(boxes) if boxes else []
+        res.append([[int(b[0] * ratio_w * ratio_net), int(b[1] * ratio_h * ratio_net), int(b[2] * ratio_w * ratio_net),
+                     int(b[3] * ratio_h * ratio_net)] for b in np.asarray(merged).tolist()])
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ TrOCR
 def load_trocr(blob: bytes, device=0):
     buf = ctypes.create_string_buffer(blob, len(blob))

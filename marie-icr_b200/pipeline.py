@@ -89,7 +89,7 @@ class PagePipeline:
         self.has_trocr = True
 
     # ------------------------------------------------------------------------------------------ detection
-    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False):
+    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False, line_refiner=False):
         """pages_dev [n,H,W,3] u8 (BGR) on the device -> dict with per-crop `rects` [N,4] i32 (x,y,w,h), `page_idx`
         [N] i32, `boxes` [N,4,2] f32 (page coordinates, adjustResultCoordinates output), `counts` (host list)."""
         if not self.has_craft:
@@ -98,6 +98,7 @@ class PagePipeline:
         tt, lt, low = preset
         rects, boxes, pidx, counts = [], [], [], []
         scores_all, ratio = None, None
+        refined_all = None                      # line branch (craft_box_processor.py:150-217), off in the reference
         # K1 + CRAFT in micro-batches (activation memory), score maps of the whole batch kept in HBM ...
         for i0 in range(0, n, self.micro_batch):
             chunk = pages_dev[i0:i0 + self.micro_batch]
@@ -106,7 +107,15 @@ class PagePipeline:
             x, ratio = ops.page_preprocess(chunk)
             self.timer.stop("k1_preprocess", t, m)
             t = self.timer.start()
-            scores = ops.craft_forward(x)
+            if line_refiner:
+                scores, feat = ops.craft_forward(x, want_feature=True)
+                refined = ops.refine_forward(scores, feat)
+                del feat
+                if refined_all is None:
+                    refined_all = torch.empty((n,) + tuple(refined.shape[1:]), dtype=torch.float32, device=pages_dev.device)
+                refined_all[i0:i0 + m] = refined
+            else:
+                scores = ops.craft_forward(x)
             self.timer.stop("k2_4_craft", t, m)
             del x
             if scores_all is None:
@@ -126,6 +135,10 @@ class PagePipeline:
         counts = nb
         res = dict(rects=torch.cat(rects).contiguous(), boxes=torch.cat(boxes).contiguous(),
                    page_idx=torch.cat(pidx).contiguous(), counts=counts)
+        if line_refiner:
+            res["lines"] = ops.line_boxes(refined_all, lt, 1.0 / ratio, 1.0 / ratio)
+            if keep_maps:
+                res["refined_link"] = refined_all
         if keep_maps:
             res["scores"] = scores_all
         return res

@@ -108,6 +108,33 @@ def pack_craft(state_dict, dtype=torch.float16):
     return build_blob(t)
 
 
+def pack_refine(state_dict, dtype=torch.float16):
+    """Reference RefineNet state dict (marie/models/craft/refinenet.py:15-55) -> blob bytes for mb_load_refine.
+    BatchNorm folded in fp32, weights rounded once.  The first layer's 34 input channels (text, link, feature[0:32]) are
+    permuted to the device layout (feature[0:32], text, link, zero padding to 64); the four final 1x1 -> 1 convolutions
+    become one [16, 512] matrix over the four branches' hidden states laid side by side (their biases add up)."""
+    sd = {k[len("module."):] if k.startswith("module.") else k: v.detach().float().cpu() for k, v in state_dict.items()
+          if torch.is_tensor(v)}
+    t = {}
+    for i, (ci, bi) in enumerate(((0, 1), (3, 4), (6, 7)), 1):
+        w, b = _fold_bn(sd[f"last_conv.{ci}.weight"], sd[f"last_conv.{ci}.bias"], sd, f"last_conv.{bi}")
+        if i == 1:
+            w = torch.cat([w[:, 2:34], w[:, 0:2]], 1)
+        t[f"ref.c{i}.w"] = _pack_conv(w, 64, 64, dtype)
+        t[f"ref.c{i}.b"] = _pad_bias(b, 64)
+    fin_w = torch.zeros(16, 512)
+    fin_b = torch.zeros(16)
+    for k in range(1, 5):
+        w, b = _fold_bn(sd[f"aspp{k}.0.weight"], sd[f"aspp{k}.0.bias"], sd, f"aspp{k}.1")
+        t[f"ref.a{k}a.w"], t[f"ref.a{k}a.b"] = _pack_conv(w, 128, 64, dtype), _pad_bias(b, 128)
+        w, b = _fold_bn(sd[f"aspp{k}.3.weight"], sd[f"aspp{k}.3.bias"], sd, f"aspp{k}.4")
+        t[f"ref.a{k}b.w"], t[f"ref.a{k}b.b"] = _pack_conv(w, 128, 128, dtype), _pad_bias(b, 128)
+        fin_w[0, (k - 1) * 128:k * 128] = sd[f"aspp{k}.6.weight"].reshape(128)
+        fin_b[0] += sd[f"aspp{k}.6.bias"].reshape(())
+    t["ref.final.w"], t["ref.final.b"] = fin_w.to(dtype), fin_b
+    return build_blob(t)
+
+
 def pack_trocr(state_dict, cfg, dtype=torch.float16):
     """fairseq TrOCR state dict (`encoder.deit.*`, `decoder.*`) -> blob bytes for mb_load_trocr.
     cfg: any object with enc_dim, enc_layers, enc_heads, enc_ffn, dec_dim, dec_layers, dec_heads, dec_ffn, vocab,

@@ -6,6 +6,9 @@
                      tests/test_oracle_vs_reference.py (same state dict -> identical outputs).
   synth_craft_state  init_weights (vgg16_bn.py:10-21): xavier-uniform convolutions, zero biases, BN gamma=1 beta=0
                      running stats 0/1; optional randomised BN statistics to exercise the BN folding of the packer.
+  refine_forward     RefineNet.forward (marie/models/craft/refinenet.py:57-66): cat(y, upconv4) -> three 3x3 conv+BN+ReLU
+                     -> four ASPP branches (3x3 dilation 6/12/18/24, 1x1, 1x1 -> 1 channel) -> sum.  Pinned against the
+                     reference module (tests/test_oracle_vs_reference.py) and tests/golden/refine_net.npz.
   calibrate_head     the "calibrated head" of SURVEY.md §8d: random-init CRAFT emits maps within ±0.03, so the
                      last 1x1 convolution is rescaled/biased until a fixed percentile of each map crosses the
                      PSM thresholds.  Same weights go to the oracle and the device.
@@ -14,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from synthetic.weights import glyph_craft_state, synth_craft_state  # noqa: F401  (generators live outside oracle/)
+from synthetic.weights import glyph_craft_state, synth_craft_state, synth_refine_state  # noqa: F401  (generators live outside oracle/)
 
 
 def _cbr(sd, x, ck, bk, relu=True, padding=1, dilation=1):
@@ -82,3 +85,18 @@ def calibrate_head(sd, y_uncal, low_text=0.3, link_threshold=0.45, text_pct=98.5
         sd["conv_cls.8.bias"][ch] = float(sd["conv_cls.8.bias"][ch] * scale + bias)
         out.append((float(scale), float(bias)))
     return out
+
+
+def refine_forward(sd, y, feature):
+    """y: [B,H,W,2] (CRAFT.forward output), feature: [B,32,H,W] -> refined link map [B,H,W,1]."""
+    h = torch.cat([y.permute(0, 3, 1, 2), feature], 1)
+    h = _cbr(sd, h, "last_conv.0", "last_conv.1")
+    h = _cbr(sd, h, "last_conv.3", "last_conv.4")
+    h = _cbr(sd, h, "last_conv.6", "last_conv.7")
+    out = None
+    for k, d in ((1, 6), (2, 12), (3, 18), (4, 24)):
+        a = _cbr(sd, h, f"aspp{k}.0", f"aspp{k}.1", padding=d, dilation=d)
+        a = _cbr(sd, a, f"aspp{k}.3", f"aspp{k}.4", padding=0)
+        a = F.conv2d(a, sd[f"aspp{k}.6.weight"], sd[f"aspp{k}.6.bias"])
+        out = a if out is None else out + a
+    return out.permute(0, 2, 3, 1)

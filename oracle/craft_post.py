@@ -465,3 +465,48 @@ def det_boxes_restated(textmap, linkmap, text_threshold, link_threshold, low_tex
         det.append(component_box_restated(rows, sx, ex, sy, ey, niter))
         mapper.append(k)
     return det, labels, mapper
+
+
+def close3x3_restated(mask):
+    """cv2.morphologyEx(MORPH_CLOSE, 3x3 rect, iterations=1) on a binary image: dilation then erosion; OpenCV's default
+    morphology border never wins (outside pixels count as background for the dilation, as foreground for the erosion)."""
+    m = np.asarray(mask, bool)
+    h, w = m.shape
+    p = np.zeros((h + 2, w + 2), bool)
+    p[1:-1, 1:-1] = m
+    d = np.zeros((h, w), bool)
+    for dy in range(3):
+        for dx in range(3):
+            d |= p[dy:dy + h, dx:dx + w]
+    p = np.ones((h + 2, w + 2), bool)
+    p[1:-1, 1:-1] = d
+    e = np.ones((h, w), bool)
+    for dy in range(3):
+        for dx in range(3):
+            e &= p[dy:dy + h, dx:dx + w]
+    return e
+
+
+def line_components_cv(linkmap, link_threshold):
+    """The line branch of get_prediction up to the component list (marie/boxes/craft_box_processor.py:161-205):
+    link > threshold (the text map is thresholded there too, but `text_score_comb` is overwritten by link_score * 255),
+    MORPH_CLOSE 3x3, 4-connected components -> (labels i32, boxes [[x, y, w, h], ...] in label order)."""
+    import cv2
+    _, link_score = cv2.threshold(linkmap, link_threshold, 1, 0)
+    comb = link_score * 255
+    kernel = cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3))
+    line_img = cv2.morphologyEx(comb, cv2.MORPH_CLOSE, kernel, iterations=1)
+    n, labels, stats, _ = cv2.connectedComponentsWithStats(line_img.astype(np.uint8), connectivity=4)
+    boxes = [[int(stats[k, cv2.CC_STAT_LEFT]), int(stats[k, cv2.CC_STAT_TOP]), int(stats[k, cv2.CC_STAT_WIDTH]),
+              int(stats[k, cv2.CC_STAT_HEIGHT])] for k in range(1, n)]
+    return labels, boxes
+
+
+def line_boxes(linkmap, link_threshold, ratio_w, ratio_h, ratio_net=2):
+    """Line boxes of the refiner branch in page coordinates (craft_box_processor.py:161-217): components -> line_merge
+    (marie/boxes/line_processor.py:48-171, restated in oracle/lines.py) -> int() scaling."""
+    from oracle import lines as _lines
+    _, boxes = line_components_cv(linkmap, link_threshold)
+    merged = _lines.line_merge(boxes) if boxes else []
+    return [[int(b[0] * ratio_w * ratio_net), int(b[1] * ratio_h * ratio_net), int(b[2] * ratio_w * ratio_net),
+             int(b[3] * ratio_h * ratio_net)] for b in merged]

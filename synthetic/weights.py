@@ -228,3 +228,43 @@ def apply_eos_row(sd, name="trocr_base_seed0", round_to=torch.float16):
     assert row.shape[0] == w.shape[1]
     w[EOS] = row.to(round_to).float() if round_to is not None else row
     return sd
+
+
+# RefineNet (marie/models/craft/refinenet.py:15-55): Sequential indices of the convolutions / batch norms
+_REFINE = {"last_conv": [(0, 1, 34, 64, 3), (3, 4, 64, 64, 3), (6, 7, 64, 64, 3)]}
+for _k in range(1, 5):
+    _REFINE[f"aspp{_k}"] = [(0, 1, 64, 128, 3), (3, 4, 128, 128, 1), (6, None, 128, 1, 1)]
+
+
+def synth_refine_state(seed=0, random_bn=False, round_to=torch.float16, out_gain=1.0, out_bias=0.0):
+    """RefineNet state dict as its own init_weights leaves it (xavier-uniform convolutions, zero biases, BN gamma 1 /
+    beta 0 / running stats 0 / 1; vgg16_bn.py:10-21), convolution weights rounded once to `round_to`.  `out_gain` /
+    `out_bias` rescale the four final 1x1 convolutions (a random-init refiner emits values near zero, below every link
+    threshold)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, layers in _REFINE.items():
+        for ci, bi, cin, cout, k in layers:
+            w = torch.empty(cout, cin, k, k)
+            bound = (6.0 / (cin * k * k + cout * k * k)) ** 0.5
+            w.uniform_(-bound, bound, generator=g)
+            last = bi is None
+            if last:
+                w = w * out_gain
+            if round_to is not None:
+                w = w.to(round_to).float()
+            sd[f"{name}.{ci}.weight"] = w
+            sd[f"{name}.{ci}.bias"] = torch.full((cout,), out_bias / 4.0) if last else torch.zeros(cout)
+            if bi is not None:
+                if random_bn:
+                    sd[f"{name}.{bi}.weight"] = torch.empty(cout).uniform_(0.6, 1.4, generator=g)
+                    sd[f"{name}.{bi}.bias"] = torch.empty(cout).uniform_(-0.2, 0.2, generator=g)
+                    sd[f"{name}.{bi}.running_mean"] = torch.empty(cout).uniform_(-0.2, 0.2, generator=g)
+                    sd[f"{name}.{bi}.running_var"] = torch.empty(cout).uniform_(0.5, 1.5, generator=g)
+                else:
+                    sd[f"{name}.{bi}.weight"] = torch.ones(cout)
+                    sd[f"{name}.{bi}.bias"] = torch.zeros(cout)
+                    sd[f"{name}.{bi}.running_mean"] = torch.zeros(cout)
+                    sd[f"{name}.{bi}.running_var"] = torch.ones(cout)
+                sd[f"{name}.{bi}.num_batches_tracked"] = torch.tensor(0)
+    return sd

@@ -76,3 +76,33 @@ def test_line_merge(ref):
         for box in boxes[:10]:
             assert ref["lines"].find_line_number(a.tolist(), box) == lines.find_line_number(b.tolist(), box)
     assert ref["lines"].find_line_number([], [1, 2, 3, 4]) == -1 == lines.find_line_number([], [1, 2, 3, 4])
+
+
+def test_refine_forward(ref):
+    """RefineNet.forward (marie/models/craft/refinenet.py:57-66) vs oracle/craft_net.refine_forward, same state dict."""
+    import importlib
+    from oracle import craft_net
+    refinenet = importlib.import_module("refinenet")            # marie/models/craft is on sys.path (ref_loader.load)
+    sd = craft_net.synth_refine_state(1, random_bn=True, round_to=None)
+    net = refinenet.RefineNet()
+    net.load_state_dict(sd)
+    net.eval()
+    torch.manual_seed(3)
+    y, f = torch.randn(2, 40, 56, 2), torch.randn(2, 32, 40, 56)
+    with torch.no_grad():
+        a = net(y, f)
+        b = craft_net.refine_forward(sd, y, f)
+    assert a.shape == (2, 40, 56, 1) and torch.equal(a, b)
+
+
+def test_line_closing_restatement():
+    """The bit-level closing used to check the device kernels equals cv2.morphologyEx(MORPH_CLOSE, 3x3) — the call the
+    reference's line branch makes (marie/boxes/craft_box_processor.py:170-174)."""
+    import cv2
+    from oracle import craft_post
+    rng = np.random.default_rng(0)
+    for shape, p in (((50, 70), 0.6), ((33, 31), 0.3), ((7, 100), 0.8), ((1, 5), 0.5)):
+        m = rng.random(shape) > p
+        cvc = cv2.morphologyEx((m * 255).astype(np.float32), cv2.MORPH_CLOSE,
+                               cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3)), iterations=1)
+        assert np.array_equal(cvc > 0, craft_post.close3x3_restated(m))

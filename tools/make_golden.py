@@ -57,6 +57,20 @@ def main():
     np.savez_compressed(os.path.join(OUT, "craft_net.npz"), x=x.numpy(), y=y.numpy(), feature=feat.numpy(),
                         seed=np.int32(3))
 
+    # --- RefineNet.forward (refinenet.py:57-66) with a seeded state dict (random BN statistics)
+    import importlib
+    refinenet = importlib.import_module("refinenet")
+    rsd = craft_net.synth_refine_state(4, random_bn=True, round_to=None)
+    rnet = refinenet.RefineNet()
+    rnet.load_state_dict(rsd)
+    rnet.eval()
+    torch.manual_seed(6)
+    ry, rf = torch.randn(1, 36, 52, 2), torch.randn(1, 32, 36, 52)
+    with torch.no_grad():
+        rout = rnet(ry, rf)
+    np.savez_compressed(os.path.join(OUT, "refine_net.npz"), y=ry.numpy(), feature=rf.numpy(), out=rout.numpy(),
+                        seed=np.int32(4))
+
     # --- line_merge / find_line_number (line_processor.py:15-171), merge_bboxes_as_block (overlap.py:186-204)
     cases = []
     rng = np.random.default_rng(31)
