@@ -1,6 +1,7 @@
 """Thin torch-tensor wrappers over the stage-level C-ABI entry points (used by tests and the plugins)."""
 import ctypes
 
+import numpy as np
 import torch
 
 from ._lib import Context, c_float, c_int, c_ll, c_void_p, cur_stream, ptr
