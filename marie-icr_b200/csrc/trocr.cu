@@ -384,9 +384,8 @@ __global__ void __launch_bounds__(128, 4) attention_kernel(const bf16* __restric
 // This kernel: one CTA per crop, the 16 heads are the 16 rows of an m16n8k16 tile; 4 warps split the E dimension (8 warps measured slower: the redundant per-warp softmax and the larger partial-score reduction outweigh the extra latency hiding)
 // (scores: partial sums reduced through shared memory; context: each warp owns E/4 output columns); encoder rows are
 // streamed in 32-key tiles through a cp.async ring.  qp, ctx: [rows, 16*E]; enc: [rows*T, E].
-constexpr int XE_KEYS = 32;
-template <bool F16, int ESLICE, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) dec_cross_enc_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ enc,
+template <bool F16, int ESLICE, int WARPS, int STAGES, int XE_KEYS = 32>
+__global__ void __launch_bounds__(WARPS * 32, (STAGES * XE_KEYS * ESLICE * WARPS * 2 + WARPS * 64 * XE_KEYS <= 56 * 1024) ? 4 : ((STAGES * XE_KEYS * ESLICE * WARPS * 2 + WARPS * 64 * XE_KEYS <= 112 * 1024) ? 2 : 1)) dec_cross_enc_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ enc,
                                                                 bf16* __restrict__ ctxo, int T, int heads,
                                                                 const unsigned char* __restrict__ finished) {
     constexpr int E = ESLICE * WARPS;
@@ -396,7 +395,8 @@ __global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) d
     extern __shared__ __align__(128) unsigned char xe_smem[];
     unsigned char* sE = xe_smem;                      // STAGES x [32][E]; the projected queries are staged through stage 0
     unsigned char* sQ = sE;                           // [16][E], only until their fragments sit in registers
-    float* sS = reinterpret_cast<float*>(sE + STAGES * XE_KEYS * ROWB);   // [WARPS][16][32] partial scores
+    float* sS = reinterpret_cast<float*>(sE + STAGES * XE_KEYS * ROWB);   // [WARPS][16][XE_KEYS] partial scores
+    constexpr int NKB = XE_KEYS / 8;                   // 8-key blocks per tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long crop = blockIdx.x;
     // a crop whose hypothesis has ended (EOS chosen in an earlier step) is dropped from the batch by the reference's
@@ -446,44 +446,46 @@ __global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) d
         cp_async_wait<STAGES - 1>();
         __syncthreads();
         // partial scores over this warp's slice of E: S[16 heads x 32 keys]
-        float s[4][4];
+        float s[NKB][4];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
+        for (int nb = 0; nb < NKB; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
 #pragma unroll
         for (int kp = 0; kp < ESLICE / 32; ++kp) {
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
+            for (int nb = 0; nb < NKB; ++nb) {
                 uint32_t b0, b1, b2, b3;
                 ldsm_x4(smem_addr(tile + swz_w(nb * 8 + (lane & 7), cbase + kp * 4 + (lane >> 3))), b0, b1, b2, b3);
                 mma16816<F16>(s[nb], aq[kp * 2], b0, b1);
                 mma16816<F16>(s[nb], aq[kp * 2 + 1], b2, b3);
             }
         }
-        float* mine = sS + warp * 16 * 32;
+        float* mine = sS + warp * 16 * XE_KEYS;
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-            *reinterpret_cast<float2*>(mine + g * 32 + nb * 8 + tg * 2) = make_float2(s[nb][0], s[nb][1]);
-            *reinterpret_cast<float2*>(mine + (g + 8) * 32 + nb * 8 + tg * 2) = make_float2(s[nb][2], s[nb][3]);
+        for (int nb = 0; nb < NKB; ++nb) {
+            *reinterpret_cast<float2*>(mine + g * XE_KEYS + nb * 8 + tg * 2) = make_float2(s[nb][0], s[nb][1]);
+            *reinterpret_cast<float2*>(mine + (g + 8) * XE_KEYS + nb * 8 + tg * 2) = make_float2(s[nb][2], s[nb][3]);
         }
         __syncthreads();
         const int key0 = j * XE_KEYS + tg * 2;
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
+        for (int nb = 0; nb < NKB; ++nb) {
             float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
-                const float2 u0 = *reinterpret_cast<const float2*>(sS + w * 512 + g * 32 + nb * 8 + tg * 2);
-                const float2 u1 = *reinterpret_cast<const float2*>(sS + w * 512 + (g + 8) * 32 + nb * 8 + tg * 2);
+                const float2 u0 = *reinterpret_cast<const float2*>(sS + w * 16 * XE_KEYS + g * XE_KEYS + nb * 8 + tg * 2);
+                const float2 u1 = *reinterpret_cast<const float2*>(sS + w * 16 * XE_KEYS + (g + 8) * XE_KEYS + nb * 8 + tg * 2);
                 t0.x += u0.x; t0.y += u0.y; t1.x += u1.x; t1.y += u1.y;
             }
             const int k = key0 + nb * 8;
             s[nb][0] = k < T ? t0.x : -INFINITY; s[nb][1] = k + 1 < T ? t0.y : -INFINITY;
             s[nb][2] = k < T ? t1.x : -INFINITY; s[nb][3] = k + 1 < T ? t1.y : -INFINITY;
         }
-        float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
-        float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
-        mx0 = fmaxf(mx0, fmaxf(fmaxf(s[2][0], s[2][1]), fmaxf(s[3][0], s[3][1])));
-        mx1 = fmaxf(mx1, fmaxf(fmaxf(s[2][2], s[2][3]), fmaxf(s[3][2], s[3][3])));
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < NKB; ++nb) {
+            mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+        }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
@@ -495,9 +497,9 @@ __global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) d
             for (int i = 0; i < NB; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
             m0 = mn0; m1 = mn1;
         }
-        uint32_t ap[2][4];
+        uint32_t ap[NKB / 2][4];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
+        for (int nb = 0; nb < NKB; ++nb) {
             const float p0 = fast_exp2((s[nb][0] - mn0) * L2E), p1 = fast_exp2((s[nb][1] - mn0) * L2E);
             const float p2 = fast_exp2((s[nb][2] - mn1) * L2E), p3 = fast_exp2((s[nb][3] - mn1) * L2E);
             l0 += p0 + p1; l1 += p2 + p3;
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ESLICE * WARPS <= 768) ? 2 : 1) d
         }
         // context slice: O[16 x ESLICE] += P[16 x 32] . E[32 x ESLICE]
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
+        for (int kk = 0; kk < NKB / 2; ++kk) {
 #pragma unroll
             for (int dp = 0; dp < NB / 2; ++dp) {
                 uint32_t b0, b1, b2, b3;
@@ -1056,16 +1058,16 @@ size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* b
 }
 
 // one decoder step for all R rows: tokens[:, step] -> logits [R, V]
-template <bool F16, int ESLICE, int WARPS, int STAGES>
+template <bool F16, int ESLICE, int WARPS, int STAGES, int XE_KEYS = 32>
 int launch_cross_enc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* ctxe, int n, int T, int heads,
                      const unsigned char* finished, cudaStream_t s) {
-    const size_t smem = (size_t)(STAGES * XE_KEYS) * ESLICE * WARPS * 2 + WARPS * 16 * 32 * sizeof(float);
+    const size_t smem = (size_t)(STAGES * XE_KEYS) * ESLICE * WARPS * 2 + WARPS * 16 * XE_KEYS * sizeof(float);
     static bool done = false;
     if (!done) {
-        MB_CUDA(ctx, cudaFuncSetAttribute(dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MB_CUDA(ctx, cudaFuncSetAttribute(dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES, XE_KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
-    dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES><<<n, WARPS * 32, smem, s>>>(qp, enc, ctxe, T, heads, finished);
+    dec_cross_enc_kernel<F16, ESLICE, WARPS, STAGES, XE_KEYS><<<n, WARPS * 32, smem, s>>>(qp, enc, ctxe, T, heads, finished);
     MB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1080,7 +1082,19 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     g.batches = heads; g.a_col_stride = DH; g.w_row_stride = E; g.out_col_stride = E;
     RC(mb_tap_gemm(ctx, g, s));
     int rc;
-    if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    // E = 768: the kernel is bound by how many encoder rows are in flight per SM, not by its arithmetic: one CTA per SM with
+    // a four-stage ring (three 48 KB tiles in flight) beats two CTAs with two stages each (MB_XE_STAGES=2 / 3 for A/B)
+    // The kernel is bound by the latency of its per-tile chain (cp.async wait -> partial scores -> smem reduction -> softmax
+    // -> P E, three barriers), not by arithmetic: 16-key tiles through a four-stage ring (three tiles = 72 KB in flight per
+    // CTA, two CTAs / SM) measured 8.70 ms per decode step at 2048 live crops against 9.66 for 32-key tiles x 2 stages
+    // (tools/gpu_probe_decode.py; MB_XE_MODE = 0: 32 x 2, 1: 16 x 2 (4 CTAs / SM, 11.8 ms), 2: 16 x 3 (8.8), 3: 16 x 4, 4: 8 warps (12.2)).
+    static int xe_mode = -1;
+    if (xe_mode < 0) { const char* e = getenv("MB_XE_MODE"); xe_mode = e ? atoi(e) : 3; if (xe_mode < 0 || xe_mode > 4) xe_mode = 3; }
+    if (E == 768 && xe_mode == 1) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 2, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    else if (E == 768 && xe_mode == 2) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 3, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 3, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    else if (E == 768 && xe_mode == 3) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 4, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 4, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    else if (E == 768 && xe_mode == 4) rc = ctx->f16 ? launch_cross_enc<true, 96, 8, 3, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 96, 8, 3, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
+    else if (E == 768) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
     else if (E == 1024) rc = ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
     else if (E == 128) rc = ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
     else return mb_set_err(ctx, MB_ERR_STATE, "cross_enc_attention: unsupported encoder width %d", E);
