@@ -438,13 +438,14 @@ __global__ void __launch_bounds__(WARPS * 32, (STAGES * XE_KEYS * ESLICE * WARPS
     const int g = lane >> 2, tg = lane & 3;
     for (int j = 0; j < n_tiles; ++j) {
         unsigned char* tile = sE + (j % STAGES) * XE_KEYS * ROWB;
+        cp_async_wait<STAGES - 2>();      // tile j has landed (tiles j+1 .. j+STAGES-2 may still be in flight)
+        __syncthreads();                  // ... for every thread; and every warp is done with iteration j-1 (its tile, sS)
         {
+            // refill the stage that iteration j-1 just released: STAGES-1 tiles are in flight while tile j is processed
             const int jn = j + STAGES - 1;
             if (jn < n_tiles) load_rows(sE + (jn % STAGES) * XE_KEYS * ROWB, ebase, XE_KEYS, jn * XE_KEYS, T);
             cp_async_commit();
         }
-        cp_async_wait<STAGES - 1>();
-        __syncthreads();
         // partial scores over this warp's slice of E: S[16 heads x 32 keys]
         float s[NKB][4];
 #pragma unroll
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(WARPS * 32, (STAGES * XE_KEYS * ESLICE * WARPS
                 mma16816<F16>(o[dp * 2 + 1], ap[kk], b2, b3);
             }
         }
-        __syncthreads();   // tile and sS are free for the next iteration
+        // no barrier here: the next iteration's first barrier orders this iteration's reads of `tile` / sS before their reuse
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
