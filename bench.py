@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--crop-chunk", type=int, default=2048, help="crops per recogniser chunk")
+    ap.add_argument("--crop-chunk", type=int, default=4096, help="crops per recogniser chunk (results do not depend on it)")
     return ap.parse_args()
 
 

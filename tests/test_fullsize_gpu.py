@@ -81,3 +81,21 @@ def test_batch_properties(letter):
         n = int(r[6])
         assert r[RECORD_HEAD + n - 1] == 2 and 1 not in r[RECORD_HEAD:RECORD_HEAD + n].tolist()
     assert sum(counts) == len(rec) and all(c > 450 for c in counts)
+
+
+def test_chunk_invariance(letter):
+    """The recogniser's chunking is a memory knob, not part of the result: word records are identical whether the crops of
+    a batch go through K9 / encoder / decode in chunks of 100, 777 or all at once."""
+    pipe, pages, _ = letter
+    batch = torch.from_numpy(np.stack([pages[0], pages[1]])).cuda()
+    kw = dict(beam=1, max_len_b=12, out_ld=16)
+    old = pipe.crop_chunk
+    try:
+        recs = []
+        for chunk in (100, 777, 1 << 20):
+            pipe.crop_chunk = chunk
+            rec, counts = pipe.run_device(batch, **kw)
+            recs.append(rec.clone())
+        assert torch.equal(recs[0], recs[1]) and torch.equal(recs[0], recs[2]) and sum(counts) == len(recs[0]) > 900
+    finally:
+        pipe.crop_chunk = old
