@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--crop-chunk", type=int, default=4096, help="crops per recogniser chunk (results do not depend on it)")
+    ap.add_argument("--crop-chunk", type=int, default=8192, help="crops per decode batch (results do not depend on it)")
+    ap.add_argument("--encode-chunk", type=int, default=2048, help="crops per K9 + encoder pass inside a decode batch")
     return ap.parse_args()
 
 
@@ -183,7 +184,7 @@ def run_ours(args, rank, world, local_rank):
     pages_np, _ = make_pages(idx)
     craft_sd, tsd, cfg = make_weights(dt)
     pipe = PagePipeline(device=local_rank, craft_blob=weights.pack_craft(craft_sd, dt),
-                        trocr_blob=weights.pack_trocr(tsd, cfg, dt), micro_batch=8, crop_chunk=args.crop_chunk)
+                        trocr_blob=weights.pack_trocr(tsd, cfg, dt), micro_batch=8, crop_chunk=args.crop_chunk, encode_chunk=args.encode_chunk)
     pages_host = torch.from_numpy(pages_np).pin_memory()
     pages_dev = pages_host.cuda(non_blocking=True)
     page_ids = torch.tensor(idx, dtype=torch.int32, device="cuda")

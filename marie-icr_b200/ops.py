@@ -231,12 +231,15 @@ def trocr_stats(device=0):
     return dict(decode_calls=int(d[0]), decode_steps=int(d[1]), decode_rows=int(d[2]))
 
 
-def trocr_encode(patches):
-    """patches [n*576, 768] 16-bit (pack_crops / pack_fragments layout=1) -> enc_out [n, 577, enc_dim]."""
+def trocr_encode(patches, out=None):
+    """patches [n*576, 768] 16-bit (pack_crops / pack_fragments layout=1) -> enc_out [n, 577, enc_dim] (written into
+    `out` when given: a contiguous [n, 577, enc_dim] view, e.g. a slice of a larger decode batch)."""
     ctx = _ctx(patches)
     dims = trocr_dims(ctx.device)
     n = patches.shape[0] // (dims["tokens"] - 1)
-    out = torch.empty((n, dims["tokens"], dims["enc_dim"]), dtype=patches.dtype, device=patches.device)
+    if out is None:
+        out = torch.empty((n, dims["tokens"], dims["enc_dim"]), dtype=patches.dtype, device=patches.device)
+    assert out.is_contiguous() and tuple(out.shape) == (n, dims["tokens"], dims["enc_dim"]) and out.dtype == patches.dtype
     ctx.call("mb_trocr_encode", ptr(patches), c_int(n), ptr(out), cur_stream())
     return out
 
