@@ -142,6 +142,42 @@ page_preprocess_kernel(const uint8_t* __restrict__ pages, long long page_stride,
     }
 }
 
+// Fallback for down-scale factors beyond the staging area of page_preprocess_kernel (very long or very wide pages):
+// one thread per output pixel straight from global memory, same arithmetic.
+__global__ void page_preprocess_generic_kernel(const uint8_t* __restrict__ pages, long long page_stride, int sh, int sw,
+                                               const LinCoef* __restrict__ xtab, const LinCoef* __restrict__ ytab, int th,
+                                               int tw, int oh, int ow, bf16* __restrict__ out, int f16) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((float)i - 127.5f) / 127.5f;
+    __syncthreads();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;
+    const int page = blockIdx.z;
+    if (ox >= ow) return;
+    float v0 = -1.0f, v1 = -1.0f, v2 = -1.0f;   // zero canvas after (0 - 127.5) / 127.5
+    if (oy < th && ox < tw) {
+        const LinCoef cx = xtab[ox], cy = ytab[oy];
+        const int x0 = cx.ofs, x1 = min(cx.ofs + 1, sw - 1);
+        const int y0 = cy.ofs, y1 = min(cy.ofs + 1, sh - 1);
+        const uint8_t* p = pages + (long long)page * page_stride;
+        const uint8_t* r0 = p + ((long long)y0 * sw) * 3;
+        const uint8_t* r1 = p + ((long long)y1 * sw) * 3;
+        int res[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int s0 = r0[x0 * 3 + c] * cx.a0 + r0[x1 * 3 + c] * cx.a1;
+            const int s1 = r1[x0 * 3 + c] * cx.a0 + r1[x1 * 3 + c] * cx.a1;
+            int v = (((cy.a0 * (s0 >> 4)) >> 16) + ((cy.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            res[c] = min(max(v, 0), 255);
+        }
+        v0 = lut[res[0]]; v1 = lut[res[1]]; v2 = lut[res[2]];
+    }
+    uint2 o;
+    o.x = pack2(v0, v1, f16);
+    o.y = pack2(v2, 0.f, f16);
+    reinterpret_cast<uint2*>(out)[((long long)page * oh + oy) * ow + ox] = o;
+}
+
 // ------------------------------------------------------------------------------------------------ K9
 constexpr int OUT = 384;
 constexpr int PREC_BITS = 32 - 8 - 2;
@@ -675,10 +711,17 @@ extern "C" int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_p
     MB_LAUNCH_CHECK(ctx);
     lin_coef_kernel<<<mb_cdiv(target_h, 256), 256, 0, stream>>>(ytab, page_h, target_h);
     MB_LAUNCH_CHECK(ctx);
-    // staging area limits (see page_preprocess_kernel): source rows / bytes under one 256 x 16 output tile
-    MB_REQUIRE(ctx, (double)page_h / target_h * K1_ROWS + 3 <= K1_MAX_SRC_ROWS &&
-                        ((double)page_w / target_w * K1_COLS + 3) * 3 + 32 <= K1_MAX_ROW_BYTES,
-               "page_preprocess: down-scale factor above 2.4 is not supported");
+    // staging area limits (see page_preprocess_kernel): source rows / bytes under one 256 x 16 output tile; beyond them
+    // (down-scale factors above ~2.3) the per-pixel kernel takes over
+    if (!((double)page_h / target_h * K1_ROWS + 3 <= K1_MAX_SRC_ROWS &&
+          ((double)page_w / target_w * K1_COLS + 3) * 3 + 32 <= K1_MAX_ROW_BYTES)) {
+        dim3 ggrid(mb_cdiv(out_w, 256), out_h, n_pages);
+        page_preprocess_generic_kernel<<<ggrid, 256, 0, stream>>>(pages_dev, (long long)page_h * page_w * 3, page_h, page_w, xtab,
+                                                                  ytab, target_h, target_w, out_h, out_w, (bf16*)out_dev,
+                                                                  ctx->f16);
+        MB_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     static bool k1_attr = false;
     if (!k1_attr) {
         MB_CUDA(ctx, cudaFuncSetAttribute(page_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -10,7 +10,7 @@ def _q(x, dt):
     return torch.from_numpy(np.ascontiguousarray(x)).to(dt)
 
 
-@pytest.mark.parametrize("ph,pw", [(330, 255), (825, 640), (200, 300), (3300, 2550)])
+@pytest.mark.parametrize("ph,pw", [(330, 255), (825, 640), (200, 300), (3300, 2550), (1400, 300), (301, 997)])
 def test_page_preprocess(cuda_ctx, dtype16, ph, pw):
     from marie_icr_b200 import ops
     from oracle import resample
