@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--crop-chunk", type=int, default=8192, help="crops per decode batch (results do not depend on it)")
+    ap.add_argument("--crop-chunk", type=int, default=16384, help="max crops per decode batch (results do not depend on it)")
     ap.add_argument("--encode-chunk", type=int, default=2048, help="crops per K9 + encoder pass inside a decode batch")
     return ap.parse_args()
 

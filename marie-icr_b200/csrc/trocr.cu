@@ -56,6 +56,9 @@ struct TrocrModel {
     std::vector<DecLayer> dec;
     const bf16* embed = nullptr; const float* pe = nullptr; const bf16* out_w = nullptr;
     void* arena = nullptr; size_t arena_bytes = 0;
+    // self-attention K / V caches of the decode in flight: their own allocation, sized for `kv_cap` steps and grown on demand
+    // (a cache for max_len = 200 steps is 81 GB at 8192 rows; hypotheses are a handful of tokens long)
+    void* kv_arena = nullptr; size_t kv_bytes = 0;
     unsigned long long decode_calls = 0, decode_steps = 0, decode_rows = 0;
     bool ln_fold = true;          // encoder LayerNorms folded into qkv / fc1 when the blob carries the folded tensors (MB_LNFOLD=0 disables)
 };
@@ -1005,6 +1008,7 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
 
 struct DecodeWs {
     bf16 *cross_kv, *kcache, *vcache, *x, *qkv, *att, *tmp, *ffn;
+    int kv_cap = 0;               // steps the K / V caches currently hold per layer
     bf16 *qp, *ctxe;              // greedy mode: per-head projected queries / attended encoder states [R, heads*E]
     bool greedy;
     float* logits; float* cand_val; int* cand_idx;
@@ -1032,8 +1036,6 @@ size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* b
         w->qp = w->ctxe = nullptr;
         w->cross_kv = a.take<bf16>((size_t)L * n * T * 2 * H);
     }
-    w->kcache = a.take<bf16>((size_t)L * (max_len + 1) * R * H);
-    w->vcache = a.take<bf16>((size_t)L * (max_len + 1) * R * H);
     w->x = a.take<bf16>(R * H);
     w->qkv = a.take<bf16>(R * 3 * H);
     w->att = a.take<bf16>(R * H);
@@ -1109,14 +1111,57 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     return mb_tap_gemm(ctx, v, s);
 }
 
+// K / V caches [L][kv_cap][R][H] x 2 in their own allocation.  need_steps: steps the caches must be able to hold;
+// keep_steps: steps already written that must survive a growth (copied layer by layer).
+int ensure_kv(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, long long R, int need_steps, int keep_steps, int max_steps,
+              cudaStream_t s) {
+    if (need_steps <= w.kv_cap) return 0;
+    static int first_cap = 0;
+    if (!first_cap) { const char* e = getenv("MB_KV_STEPS"); first_cap = e ? atoi(e) : 32; if (first_cap < 1) first_cap = 32; }
+    int cap = w.kv_cap ? w.kv_cap * 2 : first_cap;
+    while (cap < need_steps) cap *= 2;
+    if (cap > max_steps) cap = max_steps;
+    const int L = m->dec_layers, H = m->dec_dim;
+    const size_t per = (size_t)L * cap * R * H * sizeof(bf16);
+    const size_t bytes = 2 * mb_align_up(per, 256);
+    void* fresh = nullptr;
+    const bool reuse = keep_steps == 0 && bytes <= m->kv_bytes;      // a new decode fits the allocation of the last one
+    if (reuse) {
+        fresh = m->kv_arena;
+    } else {
+        if (keep_steps == 0 && m->kv_arena) { cudaFree(m->kv_arena); m->kv_arena = nullptr; m->kv_bytes = 0; }
+        if (cudaMalloc(&fresh, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return mb_set_err(ctx, MB_ERR_OOM, "trocr: K/V cache of %zu bytes failed", bytes);
+        }
+    }
+    bf16* nk = (bf16*)fresh;
+    bf16* nv = (bf16*)((unsigned char*)fresh + mb_align_up(per, 256));
+    if (keep_steps > 0) {
+        for (int l = 0; l < L; ++l) {
+            const size_t n_el = (size_t)keep_steps * R * H;
+            MB_CUDA(ctx, cudaMemcpyAsync(nk + (size_t)l * cap * R * H, w.kcache + (size_t)l * w.kv_cap * R * H, n_el * sizeof(bf16),
+                                         cudaMemcpyDeviceToDevice, s));
+            MB_CUDA(ctx, cudaMemcpyAsync(nv + (size_t)l * cap * R * H, w.vcache + (size_t)l * w.kv_cap * R * H, n_el * sizeof(bf16),
+                                         cudaMemcpyDeviceToDevice, s));
+        }
+        MB_CUDA(ctx, cudaStreamSynchronize(s));
+        cudaFree(m->kv_arena);
+    }
+    if (!reuse) { m->kv_arena = fresh; m->kv_bytes = bytes; }
+    w.kcache = nk; w.vcache = nv; w.kv_cap = cap;
+    return 0;
+}
+
 int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const bf16* enc_out, int n, int beam, int step, int max_len, cudaStream_t s) {
     const int H = m->dec_dim, T = m->tokens, F = m->dec_ffn, V = m->vocab;
     const int R = n * beam;
+    RC(ensure_kv(ctx, m, w, R, step + 1, step, max_len + 1, s));
     dec_embed_kernel<<<R, 128, 0, s>>>(w.st.tokens, max_len + 2, step, m->embed, m->pe, w.x, R, H, sqrtf((float)H), ctx->f16);
     MB_LAUNCH_CHECK(ctx);
     for (int l = 0; l < m->dec_layers; ++l) {
         const DecLayer& L = m->dec[l];
-        const size_t cache_off = (size_t)l * (max_len + 1) * R * H;
+        const size_t cache_off = (size_t)l * w.kv_cap * R * H;
         RC(gemm(ctx, w.x, H, L.sqkv_w, 3 * H, R, 3 * H, L.sqkv_b, MB_ACT_NONE, nullptr, w.qkv, MB_OUT_BF16, s));
         dec_self_attn_kernel<<<dim3(m->dec_heads, R), 32, 0, s>>>(w.qkv, w.kcache + cache_off, w.vcache + cache_off, w.st.anc,
                                                                   w.att, R, H, step, ctx->f16);
@@ -1164,6 +1209,7 @@ void mb_free_trocr(mb_ctx* ctx) {
     if (!ctx->trocr) return;
     ctx->trocr->blob.release();
     if (ctx->trocr->arena) cudaFree(ctx->trocr->arena);
+    if (ctx->trocr->kv_arena) cudaFree(ctx->trocr->kv_arena);
     delete ctx->trocr;
     ctx->trocr = nullptr;
 }

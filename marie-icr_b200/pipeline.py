@@ -156,8 +156,11 @@ class PagePipeline:
         lengths = torch.zeros((n,), dtype=torch.int32, device=dev)
         scores = torch.zeros((n,), dtype=torch.float32, device=dev)
         dims = ops.trocr_dims(self.device)
-        for i0 in range(0, n, self.crop_chunk):
-            m = min(self.crop_chunk, n - i0)
+        # decode batches of equal size (<= crop_chunk): a short remainder batch would cost a whole decode loop
+        n_batches = max(1, -(-n // self.crop_chunk))
+        batch = -(-n // n_batches)
+        for i0 in range(0, n, batch):
+            m = min(batch, n - i0)
             enc = torch.empty((m, dims["tokens"], dims["enc_dim"]), dtype=self.dtype, device=dev)
             for j0 in range(0, m, self.encode_chunk):
                 r = rects[i0 + j0:i0 + min(j0 + self.encode_chunk, m)].contiguous()
