@@ -15,7 +15,8 @@
 //   flatten   parent[run start] <- root; roots counted per image row
 //   rowscan   exclusive scan of the per-row root counts (one block per image)
 //   assign    roots get their final id = raster rank + 1 (cv2's numbering), encoded in place as -(id) - 2
-//   finalize  labels i32 written for every pixel (streams 4 B/px), per-label statistics by warp-aggregated atomics
+//   finalize  labels i32 written for every pixel (streams 4 B/px, one thread per word), statistics per run piece (atomics);
+//             words with a single run take the max text score from the per-word maximum of the mask pass
 // Page text is sparse, so the middle passes move a few bytes per 32 pixels.
 #include "common.cuh"
 

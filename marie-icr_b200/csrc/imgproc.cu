@@ -12,6 +12,8 @@
 //     coefficients (support scaled by the down-scale factor), 22-bit fixed point, horizontal pass to a u8
 //     intermediate, then vertical pass.  Coefficients are evaluated here in fp64 with the same operation order
 //     (this file is compiled with -fmad=false so nothing is contracted).
+//     Kernels: crop_resize_up_kernel (crops of at most 384 rows: one CTA per crop, dp2a vertical pass) and the tiled
+//     crop_resize_kernel for everything else; crop_classify_kernel builds their work lists.
 #include "common.cuh"
 
 namespace {
