@@ -51,8 +51,7 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const bf16* __restrict__ i
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int img = blockIdx.z;
-    if (x >= w) return;
-    float v[27];
+    float v[27];                               // (lanes beyond the row compute on zeros and store nothing)
     const uint2* src = reinterpret_cast<const uint2*>(in) + (long long)img * h * w;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -72,7 +71,10 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const bf16* __restrict__ i
             v[(ky * 3 + kx) * 3 + 2] = c;
         }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + (((long long)img * h + y) * w + x) * 64);
+    // the 128 output bytes of a pixel are produced 16 at a time; they are staged per warp in shared memory (XOR-swizzled
+    // 16-byte chunks) and written out as 512 contiguous bytes per warp instruction instead of 32 scattered 16-byte pieces
+    __shared__ __align__(16) uint4 stage[4][32][8];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int c8 = 0; c8 < 8; ++c8) {
         float4 a0 = *reinterpret_cast<const float4*>(sb + c8 * 8);
@@ -91,7 +93,16 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const bf16* __restrict__ i
         r.y = pack2(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f), f16);
         r.z = pack2(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f), f16);
         r.w = pack2(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f), f16);
-        o[c8] = r;
+        stage[wid][lane][c8 ^ (lane & 7)] = r;
+    }
+    __syncwarp();
+    const int x_warp = blockIdx.x * blockDim.x + wid * 32;            // first pixel of this warp
+    const int n_px = min(32, w - x_warp);                             // pixels of the warp inside the row
+    uint4* o = reinterpret_cast<uint4*>(out + (((long long)img * h + y) * w + x_warp) * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = k * 32 + lane, px = idx >> 3, ch = idx & 7;
+        if (px < n_px) o[idx] = stage[wid][px][ch ^ (px & 7)];
     }
 }
 
