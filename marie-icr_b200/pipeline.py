@@ -155,6 +155,8 @@ class PagePipeline:
         tokens = torch.full((n, out_ld), 1, dtype=torch.int32, device=dev)
         lengths = torch.zeros((n,), dtype=torch.int32, device=dev)
         scores = torch.zeros((n,), dtype=torch.float32, device=dev)
+        if n == 0:
+            return tokens, lengths, scores
         dims = ops.trocr_dims(self.device)
         # decode batches of equal size (<= crop_chunk): a short remainder batch would cost a whole decode loop
         n_batches = max(1, -(-n // self.crop_chunk))
