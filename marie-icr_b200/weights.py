@@ -36,6 +36,30 @@ def build_blob(tensors):
     return blob + b"".join(chunks)
 
 
+def read_blob(blob):
+    """Inverse of build_blob (tests / debugging): blob bytes -> dict name -> torch tensor."""
+    assert blob[:4] == b"MB2W"
+    _, count, _ = struct.unpack_from("<III", blob, 4)
+    entry_bytes = 64 + 4 + 4 + 32 + 8 + 8
+    data_off = (16 + count * entry_bytes + 255) // 256 * 256
+    inv = {v: k for k, v in _DT.items()}
+    out = {}
+    for i in range(count):
+        base = 16 + i * entry_bytes
+        name = blob[base:base + 64].split(b"\0", 1)[0].decode()
+        dt, nd, d0, d1, d2, d3, off, nbytes = struct.unpack_from("<II4QQQ", blob, base + 64)
+        dtype = inv[dt]
+        raw = np.frombuffer(blob, dtype=np.uint8, count=nbytes, offset=data_off + off).copy()
+        if dtype in (torch.bfloat16, torch.float16):
+            t = torch.from_numpy(raw.view(np.int16)).view(dtype)
+        elif dtype == torch.int32:
+            t = torch.from_numpy(raw.view(np.int32))
+        else:
+            t = torch.from_numpy(raw.view(np.float32))
+        out[name] = t.reshape([d0, d1, d2, d3][:nd])
+    return out
+
+
 def _fold_bn(w, b, sd, bn_key, eps=1e-5):
     g, beta = sd[bn_key + ".weight"].float(), sd[bn_key + ".bias"].float()
     mu, var = sd[bn_key + ".running_mean"].float(), sd[bn_key + ".running_var"].float()

@@ -125,3 +125,59 @@ def test_ensure_max_page_size_known_answers():
     a = rng.integers(0, 255, (70, 90, 3), dtype=np.uint8)
     import hashlib
     assert hash_frames_fast([a, a[:10]]) == hashlib.md5(a.tobytes() + a[:10].tobytes()).hexdigest()
+
+
+def test_blob_roundtrip_and_layernorm_fold_algebra():
+    """weights.pack_trocr's LayerNorm fold, checked on the CPU from the packed tensors themselves:
+    LN(x) W^T + b == rstd * (x (W * gamma)^T - mean * c) + (b + W beta) — the identity the device epilogue implements
+    (csrc/gemm_tc.cu, LNF) — and the blob reader inverts the blob writer."""
+    import torch
+    from marie_icr_b200 import weights
+    from oracle import trocr
+    cfg = trocr.trocr_tiny()
+    sd = trocr.synth_trocr_state(cfg, 5, round_to=None)
+    g = torch.Generator().manual_seed(1)
+    for k in list(sd):                                   # non-trivial affine parameters
+        if "norm1" in k or "norm2" in k:
+            sd[k] = sd[k] + 0.3 * torch.randn(sd[k].shape, generator=g)
+    t = weights.read_blob(weights.pack_trocr(sd, cfg, torch.float16))
+    assert t["config"].tolist()[:2] == [cfg.enc_dim, cfg.enc_layers]
+    e = "encoder.deit.blocks.0."
+    x = torch.randn(7, cfg.enc_dim, generator=g) * 2 + 0.5
+    for name, ln, wkey, bias in (("qkv", "norm1", "attn.qkv.weight", None), ("fc1", "norm2", "mlp.fc1.weight", sd[e + "mlp.fc1.bias"])):
+        w = sd[e + wkey]
+        ref = torch.nn.functional.layer_norm(x, (cfg.enc_dim,), sd[e + ln + ".weight"], sd[e + ln + ".bias"], 1e-6) @ w.t()
+        if bias is not None:
+            ref = ref + bias
+        wf, c, bf = t[f"enc.L0.{name}.wf"].float(), t[f"enc.L0.{name}.c"], t[f"enc.L0.{name}.bf"]
+        assert torch.equal(t[f"enc.L0.{name}.w"], w.to(torch.float16))
+        mean = x.mean(1, keepdim=True)
+        rstd = torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-6)
+        got = rstd * (x @ wf.t() - mean * c[None]) + bf[None]
+        assert (got - ref).abs().max() <= 5e-3 * ref.abs().max()        # fp16 rounding of W * gamma only
+
+
+def test_pack_refine_layout():
+    """weights.pack_refine on the CPU: the packed (BN-folded, channel-permuted, tap-major) matrices reproduce the
+    oracle's first RefineNet layer and its summed 1x1 heads."""
+    import torch
+    import torch.nn.functional as F
+    from marie_icr_b200 import weights
+    from oracle import craft_net
+    sd = craft_net.synth_refine_state(3, random_bn=True, round_to=None)
+    t = weights.read_blob(weights.pack_refine(sd, torch.float16))
+    g = torch.Generator().manual_seed(2)
+    y, feat = torch.randn(1, 9, 11, 2, generator=g), torch.rand(1, 32, 9, 11, generator=g)
+    x34 = torch.cat([y.permute(0, 3, 1, 2), feat], 1)
+    ref = craft_net._cbr(sd, x34, "last_conv.0", "last_conv.1")
+    # device input layout: channels 0..31 = feature, 32 = text, 33 = link, rest zero; k = tap * 64 + c
+    x64 = torch.zeros(1, 64, 9, 11)
+    x64[:, :32], x64[:, 32:34] = feat, y.permute(0, 3, 1, 2)
+    cols = F.unfold(x64, 3, padding=1).reshape(64, 9, -1).permute(1, 0, 2).reshape(576, -1)    # [tap * 64 + c, px]
+    got = torch.relu(t["ref.c1.w"].float() @ cols + t["ref.c1.b"][:, None]).reshape(1, 64, 9, 11)
+    assert (got - ref).abs().max() <= 5e-3 * ref.abs().max()
+    # final layer: one [16, 512] matrix = the four 1x1 -> 1 heads side by side, biases added up
+    assert t["ref.final.w"].shape == (16, 512) and float(t["ref.final.w"][1:].abs().max()) == 0.0
+    for k in range(1, 5):
+        assert torch.equal(t["ref.final.w"][0, (k - 1) * 128:k * 128], sd[f"aspp{k}.6.weight"].reshape(128).to(torch.float16))
+    assert abs(float(t["ref.final.b"][0]) - sum(float(sd[f"aspp{k}.6.bias"]) for k in range(1, 5))) < 1e-6
