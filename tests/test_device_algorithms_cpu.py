@@ -1,0 +1,79 @@
+"""CPU emulations of the integer / bit-level tricks the CUDA kernels rely on, checked against the oracle restatements
+(no GPU needed): the dp2a coefficient split of the K9 vertical pass (csrc/imgproc.cu crop_resize_up_kernel) and the
+word-level 3x3 morphology of the line branch (csrc/refine.cu morph3x3_kernel)."""
+import numpy as np
+
+
+def test_dp2a_coefficient_split_is_exact():
+    """k = kh * 2^11 + kl with kl = k & 2047, kh = k >> 11 (arithmetic): sum k * v == (sum kh * v << 11) + sum kl * v, both
+    halves fit the signed 16-bit lanes of dp2a, for Pillow's whole coefficient range (negative lobes included)."""
+    from oracle import resample
+    rng = np.random.default_rng(0)
+    for in_size in (1, 2, 3, 17, 45, 63, 64, 200, 383, 384):
+        _, kk = resample.pil_coeffs(in_size, 384)
+        k = np.asarray(kk, np.int64)
+        kh, kl = k >> 11, k & 2047
+        assert (k == kh * 2048 + kl).all() and kh.min() >= -32768 and kh.max() <= 32767 and kl.min() >= 0
+        v = rng.integers(0, 256, k.shape, dtype=np.int64)
+        full = (k * v).sum(1) + (1 << 21)
+        split = ((kh * v).sum(1) << 11) + (kl * v).sum(1) + (1 << 21)
+        assert (full == split).all()
+        assert np.abs((kh * v).sum(1)).max() < 2 ** 31 and (kl * v).sum(1).max() < 2 ** 31
+        # the clamp folded into the 512-entry table: (acc >> 22) + 128 stays inside it
+        idx = (full >> 22) + 128
+        assert idx.min() >= 0 and idx.max() < 512
+
+
+def _to_words(mask):
+    h, w = mask.shape
+    wd = (w + 31) // 32
+    pad = np.zeros((h, wd * 32), bool)
+    pad[:, :w] = mask
+    bits = pad.reshape(h, wd, 32)
+    return (bits * (1 << np.arange(32, dtype=np.uint64))).sum(2).astype(np.uint32)
+
+
+def _from_words(words, w):
+    h, wd = words.shape
+    bits = ((words[:, :, None].astype(np.uint64) >> np.arange(32, dtype=np.uint64)) & 1).astype(bool)
+    return bits.reshape(h, wd * 32)[:, :w]
+
+
+def _morph_words(words, w, erode):
+    """morph3x3_kernel, word for word."""
+    h, wd = words.shape
+    full = np.uint32(0xFFFFFFFF)
+    tail = np.uint32((1 << (w & 31)) - 1) if (w & 31) else full
+    out = np.zeros_like(words)
+    for y in range(h):
+        for wx in range(wd):
+            acc = full if erode else np.uint32(0)
+            for dy in (-1, 0, 1):
+                yy = y + dy
+                if yy < 0 or yy >= h:
+                    continue
+                m = words[yy, wx]
+                left = words[yy, wx - 1] if wx > 0 else (full if erode else np.uint32(0))
+                right = words[yy, wx + 1] if wx + 1 < wd else (full if erode else np.uint32(0))
+                if erode:
+                    if wx == wd - 1:
+                        m = m | ~tail
+                    if wx + 1 == wd - 1:
+                        right = right | ~tail
+                l1 = np.uint32((int(m) << 1) & 0xFFFFFFFF) | (left >> np.uint32(31))
+                r1 = (m >> np.uint32(1)) | np.uint32((int(right) << 31) & 0xFFFFFFFF)
+                acc = (acc & m & l1 & r1) if erode else (acc | m | l1 | r1)
+            if wx == wd - 1:
+                acc = acc & tail
+            out[y, wx] = acc
+    return out
+
+
+def test_word_level_closing_matches_restatement():
+    from oracle import craft_post
+    rng = np.random.default_rng(1)
+    for (h, w), p in (((9, 31), 0.5), ((12, 32), 0.7), ((7, 33), 0.4), ((20, 70), 0.6), ((5, 64), 0.3), ((1, 100), 0.5)):
+        m = rng.random((h, w)) > p
+        words = _to_words(m)
+        closed = _morph_words(_morph_words(words, w, erode=False), w, erode=True)
+        assert np.array_equal(_from_words(closed, w), craft_post.close3x3_restated(m)), (h, w)
