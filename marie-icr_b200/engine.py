@@ -55,12 +55,21 @@ class OcrEngineB200:
                    and len({f.shape for f in ro_frames}) == 1 and not kwargs.get("crop_to_content", False))
         if batched:
             return self._extract_batched(ro_frames, pms_mode, coordinate_format)
-        return self._extract_pagewise(ro_frames, queue_id, "0", pms_mode, coordinate_format)
+        return self._extract_pagewise(ro_frames, queue_id, "0", pms_mode, coordinate_format,
+                                      crop=bool(kwargs.get("crop_to_content", False)))
 
-    # page-by-page loop of __process_extract_fullpage (ocr_engine.py:154-221)
-    def _extract_pagewise(self, frames, queue_id, checksum, pms_mode, coordinate_format):
+    # page-by-page loop of __process_extract_fullpage (ocr_engine.py:154-221); `crop_to_content=True` crops every page to its
+    # content and pads it with 4 white pixels first (:169-185)
+    def _extract_pagewise(self, frames, queue_id, checksum, pms_mode, coordinate_format, crop=False):
+        from .ingest import crop_to_content
         results = []
         for i, img in enumerate(frames):
+            if crop:
+                img = crop_to_content(img)
+                h, w = img.shape[:2]
+                overlay = np.full((h + 8, w + 8, 3), 255, np.uint8)
+                overlay[4:h + 4, 4:w + 4] = img
+                img = overlay
             boxes, fragments, lines, _, line_bboxes = self.box_processor.extract_bounding_boxes(queue_id, checksum, img, pms_mode)
             result, _ = self.icr_processor.recognize(queue_id, checksum, img, boxes, fragments, lines)
             self._finish(result, i, lines, line_bboxes, coordinate_format)

@@ -96,3 +96,20 @@ def load_ocr_processor():
     mod = _load("ref_ocr_processor", "marie/document/ocr_processor.py")
     _cache["ocr_processor"] = mod.OcrProcessor
     return mod.OcrProcessor
+
+
+def load_image_utils():
+    """marie/utils/image_utils.py (crop_to_content, ensure_max_page_size, hash_frames_fast) loaded by path behind a stub
+    for marie.timer."""
+    if "image_utils" in _cache:
+        return _cache["image_utils"]
+    load()
+    if "marie.timer" not in sys.modules:
+        t = types.ModuleType("marie.timer")
+        t.Timer = object
+        sys.modules["marie.timer"] = t
+    spec = importlib.util.spec_from_file_location("ref_image_utils", os.path.join(REF_ROOT, "marie/utils/image_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _cache["image_utils"] = mod
+    return mod

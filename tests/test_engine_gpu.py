@@ -109,6 +109,29 @@ def test_engine_batched_equals_pagewise(engine):
     assert r[0]["words"] == [] and len(r[1]["words"]) == len(a[0]["words"])
 
 
+def test_engine_crop_to_content(engine):
+    """`crop_to_content=True` (ocr_engine.py:169-185): every page is cropped to its content and padded with 4 white pixels
+    before detection — same result as handing the engine that padded crop directly."""
+    from marie_icr_b200 import ingest
+    from marie_icr_b200.plugin_api import PSMode
+    eng, pages, _, _, _ = engine
+    page = pages[0]
+    cropped = ingest.crop_to_content(page)
+    assert cropped.shape[1] < page.shape[1]
+    h, w = cropped.shape[:2]
+    padded = np.full((h + 8, w + 8, 3), 255, np.uint8)
+    padded[4:h + 4, 4:w + 4] = cropped
+    a = _plain(eng.extract([page], PSMode.SPARSE, crop_to_content=True))
+    b = _plain(eng._extract_pagewise([padded], "q", "0", PSMode.SPARSE, eng_format(eng)))
+    assert a[0]["meta"]["imageSize"] == {"width": w + 8, "height": h + 8}
+    assert len(a[0]["words"]) > 10 and a[0]["words"] == b[0]["words"] and a[0]["lines"] == b[0]["lines"]
+
+
+def eng_format(eng):
+    from marie_icr_b200.plugin_api import CoordinateFormat
+    return CoordinateFormat.XYWH
+
+
 def test_engine_regions(engine):
     """Region / field extraction (ocr_engine.py:223-414): per-region PSM, 4 px padding, one recognize() per page, the
     {"regions", "extended"} payload; results equal recognising the padded region directly."""

@@ -106,3 +106,20 @@ def test_line_closing_restatement():
         cvc = cv2.morphologyEx((m * 255).astype(np.float32), cv2.MORPH_CLOSE,
                                cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3)), iterations=1)
         assert np.array_equal(cvc > 0, craft_post.close3x3_restated(m))
+
+
+def test_crop_to_content():
+    """ingest.crop_to_content (host mirror of marie/utils/image_utils.py:190-251, the engine's optional pre-step) against
+    the reference function itself."""
+    from marie_icr_b200 import ingest
+    from synthetic import pages as synth
+    ref_iu = ref_loader.load_image_utils()
+    page, _ = synth.synth_page(3, height=600, width=800, scale=0.9, line_pitch=52, gap=30, margin=120)
+    gray = page[..., 0].copy()
+    blank = np.full((50, 60, 3), 255, np.uint8)
+    for frame in (page, gray, blank):
+        for aware in (True, False):
+            a = ref_iu.crop_to_content(frame.copy(), content_aware=aware)
+            b = ingest.crop_to_content(frame.copy(), content_aware=aware)
+            assert a.shape == b.shape and np.array_equal(a, b)
+    assert ingest.crop_to_content(page).shape[1] < page.shape[1]
