@@ -154,3 +154,32 @@ def test_run_based_labelling_matches_opencv():
         n_ref, ref = cv2.connectedComponents(m.astype(np.uint8), connectivity=4)
         lab, n = _run_ccl(m)
         assert n == n_ref and np.array_equal(lab, ref), (h, w)
+
+
+def test_k1_source_row_walk_emits_every_row_once():
+    """page_preprocess_kernel (csrc/imgproc.cu) walks the staged source rows of a 16-row output tile once and emits every
+    output row whose LOWER source row is the current one.  Replayed here for many (source, target) heights — identity,
+    down-scales up to the staging limit, the clamped bottom edge — every output row must come out exactly once, from the
+    source-row pair cv2's INTER_LINEAR table prescribes."""
+    from oracle import resample
+    rng = np.random.default_rng(3)
+    cases = [(330, 255), (3300, 2550), (200, 200), (17, 16), (64, 33), (1000, 435)]
+    cases += [(int(s), int(max(1, s * f))) for s, f in zip(rng.integers(20, 900, 30), rng.uniform(0.44, 1.0, 30))]
+    for sh, th in cases:
+        ofs, _, _ = resample._cv_lin_coeffs(sh, th)
+        for oy0 in range(0, th, 16):
+            n_rows = min(oy0 + 16, th) - oy0
+            ys0 = int(ofs[oy0])
+            nsrc = min(int(ofs[oy0 + n_rows - 1]) + 1, sh - 1) - ys0 + 1
+            assert nsrc <= 40, (sh, th)                       # K1_MAX_SRC_ROWS for factors the launcher accepts
+            k, emitted = 0, []
+            for r in range(nsrc):
+                while k < n_rows:
+                    o = int(ofs[oy0 + k])
+                    if min(o + 1, sh - 1) - ys0 != r:
+                        break
+                    same = (o - ys0 == r)
+                    emitted.append((oy0 + k, ys0 + (r if same else r - 1), ys0 + r))
+                    k += 1
+            want = [(oy, int(ofs[oy]), min(int(ofs[oy]) + 1, sh - 1)) for oy in range(oy0, oy0 + n_rows)]
+            assert emitted == want, (sh, th, oy0)
