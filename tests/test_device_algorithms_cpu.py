@@ -183,3 +183,47 @@ def test_k1_source_row_walk_emits_every_row_once():
                     k += 1
             want = [(oy, int(ofs[oy]), min(int(ofs[oy]) + 1, sh - 1)) for oy in range(oy0, oy0 + n_rows)]
             assert emitted == want, (sh, th, oy0)
+
+
+def test_k9_pair_table_and_bands_reproduce_pillow_vertical_pass():
+    """crop_resize_up_kernel (csrc/imgproc.cu): the vertical taps of every output row are re-packed into row PAIRS
+    (p0, pairs, three (k_even, k_odd) slots) and the rows are processed in bands whose source pairs fit the staging area.
+    Replayed for every crop height 1..384: the pair form must give Pillow's vertical pass exactly, and every band must stay
+    inside its allocation."""
+    from oracle import resample
+    rng = np.random.default_rng(4)
+    for h in list(range(1, 70)) + [95, 96, 97, 128, 200, 255, 256, 383, 384]:
+        bounds, kk = resample.pil_coeffs(h, 384)
+        assert kk.shape[1] == 5 and int(bounds[:, 1].max()) <= 5            # up-scale: at most five taps
+        tmp = rng.integers(0, 256, (h, 7), dtype=np.int64)                   # a few columns of the u8 intermediate
+        npair = (h + 1) // 2
+        rows = np.zeros((2 * npair + 6, 7), np.int64)                        # pair storage; rows past the crop: arbitrary
+        rows[:h] = tmp
+        rows[h:] = rng.integers(0, 256, rows[h:].shape)
+        table = []
+        for yy in range(384):
+            ymin, n = int(bounds[yy, 0]), int(bounds[yy, 1])
+            odd = ymin & 1
+            k6 = [0] * 6
+            for x in range(n):
+                k6[x + odd] = int(kk[yy, x])
+            p0, pairs = ymin >> 1, (odd + n + 1) >> 1
+            assert 1 <= pairs <= 3
+            table.append((p0, pairs, k6))
+            acc = 1 << 21
+            for q in range(pairs):
+                acc = acc + k6[2 * q] * rows[2 * (p0 + q)] + k6[2 * q + 1] * rows[2 * (p0 + q) + 1]
+            want = (kk[yy, :n].astype(np.int64)[:, None] * tmp[ymin:ymin + n]).sum(0) + (1 << 21)
+            assert (acc == want).all(), (h, yy)
+        # band selection with the smallest staging area the kernel accepts (UP_MIN_PAIRS) and with a typical one
+        for max_pairs in (12, 38):
+            yb0 = 0
+            while yb0 < 384:
+                pf = table[yb0][0]
+                yb1 = yb0 + 8
+                while yb1 < 384 and table[yb1 + 7][0] + table[yb1 + 7][1] - pf <= max_pairs:
+                    yb1 += 8
+                used = max(t[0] + t[1] for t in table[yb0:yb1]) - pf
+                assert 0 < used <= max_pairs, (h, yb0, yb1, used)
+                assert all(t[0] >= pf for t in table[yb0:yb1])
+                yb0 = yb1
