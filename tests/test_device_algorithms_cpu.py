@@ -227,3 +227,40 @@ def test_k9_pair_table_and_bands_reproduce_pillow_vertical_pass():
                 assert 0 < used <= max_pairs, (h, yb0, yb1, used)
                 assert all(t[0] >= pf for t in table[yb0:yb1])
                 yb0 = yb1
+
+
+def test_row_extremes_from_text_bit_runs():
+    """box_extract_small_kernel (csrc/boxes.cu) fetches ONE label per run of consecutive `text > low_text` bits inside a
+    component's bounding box (such a run lies inside one foreground run, hence inside one component).  Replayed against the
+    direct definition min / max x of {label == k and text > low_text} per row."""
+    import cv2
+    from oracle import synth
+    for seed in (1, 2, 3):
+        text, link = synth.random_score_maps(seed, 90, 150, n_blobs=25)
+        fg = (text > np.float32(0.3)) | (link > np.float32(0.45))
+        tx = text > np.float32(0.3)
+        n, labels, stats, _ = cv2.connectedComponentsWithStats(fg.astype(np.uint8), connectivity=4)
+        words = _to_words(tx)
+        for k in range(1, n):
+            x0, y0, bw, bh = (int(stats[k, i]) for i in range(4))
+            for r in range(bh):
+                y = y0 + r
+                mn, mx = 0x7fff, -1
+                for wx in range(x0 >> 5, ((x0 + bw - 1) >> 5) + 1):
+                    t = int(words[y, wx])
+                    lo, hi = x0 - wx * 32, x0 + bw - 1 - wx * 32
+                    if lo > 0:
+                        t &= (0xFFFFFFFF << lo) & 0xFFFFFFFF
+                    if hi < 31:
+                        t &= 0xFFFFFFFF >> (31 - hi)
+                    while t:
+                        b = (t & -t).bit_length() - 1
+                        ln = 0
+                        while b + ln < 32 and (t >> (b + ln)) & 1:
+                            ln += 1
+                        if labels[y, wx * 32 + b] == k:
+                            mn, mx = min(mn, wx * 32 + b), max(mx, wx * 32 + b + ln - 1)
+                        t &= ~(((1 << ln) - 1) << b)
+                xs = np.nonzero((labels[y, x0:x0 + bw] == k) & tx[y, x0:x0 + bw])[0]
+                want = (x0 + int(xs.min()), x0 + int(xs.max())) if len(xs) else (0x7fff, -1)
+                assert (mn, mx) == want, (seed, k, r)
