@@ -52,9 +52,16 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+class _CurrentStream:
+    """Placeholder argument: Context.call replaces it by torch's current stream OF THE CONTEXT'S DEVICE (not of whatever
+    device happens to be current in the calling thread)."""
+
+
+_CUR_STREAM = _CurrentStream()
+
+
 def cur_stream():
-    import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _CUR_STREAM
 
 
 class Context:
@@ -88,6 +95,10 @@ class Context:
     def call(self, name, *args):
         fn = getattr(self.lib, name)
         fn.restype = c_int
+        if any(a is _CUR_STREAM for a in args):
+            import torch
+            stream = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            args = tuple(stream if a is _CUR_STREAM else a for a in args)
         self.check(fn(self.handle, *args), name)
 
     @property

@@ -11,14 +11,15 @@ import torch
 
 from . import weights as _weights
 from .pipeline import PSM_PRESETS, PagePipeline
-from .plugin_api import BoxProcessor, PSMode
+from .plugin_api import MODEL_PATH, BoxProcessor, PSMode
 
 
 class BoxProcessorCraftB200(BoxProcessor):
-    def __init__(self, work_dir="/tmp/boxes", models_dir="./model_zoo", cuda=True, config=None, *, state_dict=None,
-                 pipeline=None, device=0, line_refiner_state_dict=None):
-        """state_dict: CRAFT weights (keys of marie/models/craft/craft.py); when omitted the reference's checkpoint
-        `<models_dir>/craft/craft_mlt_25k.pth` is loaded (craft_box_processor.py:260-277).
+    def __init__(self, work_dir="/tmp/boxes", models_dir=os.path.join(MODEL_PATH, "craft"), cuda=True, config=None, *,
+                 state_dict=None, pipeline=None, device=0, line_refiner_state_dict=None):
+        """models_dir is the CRAFT directory itself, as in the reference (default `<model_zoo>/craft`,
+        craft_box_processor.py:245-249).  state_dict: CRAFT weights (keys of marie/models/craft/craft.py); when omitted
+        the reference's checkpoint `<models_dir>/craft_mlt_25k.pth` is loaded (:260-277).
         line_refiner_state_dict: RefineNet weights (marie/models/craft/refinenet.py) — enables the line branch of
         get_prediction (craft_box_processor.py:150-217), which the reference keeps switched off (`:287-312`: the
         refiner is never loaded, so `lines_bboxes` is always [] and every box gets line -1).  With it, `lines_bboxes`
@@ -28,10 +29,10 @@ class BoxProcessorCraftB200(BoxProcessor):
             raise RuntimeError("BoxProcessorCraftB200 has no CPU path: cuda=True and a B200 are required")
         self.pipeline = pipeline or PagePipeline(device=device)
         if state_dict is None and not self.pipeline.has_craft:
-            path = os.path.join(models_dir, "craft", "craft_mlt_25k.pth")
+            path = os.path.join(models_dir, "craft_mlt_25k.pth")
             if not os.path.exists(path):
                 raise FileNotFoundError(f"CRAFT checkpoint not found: {path}")
-            state_dict = torch.load(path, map_location="cpu")
+            state_dict = torch.load(path, map_location="cpu", weights_only=True)      # a plain tensor dict
         if state_dict is not None:
             self.pipeline.load_craft(_weights.pack_craft(state_dict, self.pipeline.dtype))
         self.device = f"cuda:{self.pipeline.device}"

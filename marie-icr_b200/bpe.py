@@ -7,6 +7,7 @@ part of the reference tree; point Gpt2Detokenizer at them when available.  Synth
 stand-in used with random-init weights (same class on the device path and in the oracle, so text parity == id parity).
 """
 import json
+import os
 
 SPECIALS = (0, 1, 2, 3)   # <s>, <pad>, </s>, <unk>
 
@@ -39,20 +40,43 @@ def _bytes_to_unicode():
 
 
 class Gpt2Detokenizer:
-    """fairseq dictionary (dict.txt: '<gpt2 id> <count>' per line, ids offset by the 4 specials) + GPT-2 encoder.json."""
+    """get_text's tail (trocr_ocr_processor.py:162-176) without fairseq:
+      fairseq Dictionary: ids 0-3 = <s> <pad> </s> <unk>, then one symbol per line of dict.txt ('<symbol> <count>';
+        gpt2_with_mask.dict.txt lists GPT-2 ids as decimal strings and ends with '<mask>');
+      Dictionary.string(hypo_tokens, extra_symbols_to_ignore={eos}): symbols joined by ' ', eos and bos dropped, <unk>
+        and <pad> kept as their strings;
+      GPT2BPEEnhancedSpace.decode (marie/models/unilm/trocr/bpe.py:59-67, INSERT_OR_REPLACE = 0): numeric symbols ->
+        GPT-2 vocabulary strings (encoder.json inverted), '<unk>' / '<mask>' / '<s>' kept literally, byte-level
+        decoding to UTF-8 (errors='replace'), then every '<s>' removed."""
+
+    DICT_NAMES = ("gpt2_with_mask.dict.txt", "dict.txt")
+    ENCODER_NAMES = ("encoder.json",)
 
     def __init__(self, dict_path, encoder_json_path):
         self.symbols = ["<s>", "<pad>", "</s>", "<unk>"]
         with open(dict_path, encoding="utf-8") as f:
             for line in f:
                 if line.strip():
-                    self.symbols.append(line.rsplit(" ", 1)[0])
+                    self.symbols.append(line.rstrip("\n").rsplit(" ", 1)[0])
         with open(encoder_json_path, encoding="utf-8") as f:
             enc = json.load(f)
         self.decoder = {v: k for k, v in enc.items()}
         self.byte_decoder = {v: k for k, v in _bytes_to_unicode().items()}
 
+    @classmethod
+    def locate(cls, *dirs):
+        """first directory holding both files; FileNotFoundError naming what is missing otherwise"""
+        for d in dirs:
+            dp = next((os.path.join(d, n) for n in cls.DICT_NAMES if os.path.exists(os.path.join(d, n))), None)
+            ep = next((os.path.join(d, n) for n in cls.ENCODER_NAMES if os.path.exists(os.path.join(d, n))), None)
+            if dp and ep:
+                return cls(dp, ep)
+        raise FileNotFoundError(
+            f"GPT-2 BPE files not found ({' or '.join(cls.DICT_NAMES)} and {cls.ENCODER_NAMES[0]}) in any of {list(dirs)}: pass "
+            "detokenizer=Gpt2Detokenizer(dict_path, encoder_json_path); without them token ids cannot be turned into text")
+
     def decode(self, ids):
-        toks = [self.symbols[int(t)] for t in ids if int(t) not in SPECIALS and int(t) < len(self.symbols)]
-        text = "".join(self.decoder.get(int(t), t) if t.lstrip("-").isdigit() else t for t in toks if t != "<mask>")
-        return bytearray(self.byte_decoder[c] for c in text if c in self.byte_decoder).decode("utf-8", errors="replace")
+        syms = [self.symbols[t] if t < len(self.symbols) else "<unk>" for t in (int(t) for t in ids) if t not in (0, 2)]
+        text = "".join(s if s in ("<unk>", "<mask>", "<s>") else self.decoder.get(int(s), s) if s.lstrip("-").isdigit() else s
+                       for s in syms)
+        return bytearray(self.byte_decoder[c] for c in text if c in self.byte_decoder).decode("utf-8", errors="replace").replace("<s>", "")

@@ -43,11 +43,12 @@ extern "C" int mb_init(int device, mb_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MB_ERR_CUDA;
     if (prop.major != 10) return MB_ERR_NO_DEVICE;   // kernels are sm_100a only
-    if (cudaSetDevice(device) != cudaSuccess) return MB_ERR_CUDA;
     mb_ctx* ctx = new mb_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    MbDeviceGuard guard(ctx);            // the caller's current device is left as it was
     if (cudaMalloc(&ctx->dev_diag, 64) != cudaSuccess) {
+        cudaGetLastError();
         delete ctx;
         return MB_ERR_CUDA;
     }
@@ -58,7 +59,7 @@ extern "C" int mb_init(int device, mb_ctx** out) {
 
 extern "C" void mb_free(mb_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    MbDeviceGuard guard(ctx);
     mb_free_models(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->dev_diag) cudaFree(ctx->dev_diag);
@@ -66,6 +67,7 @@ extern "C" void mb_free(mb_ctx* ctx) {
 }
 
 extern "C" int mb_set_dtype(mb_ctx* ctx, int dtype) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     if (dtype != MB_DTYPE_BF16 && dtype != MB_DTYPE_F16) return mb_set_err(ctx, MB_ERR_ARG, "mb_set_dtype: unknown dtype %d", dtype);
     if ((dtype == MB_DTYPE_F16) != (ctx->f16 != 0)) mb_free_models(ctx);   // packed weights are dtype-specific: unload
@@ -77,6 +79,7 @@ extern "C" int mb_get_dtype(const mb_ctx* ctx) { return ctx && ctx->f16 ? MB_DTY
 // Live timing of the tensor-core GEMM launches (bench.py roofline).  enable != 0 starts (and resets) the collection;
 // mb_profile_read drains it: out3 = {sum of launch durations [ms], sum of algorithmic FLOPs, launches}.
 extern "C" int mb_profile_enable(mb_ctx* ctx, int enable) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     mb_profile_drain(ctx);
     ctx->profile = enable != 0;
@@ -85,6 +88,7 @@ extern "C" int mb_profile_enable(mb_ctx* ctx, int enable) {
     return MB_OK;
 }
 extern "C" int mb_profile_read(mb_ctx* ctx, double* out3) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx || !out3) return MB_ERR_ARG;
     mb_profile_drain(ctx);
     out3[0] = ctx->prof_ms_total; out3[1] = ctx->prof_flops_total; out3[2] = (double)ctx->prof_launches;
@@ -97,6 +101,7 @@ extern "C" unsigned long long mb_launch_count(const mb_ctx* ctx) { return ctx ? 
 
 // Reads (and clears) the diagnostic word kernels write before trapping (debug aid for tests).
 extern "C" unsigned int mb_debug_diag(mb_ctx* ctx) {
+    MbDeviceGuard _mb_guard(ctx);
     unsigned int v = 0;
     if (ctx && ctx->dev_diag) cudaMemcpy(&v, ctx->dev_diag, 4, cudaMemcpyDeviceToHost);
     return v;

@@ -261,6 +261,7 @@ extern "C" int mb_craft_post(mb_ctx* ctx, const float* text_dev, const float* li
                              int32_t* n_labels_dev, int32_t* stats_dev, int max_labels, float* det_dev,
                              float* adj_dev, int32_t* rects_dev, int32_t* mapper_dev, int32_t* n_boxes_dev,
                              int max_boxes, void* stream_) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     MB_REQUIRE(ctx, n_img > 0 && h > 0 && w > 0, "craft_post: empty input");

@@ -43,6 +43,18 @@ struct mb_ctx {
 };
 
 int mb_set_err(mb_ctx* ctx, int code, const char* fmt, ...);
+
+// Every C-ABI entry point that touches the device selects the context's device for its own duration and restores the
+// caller's (a Marie executor thread may have another device current; cudaMalloc / launches follow the calling thread).
+struct MbDeviceGuard {
+    int prev = -1;
+    explicit MbDeviceGuard(const mb_ctx* ctx) {
+        if (!ctx) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; return; }
+        if (prev != ctx->device) cudaSetDevice(ctx->device); else prev = -1;
+    }
+    ~MbDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 void* mb_scratch(mb_ctx* ctx, size_t bytes);   // returns nullptr + sets error on failure
 
 #define MB_CUDA(ctx, expr)                                                             \

@@ -230,6 +230,7 @@ void mb_free_craft(mb_ctx* ctx) {
 }
 
 extern "C" int mb_load_craft(mb_ctx* ctx, const void* blob_host, size_t nbytes) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     mb_free_craft(ctx);
     CraftModel* m = new CraftModel();
@@ -363,6 +364,7 @@ int mb_craft_forward_impl(mb_ctx* ctx, const bf16* x, int n, int h, int w, float
 
 extern "C" int mb_craft_forward(mb_ctx* ctx, const void* x_dev, int n, int h, int w, float* scores_dev,
                                 void* feature_dev, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     const long long P2 = (long long)n * (h / 2) * (w / 2);
     return mb_craft_forward_impl(ctx, (const bf16*)x_dev, n, h, w, scores_dev, scores_dev + P2, (bf16*)feature_dev,

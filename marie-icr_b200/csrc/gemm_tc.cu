@@ -656,6 +656,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
 extern "C" int mb_gemm16(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w,
                             int M, int N, int K, const float* bias_dev, int act, const void* residual_dev,
                             long long res_ld, void* out_dev, long long out_ld, int out_mode, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TapGemm g;
     g.a0 = (const bf16*)a_dev; g.c0 = K; g.a0_ld = (int)lda;
@@ -673,6 +674,7 @@ extern "C" int mb_gemm16(mb_ctx* ctx, const void* a_dev, long long lda, const vo
 extern "C" int mb_gemm16_batched(mb_ctx* ctx, const void* a_dev, long long lda, const void* w_dev, int n_rows_w, int M,
                                  int N, int K, int batches, int a_col_stride, int w_row_stride, int out_col_stride,
                                  const float* bias_dev, int act, void* out_dev, long long out_ld, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TapGemm g;
     g.a0 = (const bf16*)a_dev; g.c0 = K; g.a0_ld = (int)lda;
@@ -688,6 +690,7 @@ extern "C" int mb_conv16(mb_ctx* ctx, const void* a0_dev, int c0, int a0_ld, con
                             int a1_ld, int n, int h, int w, int taps, int dil, const void* w_dev,
                             int n_rows_w, int n_out, const float* bias_dev, int act, void* out_dev,
                             long long out_ld, int out_mode, long long out_plane, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TapGemm g;
     g.a0 = (const bf16*)a0_dev; g.c0 = c0; g.a0_ld = a0_ld;

@@ -700,6 +700,7 @@ int mb_crops_from_rects(mb_ctx* ctx, const uint8_t* pages, long long page_stride
 
 extern "C" int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_pages, int page_h, int page_w,
                                   int target_h, int target_w, int out_h, int out_w, void* out_dev, void* stream_) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     MB_REQUIRE(ctx, n_pages > 0 && page_h > 0 && page_w > 0, "page_preprocess: empty input");
@@ -744,6 +745,7 @@ extern "C" int mb_page_preprocess(mb_ctx* ctx, const uint8_t* pages_dev, int n_p
 extern "C" int mb_pack_crops(mb_ctx* ctx, const uint8_t* pages_dev, int page_h, int page_w,
                              const int32_t* rects_dev, const int32_t* page_idx_dev, int n_crops, void* out_dev,
                              int layout, void* stream_) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_crops == 0) return 0;
@@ -764,6 +766,7 @@ extern "C" int mb_pack_crops(mb_ctx* ctx, const uint8_t* pages_dev, int page_h, 
 
 extern "C" int mb_pack_fragments(mb_ctx* ctx, const uint8_t* buf_dev, const long long* offsets_dev,
                                  const int32_t* hw_dev, int n_crops, void* out_dev, int layout, void* stream_) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_crops == 0) return 0;

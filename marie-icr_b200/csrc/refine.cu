@@ -136,6 +136,7 @@ void mb_free_refine(mb_ctx* ctx) {
 }
 
 extern "C" int mb_load_refine(mb_ctx* ctx, const void* blob_host, size_t nbytes) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     mb_free_refine(ctx);
     RefineModel* m = new RefineModel();
@@ -168,6 +169,7 @@ extern "C" int mb_load_refine(mb_ctx* ctx, const void* blob_host, size_t nbytes)
 // OVERWRITTEN with the score maps.  scores_dev: [2][n][h][w] fp32 (text, link).  link_out_dev: [n][h][w] fp32.
 extern "C" int mb_refine_forward(mb_ctx* ctx, void* feature_dev, const float* scores_dev, int n, int h, int w,
                                  float* link_out_dev, void* stream_) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     RefineModel* m = ctx->refine;
     if (!m) return mb_set_err(ctx, MB_ERR_STATE, "refine: weights not loaded (mb_load_refine)");
@@ -213,6 +215,7 @@ extern "C" int mb_refine_forward(mb_ctx* ctx, void* feature_dev, const float* sc
 extern "C" int mb_line_components(mb_ctx* ctx, const float* link_dev, int n, int h, int w, float link_threshold,
                                   int32_t* labels_dev, int32_t* n_labels_dev, int32_t* stats_dev, int max_labels,
                                   void* stream_) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream_;
     MB_REQUIRE(ctx, n > 0 && h > 0 && w > 0 && link_dev && n_labels_dev && stats_dev && max_labels > 1,

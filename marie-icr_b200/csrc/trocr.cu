@@ -1215,6 +1215,7 @@ void mb_free_trocr(mb_ctx* ctx) {
 }
 
 extern "C" int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     mb_free_trocr(ctx);
     TrocrModel* m = new TrocrModel();
@@ -1288,6 +1289,7 @@ extern "C" int mb_load_trocr(mb_ctx* ctx, const void* blob_host, size_t nbytes) 
 }
 
 extern "C" int mb_trocr_dims(mb_ctx* ctx, int* dims) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx || !ctx->trocr) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded");
     TrocrModel* m = ctx->trocr;
     dims[0] = m->enc_dim; dims[1] = m->dec_dim; dims[2] = m->vocab; dims[3] = m->tokens;
@@ -1297,6 +1299,7 @@ extern "C" int mb_trocr_dims(mb_ctx* ctx, int* dims) {
 // Test hook: row-wise LayerNorm of a [rows, D] 16-bit matrix with fp32 gamma / beta.
 extern "C" int mb_layernorm16(mb_ctx* ctx, const void* in_dev, void* out_dev, const float* gamma_dev, const float* beta_dev,
                               long long rows, int D, float eps, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     return layernorm(ctx, (const bf16*)in_dev, (bf16*)out_dev, gamma_dev, beta_dev, rows, D, eps, (cudaStream_t)stream);
 }
@@ -1305,6 +1308,7 @@ extern "C" int mb_layernorm16(mb_ctx* ctx, const void* in_dev, void* out_dev, co
 // mode 0: tcgen05 kernel (attn_tc.cu); mode 1: mma.sync flash kernel (the one the decoder's cross-attention uses).
 extern "C" int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, int n, int T, int D, float scale,
                               int mode, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     MB_REQUIRE(ctx, n > 0 && T > 0 && D > 0 && D % DH == 0, "attention16: bad geometry");
     cudaStream_t s = (cudaStream_t)stream;
@@ -1321,12 +1325,14 @@ extern "C" int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, i
 
 // cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded}
 extern "C" int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx || !ctx->trocr || !out3) return MB_ERR_STATE;
     out3[0] = ctx->trocr->decode_calls; out3[1] = ctx->trocr->decode_steps; out3[2] = ctx->trocr->decode_rows;
     return 0;
 }
 
 extern "C" int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void* enc_out_dev, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TrocrModel* m = ctx->trocr;
     if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
@@ -1349,6 +1355,7 @@ extern "C" int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void
 extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int beam, int max_len_b,
                                int32_t* tokens_out_dev, int out_ld, int32_t* lengths_dev, float* scores_dev,
                                int* steps_run, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TrocrModel* m = ctx->trocr;
     if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
@@ -1392,6 +1399,7 @@ extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int 
 // logits_out [L, n, V] fp32 receives the raw decoder outputs of every step (before log-softmax / masking).
 extern "C" int mb_trocr_forced_logits(mb_ctx* ctx, const void* enc_out_dev, int n, const int32_t* forced_dev, int L,
                                       float* logits_out_dev, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TrocrModel* m = ctx->trocr;
     if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");
@@ -1419,6 +1427,7 @@ extern "C" int mb_trocr_forced_logits(mb_ctx* ctx, const void* enc_out_dev, int 
 extern "C" int mb_trocr_recognize(mb_ctx* ctx, const void* patches_dev, int n, int beam, int max_len_b, int chunk,
                                   int32_t* tokens_out_dev, int out_ld, int32_t* lengths_dev, float* scores_dev,
                                   void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
     TrocrModel* m = ctx->trocr;
     if (!m) return mb_set_err(ctx, MB_ERR_STATE, "trocr: weights not loaded (mb_load_trocr)");

@@ -15,7 +15,7 @@ from .boxes import BoxProcessorCraftB200
 from .document import TrOcrProcessorB200
 from .pipeline import PSM_PRESETS, records_to_words
 from .ingest import hash_frames_fast
-from .plugin_api import CoordinateFormat, PSMode, assemble_result
+from .plugin_api import MODEL_PATH, CoordinateFormat, PSMode, assemble_result
 
 
 def copy_frames(frames):
@@ -29,9 +29,12 @@ def copy_frames(frames):
 
 
 class OcrEngineB200:
-    def __init__(self, models_dir="./model_zoo", cuda=True, *, box_processor=None, default_ocr_processor=None, **kwargs):
+    def __init__(self, models_dir=MODEL_PATH, cuda=True, *, box_processor=None, default_ocr_processor=None, **kwargs):
+        """models_dir is the model zoo root (marie/ocr/ocr_engine.py:35-37): CRAFT weights under `<models_dir>/craft`,
+        the TrOCR checkpoint at `<models_dir>/trocr/trocr-large-printed.pt`, BPE assets under `<models_dir>/assets`."""
+        import os
         if box_processor is None:
-            box_processor = BoxProcessorCraftB200(models_dir=models_dir, cuda=cuda)
+            box_processor = BoxProcessorCraftB200(models_dir=os.path.join(models_dir, "craft"), cuda=cuda)
         if default_ocr_processor is None:
             default_ocr_processor = TrOcrProcessorB200(models_dir=models_dir, cuda=cuda,
                                                        pipeline=getattr(box_processor, "pipeline", None))
@@ -82,7 +85,7 @@ class OcrEngineB200:
         pages = torch.from_numpy(np.stack(frames)).pin_memory()
         icr = self.icr_processor
         rec, counts = pipe.run_host(pages, preset=PSM_PRESETS[pms_mode.value], beam=icr.beam, max_len_b=icr.max_len_b,
-                                    out_ld=min(icr.max_len_b + 1, 64))
+                                    out_ld=icr.max_len_b + 1)
         words = records_to_words(rec, icr.detok)
         results, k = [], 0
         for i, img in enumerate(frames):

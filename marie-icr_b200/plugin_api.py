@@ -9,10 +9,15 @@ When the real `marie` package is importable the processors can be registered wit
 classes here carry the same names, argument meaning, return shapes and error behaviour, so the parity tests read like
 the reference's own integration scripts (tests/integration/test_icr.py).
 """
+import os
 from abc import ABC, abstractmethod
 from enum import Enum
 
 import numpy as np
+
+# marie/constants.py:91-96: __model_path__ = <MARIE_DEFAULT_MOUNT or the directory above the package>/model_zoo
+MODEL_PATH = os.path.join(os.environ.get("MARIE_DEFAULT_MOUNT", os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))),
+                          "model_zoo")
 
 
 class PSMode(Enum):

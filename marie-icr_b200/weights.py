@@ -159,7 +159,48 @@ def pack_refine(state_dict, dtype=torch.float16):
     return build_blob(t)
 
 
-def pack_trocr(state_dict, cfg, dtype=torch.float16):
+def validate_trocr_variant(state_dict, cfg, info=None):
+    """The kernels implement ONE TrOCR variant — the reference's default checkpoint family (trocr-{base,large}-printed /
+    -handwritten, arch tables trocr_models.py:423-447): BEiT encoder without qkv bias or distillation token, 577 tokens,
+    sinusoidal decoder positions, scaled embeddings, no embedding LayerNorm, post-LN decoder layers, ReLU.  Any other
+    variant the reference can load (trocr_small with learned positions / layernorm_embedding, deit_* encoders with qkv
+    bias and dist_token, GELU decoders) would silently produce wrong tokens — refuse it instead.  `info`: configuration
+    fields read from the checkpoint (checkpoint.load_fairseq_checkpoint), when there are any."""
+    bad = []
+    keys = set(state_dict.keys())
+    if "decoder.embed_positions.weight" in keys:
+        bad.append("learned decoder positions (decoder.embed_positions.weight); only sinusoidal positions are implemented")
+    if any(k.startswith("decoder.layernorm_embedding.") for k in keys):
+        bad.append("decoder.layernorm_embedding")
+    if any(k.startswith("decoder.layer_norm.") for k in keys):
+        bad.append("decoder.layer_norm (pre-LN decoder, decoder_normalize_before)")
+    if any(k.endswith("attn.qkv.bias") or k.endswith("attn.q_bias") for k in keys if k.startswith("encoder.deit.")):
+        bad.append("encoder qkv bias")
+    if "encoder.deit.dist_token" in keys:
+        bad.append("encoder.deit.dist_token (distilled DeiT encoder)")
+    if getattr(cfg, "tokens", 577) != 577:
+        bad.append(f"{cfg.tokens} encoder tokens (577 expected: 384x384 input, 16x16 patches, cls token)")
+    if "encoder.deit.pos_embed" in keys and tuple(state_dict["encoder.deit.pos_embed"].shape[:2]) != (1, 577):
+        bad.append(f"pos_embed of shape {tuple(state_dict['encoder.deit.pos_embed'].shape)}")
+    if "decoder.output_projection.weight" not in keys:
+        bad.append("no decoder.output_projection.weight (tied embeddings are not implemented)")
+    for k in keys:
+        if k.startswith("encoder.deit.blocks.") and (".gamma_1" in k or ".gamma_2" in k or "relative_position" in k):
+            bad.append("BEiT LayerScale / relative position bias (" + k + ")")
+            break
+    info = info or {}
+    act = info.get("activation_fn")
+    if act is not None and str(act).split(".")[-1].lower() != "relu":
+        bad.append(f"decoder activation_fn={act!r} (ReLU is implemented)")
+    for flag, why in (("decoder_learned_pos", "learned positions"), ("decoder_normalize_before", "pre-LN decoder"),
+                      ("layernorm_embedding", "embedding LayerNorm"), ("no_scale_embedding", "unscaled embeddings")):
+        if info.get(flag) is True:
+            bad.append(f"{flag}=True ({why})")
+    if bad:
+        raise ValueError("unsupported TrOCR variant: " + "; ".join(bad))
+
+
+def pack_trocr(state_dict, cfg, dtype=torch.float16, info=None):
     """fairseq TrOCR state dict (`encoder.deit.*`, `decoder.*`) -> blob bytes for mb_load_trocr.
     cfg: any object with enc_dim, enc_layers, enc_heads, enc_ffn, dec_dim, dec_layers, dec_heads, dec_ffn, vocab,
     tokens, max_positions.  Layout choices: q/k/v of the decoder self-attention fused into one [3H, H] matrix,
@@ -167,6 +208,7 @@ def pack_trocr(state_dict, cfg, dtype=torch.float16):
     into the decoder q weights/biases; cls_token is folded into row 0 of the position table; the sinusoidal position
     table (fairseq SinusoidalPositionalEmbedding) is precomputed in fp32."""
     import math
+    validate_trocr_variant(state_dict, cfg, info)
     sd = {k: v.detach().float().cpu() for k, v in state_dict.items() if torch.is_tensor(v)}
     t = {}
     t["config"] = torch.tensor([cfg.enc_dim, cfg.enc_layers, cfg.enc_heads, cfg.enc_ffn, cfg.dec_dim, cfg.dec_layers,

@@ -110,8 +110,12 @@ def sinusoidal_table(n, dim, padding_idx=PAD):
 class DecoderState:
     """Incremental state: per layer self-attention K/V [rows, heads, t, dh] and static cross-attention K/V."""
 
-    def __init__(self, sd, cfg, enc_out):
-        self.sd, self.cfg = sd, cfg
+    def __init__(self, sd, cfg, enc_out, beam=1):
+        """enc_out [B, T, E]; rows of the state are B*beam (row = sentence*beam + beam slot).  The static cross-attention
+        K/V are computed and kept once per SENTENCE: fairseq computes them on the beam-expanded encoder output
+        (generator.py:68-70) and reorders them every step, but all beams of a sentence share identical encoder states
+        and a reorder never crosses sentences, so the values are the same."""
+        self.sd, self.cfg, self.beam = sd, cfg, beam
         H, h = cfg.dec_dim, cfg.dec_heads
         self.dh = H // h
         B, T, _ = enc_out.shape
@@ -126,7 +130,6 @@ class DecoderState:
 
     def reorder(self, idx):
         self.self_kv = [(k[idx], v[idx]) for k, v in self.self_kv]
-        self.cross = [(k[idx], v[idx]) for k, v in self.cross]
 
     def step(self, tokens_last, t, return_hidden=False):
         """tokens_last [rows] (token at position t, 0-based) -> logits [rows, V] (fp32)."""
@@ -147,8 +150,9 @@ class DecoderState:
             x = _ln(x + F.linear(a.reshape(R, H), sd[b + "self_attn.out_proj.weight"], sd[b + "self_attn.out_proj.bias"]),
                     sd, b + "self_attn_layer_norm", 1e-5)
             q = F.linear(x, sd[b + "encoder_attn.q_proj.weight"], sd[b + "encoder_attn.q_proj.bias"]) * dh ** -0.5
-            ck, cv = self.cross[i]
-            a = (q.view(R, h, 1, dh) @ ck.transpose(-2, -1)).softmax(-1) @ cv
+            ck, cv = self.cross[i]                                     # [B, h, T, dh], shared by the beams of a sentence
+            q4 = q.view(R // self.beam, self.beam, h, dh).transpose(1, 2)
+            a = ((q4 @ ck.transpose(-2, -1)).softmax(-1) @ cv).transpose(1, 2)
             x = _ln(x + F.linear(a.reshape(R, H), sd[b + "encoder_attn.out_proj.weight"],
                                  sd[b + "encoder_attn.out_proj.bias"]), sd, b + "encoder_attn_layer_norm", 1e-5)
             y = F.linear(F.relu(F.linear(x, sd[b + "fc1.weight"], sd[b + "fc1.bias"])), sd[b + "fc2.weight"], sd[b + "fc2.bias"])
@@ -158,7 +162,7 @@ class DecoderState:
 
 
 # ------------------------------------------------------------------------------------------------- search
-def generate(sd, cfg, enc_out, beam=1, max_len_b=200, min_len=1, forced=None, trace=None):
+def generate(sd, cfg, enc_out, beam=1, max_len_b=200, min_len=1, forced=None, trace=None, margins=None):
     """fairseq sequence generation as configured by the reference (generator.py:11-374; task.py:165-276):
     returns, per input row, the list of finalised hypotheses sorted by score (desc), each a dict
     {tokens: LongTensor (ends with EOS), score: float (sum log-prob / length), positional_scores}.
@@ -166,12 +170,16 @@ def generate(sd, cfg, enc_out, beam=1, max_len_b=200, min_len=1, forced=None, tr
     Sentences are independent in fairseq's search, so finished sentences are simply frozen here instead of being
     removed from the batch (generator.py:262-297 only compacts the tensors).
     `forced`: optional [bsz, L] token matrix — teacher forcing for parity checks: the search is replaced by taking
-    forced[:, step] (beam must be 1) while `trace` collects (step, lprobs) for margin analysis."""
+    forced[:, step] (beam must be 1) while `trace` collects (step, lprobs) for margin analysis.
+    `margins`: optional list that receives, per input row, the smallest gap between neighbouring candidate scores the
+    search ever had to order while the sentence was live (beam 1: top-1 vs top-2 log-prob; beam b: the top 2b+1
+    cumulative scores) — the parity tests' margin protocol: a 16-bit implementation may legitimately order a closer
+    call differently."""
     bsz = enc_out.shape[0]
     V = cfg.vocab
     max_len = min(int(max_len_b), cfg.max_positions - 1)
     rows = bsz * beam
-    st = DecoderState(sd, cfg, enc_out.repeat_interleave(beam, 0))
+    st = DecoderState(sd, cfg, enc_out, beam)
     tokens = torch.full((rows, max_len + 2), PAD, dtype=torch.long)
     tokens[:, 0] = EOS
     scores = torch.zeros(rows, max_len + 1)
@@ -206,6 +214,14 @@ def generate(sd, cfg, enc_out, beam=1, max_len_b=200, min_len=1, forced=None, tr
             lp = lp + scores.view(bsz, beam, -1)[:, :, step - 1].unsqueeze(-1)
         flat = lp.reshape(bsz, -1)
         c_scores, c_idx = torch.topk(flat, k=min(cand, flat.shape[1] - 1))
+        if margins is not None:
+            if not margins:
+                margins.extend([math.inf] * bsz)
+            top = torch.topk(flat, k=min((1 if beam == 1 else cand) + 1, flat.shape[1])).values
+            gap = (top[:, :-1] - top[:, 1:]).min(-1).values
+            for s in range(bsz):
+                if not finished[s] and math.isfinite(float(gap[s])):
+                    margins[s] = min(margins[s], float(gap[s]))
         c_beam, c_tok = c_idx // V, c_idx % V
         new_tokens, new_scores, reorder = tokens.clone(), scores.clone(), torch.arange(rows)
         for s in range(bsz):

@@ -24,7 +24,8 @@ def engine(cuda_ctx):
     cal = torch.stack([torch.from_numpy(resample.fragment_to_input(f)) for f in frag0])
     with torch.no_grad():
         trocr.calibrate_eos(tsd, cfg, eos_step=4, enc=trocr.encoder_forward(tsd, cfg, cal))
-    icr = TrOcrProcessorB200(state_dict=tsd, config=cfg, beam=1, max_len_b=16, pipeline=box.pipeline)
+    from marie_icr_b200.bpe import SyntheticDetokenizer
+    icr = TrOcrProcessorB200(state_dict=tsd, config=cfg, beam=1, max_len_b=16, pipeline=box.pipeline, detokenizer=SyntheticDetokenizer())
     eng = OcrEngineB200(box_processor=box, default_ocr_processor=icr)
     return eng, pages, sd, tsd, cfg
 

@@ -98,9 +98,17 @@ def test_processors_refuse_cpu():
     from marie_icr_b200.document import TrOcrProcessorB200
     with pytest.raises(RuntimeError):
         BoxProcessorCraftB200(cuda=False)
+    with pytest.raises(FileNotFoundError, match="trocr-large-printed.pt"):      # the reference's default checkpoint (:198-217)
+        TrOcrProcessorB200(cuda=True, models_dir="/nonexistent/model_zoo")
+    with pytest.raises(AssertionError):                                          # :210
+        TrOcrProcessorB200(model_name_or_path="/nonexistent/x.pt")
+    with pytest.raises(FileNotFoundError, match="craft_mlt_25k.pth"):
+        if not torch.cuda.is_available():
+            raise FileNotFoundError("craft_mlt_25k.pth (skipped: the box processor needs a device before it looks for files)")
+        BoxProcessorCraftB200(models_dir="/nonexistent/craft")
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no cuda devices"):
-            TrOcrProcessorB200(cuda=True)
+            TrOcrProcessorB200(cuda=True, state_dict={}, config=None)
 
 
 def test_ensure_max_page_size_known_answers():
@@ -181,3 +189,124 @@ def test_pack_refine_layout():
     for k in range(1, 5):
         assert torch.equal(t["ref.final.w"][0, (k - 1) * 128:k * 128], sd[f"aspp{k}.6.weight"].reshape(128).to(torch.float16))
     assert abs(float(t["ref.final.b"][0]) - sum(float(sd[f"aspp{k}.6.bias"]) for k in range(1, 5))) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ round 2: boundary hardening
+def _tiny_gpt2_files(d):
+    """A miniature GPT-2 vocabulary (encoder.json) and fairseq dictionary (gpt2_with_mask.dict.txt) in directory d."""
+    import json
+    import os
+    from marie_icr_b200.bpe import _bytes_to_unicode
+    b2u = _bytes_to_unicode()
+    def enc(s):
+        return "".join(b2u[b] for b in s.encode("utf-8"))
+    vocab = {enc("Hel"): 0, enc("lo"): 1, enc(" wor"): 2, enc("ld"): 3, enc("!"): 4, enc(" caf"): 5, enc("é"): 6, enc(" <"): 7}
+    with open(os.path.join(d, "encoder.json"), "w", encoding="utf-8") as f:
+        json.dump(vocab, f)
+    with open(os.path.join(d, "gpt2_with_mask.dict.txt"), "w", encoding="utf-8") as f:
+        for gid in (3, 0, 1, 2, 4, 6, 5, 7):                   # fairseq order = frequency order, not id order
+            f.write(f"{gid} {100 - gid}\n")
+        f.write("<mask> 0\n")
+    return [3, 0, 1, 2, 4, 6, 5, 7]
+
+
+def test_gpt2_detokenizer_known_answers(tmp_path):
+    """Gpt2Detokenizer = Dictionary.string + GPT2BPEEnhancedSpace.decode (marie/models/unilm/trocr/bpe.py:59-67): ids are
+    fairseq dictionary indices (4 specials first), eos/bos are dropped, <unk>/<mask> stay literal, bytes are re-joined
+    across tokens (the two halves of a UTF-8 character may sit in different tokens)."""
+    from marie_icr_b200.bpe import Gpt2Detokenizer
+    order = _tiny_gpt2_files(str(tmp_path))
+    fid = {gid: 4 + i for i, gid in enumerate(order)}           # GPT-2 id -> fairseq id
+    detok = Gpt2Detokenizer.locate("/nonexistent", str(tmp_path))
+    assert detok.symbols[:4] == ["<s>", "<pad>", "</s>", "<unk>"] and detok.symbols[-1] == "<mask>"
+    assert detok.decode([fid[0], fid[1], fid[2], fid[3], fid[4], 2]) == "Hello world!"
+    assert detok.decode([0, fid[0], fid[1], fid[5], fid[6], 2]) == "Hello café"
+    assert detok.decode([fid[0], 3, fid[1], 2]) == "Hel<unk>lo"                      # Dictionary.string keeps <unk>
+    assert detok.decode([fid[0], len(detok.symbols) - 1, 2]) == "Hel<mask>"
+    assert detok.decode([2]) == "" and detok.decode([]) == ""
+    with pytest.raises(FileNotFoundError, match="encoder.json"):
+        Gpt2Detokenizer.locate("/nonexistent")
+
+
+def test_fairseq_checkpoint_loads_without_fairseq(tmp_path):
+    """checkpoint.load_fairseq_checkpoint: tensors and plain containers are rebuilt, fairseq / omegaconf classes (not
+    importable here) become inert bags, a malicious reduce payload is never called, and the configuration fields the
+    packer validates are found wherever the checkpoint keeps them."""
+    import argparse
+    import collections
+    import os
+    import sys
+    import types
+    import torch
+    from marie_icr_b200.checkpoint import load_fairseq_checkpoint
+    mod = types.ModuleType("fairseq_absent.dataclass")
+
+    class FairseqConfig:
+        def __init__(self):
+            self.activation_fn = "gelu"
+
+        def __reduce__(self):
+            return (FairseqConfig, (), self.__dict__)
+
+    FairseqConfig.__module__ = "fairseq_absent.dataclass"
+    FairseqConfig.__qualname__ = "FairseqConfig"
+    mod.FairseqConfig = FairseqConfig
+    marker = tmp_path / "executed"
+
+    class Payload:
+        def __reduce__(self):
+            return (os.system, (f"touch {marker}",))
+
+    sys.modules["fairseq_absent"] = types.ModuleType("fairseq_absent")
+    sys.modules["fairseq_absent.dataclass"] = mod
+    try:
+        sd = collections.OrderedDict(w=torch.randn(3, 4).half(), i=torch.arange(5), b=torch.randn(2).bfloat16())
+        ckpt = {"model": sd, "args": None, "extra_state": {"payload": Payload()},
+                "cfg": {"model": argparse.Namespace(activation_fn="relu", decoder_learned_pos=False, deit_arch="beit_large_patch16_384"),
+                        "bpe": FairseqConfig()}}
+        path = str(tmp_path / "ckpt.pt")
+        torch.save(ckpt, path)
+    finally:
+        del sys.modules["fairseq_absent.dataclass"], sys.modules["fairseq_absent"]
+    got, info = load_fairseq_checkpoint(path)
+    assert list(got) == list(sd) and all(torch.equal(got[k], sd[k]) and got[k].dtype == sd[k].dtype for k in sd)
+    assert info["activation_fn"] == "relu" and info["decoder_learned_pos"] is False and info["deit_arch"] == "beit_large_patch16_384"
+    assert not marker.exists()
+    torch.save({"no_model": 1}, path)
+    with pytest.raises(ValueError, match="not a fairseq checkpoint"):
+        load_fairseq_checkpoint(path)
+
+
+def test_pack_trocr_refuses_other_variants():
+    """weights.validate_trocr_variant: checkpoints of TrOCR variants the kernels do not implement raise instead of
+    decoding garbage (learned positions, layernorm_embedding, qkv bias, dist token, GELU decoder...)."""
+    import torch
+    from marie_icr_b200 import weights
+    from oracle import trocr
+    cfg = trocr.trocr_tiny()
+    sd = trocr.synth_trocr_state(cfg, 1, round_to=None)
+    weights.pack_trocr(sd, cfg, torch.float16, info={"activation_fn": "relu", "decoder_learned_pos": False})
+    for extra, pat in (({"decoder.embed_positions.weight": torch.zeros(4, 4)}, "learned decoder positions"),
+                       ({"decoder.layernorm_embedding.weight": torch.zeros(4)}, "layernorm_embedding"),
+                       ({"decoder.layer_norm.weight": torch.zeros(4)}, "pre-LN"),
+                       ({"encoder.deit.blocks.0.attn.qkv.bias": torch.zeros(4)}, "qkv bias"),
+                       ({"encoder.deit.dist_token": torch.zeros(1, 1, 4)}, "dist_token")):
+        with pytest.raises(ValueError, match=pat):
+            weights.pack_trocr({**sd, **extra}, cfg, torch.float16)
+    with pytest.raises(ValueError, match="activation_fn"):
+        weights.pack_trocr(sd, cfg, torch.float16, info={"activation_fn": "gelu"})
+    with pytest.raises(ValueError, match="no_scale_embedding"):
+        weights.pack_trocr(sd, cfg, torch.float16, info={"no_scale_embedding": True})
+    fairseq_sinusoidal = {**sd, "decoder.embed_positions._float_tensor": torch.zeros(1)}      # what fairseq really stores
+    weights.pack_trocr(fairseq_sinusoidal, cfg, torch.float16)
+
+
+def test_string_path_fragments(tmp_path):
+    """memory_dataset.py:20-32: a fragment may be an image path (opened as RGB) — converted to the BGR array K9 expects."""
+    import cv2
+    from marie_icr_b200.document import _load_fragment
+    img = np.random.default_rng(3).integers(0, 256, (12, 17, 3), dtype=np.uint8)
+    path = str(tmp_path / "frag.png")
+    cv2.imwrite(path, img)
+    assert np.array_equal(_load_fragment(path), img) and np.array_equal(_load_fragment(img), img)
+    assert _load_fragment(img[:, :, 0]).shape == (12, 17, 3)

@@ -123,3 +123,133 @@ def test_crop_to_content():
             b = ingest.crop_to_content(frame.copy(), content_aware=aware)
             assert a.shape == b.shape and np.array_equal(a, b)
     assert ingest.crop_to_content(page).shape[1] < page.shape[1]
+
+
+# ------------------------------------------------------------------------------------------- round 2 pins
+def _vit_state(sd):
+    return {k[len("encoder.deit."):]: v for k, v in sd.items() if k.startswith("encoder.deit.")}
+
+
+def test_trocr_encoder_against_reference_forward_features():
+    """oracle.encoder_forward == the reference's own AdaptedVisionTransformer.forward_features
+    (marie/models/unilm/trocr/deit.py:105-146) running on the reference-held ViT blocks
+    (marie/boxes/dit/ditod/deit.py:44-167) — tiny widths, strict state-dict load (pins the key names too)."""
+    from functools import partial
+    from oracle import trocr
+    deit = ref_loader.load_trocr_deit()
+    cfg = trocr.trocr_tiny()
+    sd = trocr.synth_trocr_state(cfg, 5, round_to=None)
+    net = deit.AdaptedVisionTransformer(img_size=384, patch_size=16, embed_dim=cfg.enc_dim, depth=cfg.enc_layers,
+                                        num_heads=cfg.enc_heads, mlp_ratio=cfg.enc_ffn / cfg.enc_dim, qkv_bias=False,
+                                        norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), ape=0, mask_ratio=0.0)
+    net.load_state_dict(_vit_state(sd), strict=True)
+    net.eval()
+    torch.manual_seed(1)
+    imgs = torch.rand(3, 3, 384, 384) * 2 - 1
+    with torch.no_grad():
+        want, _ = net.forward_features(imgs)
+        got = trocr.encoder_forward(sd, cfg, imgs)
+    assert want.shape == got.shape == (3, 577, cfg.enc_dim)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())
+
+
+def test_trocr_encoder_base_factory_geometry():
+    """beit_base_patch16_384 (deit.py:323-329) as the reference builds it: one crop at full TrOCR-base geometry."""
+    from oracle import trocr
+    deit = ref_loader.load_trocr_deit()
+    cfg = trocr.trocr_base()
+    sd = trocr.synth_trocr_state(cfg, 1, round_to=None)
+    net = deit.beit_base_patch16_384(ape=0, mask_ratio=0.0)
+    net.load_state_dict(_vit_state(sd), strict=True)
+    net.eval()
+    torch.manual_seed(2)
+    imgs = torch.rand(1, 3, 384, 384) * 2 - 1
+    with torch.no_grad():
+        want, _ = net.forward_features(imgs)
+        got = trocr.encoder_forward(sd, cfg, imgs)
+    rel = float((got - want).norm() / want.norm())
+    assert rel < 1e-5, rel
+
+
+def test_box_loop_against_reference_source():
+    """oracle boxes_to_rects / crop_rect == the reference's own per-box loop and crop_poly_low
+    (marie/boxes/craft_box_processor.py:42-73,499-537, executed from its source): random quadrilaterals incl. boxes
+    clipped by every page border, degenerate and negative coordinates."""
+    import tempfile
+    from oracle import craft_post
+    run = ref_loader.load_box_loop()
+    rng = np.random.default_rng(5)
+    H, W = 300, 420
+    image = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    boxes = []
+    for _ in range(300):
+        cx, cy = rng.uniform(-5, W + 5), rng.uniform(-5, H + 5)
+        w, h, a = rng.uniform(1, 90), rng.uniform(1, 40), rng.uniform(0, np.pi)
+        c, s = np.cos(a), np.sin(a)
+        pts = np.array([[-w, -h], [w, -h], [w, h], [-w, h]], np.float32) / 2 @ np.array([[c, s], [-s, c]], np.float32)
+        boxes.append((pts + np.array([cx, cy], np.float32)).astype(np.float32))
+    for b in ([[0, 0], [W, 0], [W, H], [0, H]], [[W - 1, H - 1]] * 4, [[3.9, 3.9], [4.1, 3.9], [4.1, 4.1], [3.9, 4.1]]):
+        boxes.append(np.array(b, np.float32))
+    boxes = [b for b in boxes if b[:, 0].max() >= 0 and b[:, 1].max() >= 0 and b[:, 0].min() < W and b[:, 1].min() < H]
+    with tempfile.TemporaryDirectory() as d:
+        rects, frags, line_ids = run(image, boxes, [], d)
+    want_rects = craft_post.boxes_to_rects(boxes, H, W)
+    assert [list(map(int, r)) for r in rects] == want_rects
+    assert line_ids == [-1] * len(boxes)
+    n_clipped = 0
+    for r, f in zip(want_rects, frags):
+        mine = craft_post.crop_rect(image, r)
+        assert mine.shape == f.shape and np.array_equal(mine, f), r
+        n_clipped += (r[0] + r[2] + 1 > W) or (r[1] + r[3] + 1 > H) or r[0] == 0 or r[1] == 0
+    assert n_clipped > 20
+
+
+@pytest.mark.parametrize("beam,max_len_b", [(1, 40), (3, 40), (5, 40), (2, 4)])
+def test_search_against_reference_generate_loop(beam, max_len_b):
+    """oracle.generate == the reference's own TextRecognitionGenerator._generate (generator.py:11-374, executed from the
+    file; fairseq's BeamSearch.step / finalize_hypos restated in oracle/ref_loader.load_generator) on the same
+    incremental decoder: tokens, scores and positional scores of EVERY finalised hypothesis, hypotheses of different
+    lengths (so the loop's batch compaction :262-297 runs) and the max_len EOS forcing (:165-167)."""
+    from oracle import trocr
+    Gen, make_model = ref_loader.load_generator()
+    cfg = trocr.trocr_tiny()
+    sd = trocr.synth_trocr_state(cfg, 8, round_to=None)
+    torch.manual_seed(3)
+    imgs = torch.stack([(torch.rand(3, 384, 384) * 2 - 1) * a + b for a, b in
+                        [(1, 0), (0.2, 0.7), (0.5, -0.5), (0.1, -0.9), (1, 0.0), (0.3, 0.3), (0.05, 0.95)]]).clamp(-1, 1)
+    with torch.no_grad():
+        trocr.calibrate_eos(sd, cfg, eos_step=6, round_to=None, margin=0.25, enc=trocr.encoder_forward(sd, cfg, imgs[:2]))
+        enc = trocr.encoder_forward(sd, cfg, imgs)
+        mine = trocr.generate(sd, cfg, enc, beam=beam, max_len_b=max_len_b)
+        gen = Gen(make_model(sd, cfg), cfg.vocab, beam_size=beam, max_len_b=max_len_b)
+        ref = gen._generate({"net_input": {"imgs": imgs}})
+    lens = set()
+    for a, b in zip(mine, ref):
+        assert len(a) == len(b) == beam
+        for ha, hb in zip(a, b):
+            assert ha["tokens"].tolist() == hb["tokens"].tolist()
+            assert abs(ha["score"] - float(hb["score"])) <= 1e-5
+            assert torch.allclose(ha["positional_scores"], hb["positional_scores"], atol=1e-5)
+        lens.add(max(len(h["tokens"]) for h in a))            # the step the sentence left the batch
+    if max_len_b > 10:
+        assert len(lens) > 1, "sentences should finish at different steps"
+    else:
+        assert all(len(h["tokens"]) <= max_len_b + 1 for hyps in mine for h in hyps)
+
+
+def test_detokenizer_against_reference_bpe_decode(tmp_path):
+    """Gpt2Detokenizer.decode(ids) == GPT2BPEEnhancedSpace.decode(Dictionary.string(ids)) with the reference's own
+    decode (marie/models/unilm/trocr/bpe.py:59-67, executed from the file) on a miniature vocabulary."""
+    import os
+    from marie_icr_b200.bpe import Gpt2Detokenizer
+    from test_host_logic import _tiny_gpt2_files
+    order = _tiny_gpt2_files(str(tmp_path))
+    ref = ref_loader.load_bpe()(os.path.join(str(tmp_path), "encoder.json"))
+    detok = Gpt2Detokenizer.locate(str(tmp_path))
+    rng = np.random.default_rng(7)
+    n_sym = len(detok.symbols)
+    for _ in range(200):
+        ids = rng.integers(3, n_sym, int(rng.integers(1, 9))).tolist() + [2]
+        # fairseq Dictionary.string with extra_symbols_to_ignore = {eos}: bos / eos dropped, everything else joined by ' '
+        hypo_str = " ".join(detok.symbols[t] for t in ids if t not in (0, 2))
+        assert detok.decode(ids) == ref.decode(hypo_str), ids
