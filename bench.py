@@ -1,17 +1,26 @@
-"""bench.py — the hot path on synthetic letter pages: CRAFT box detection + TrOCR-base greedy ICR (BASELINE.json
-configs[1]: batch of 64 pages per GPU).  One JSON line on stdout (rank 0).
+"""bench.py — the CRAFT -> TrOCR hot path on synthetic pages.  One JSON line on stdout (rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (B200, hand-written CUDA through the C ABI)
-  python bench.py --impl reference [...]                         the reference's algorithm on the host cores
-                                                                 (oracle port: the reference needs fairseq/timm, absent)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--dtype fp16|bf16]     our arm (B200, hand-written CUDA)
+  python bench.py --impl reference [...]       the reference's algorithm on the host cores (CPU port: the reference itself
+                                               needs fairseq / timm / docarray, absent here — DESIGN.md §4)
+  python bench.py --impl reference --full-pages  the SURVEY §8d CPU protocol: 1 warm-up + 3 timed FULL pages, both variants
+
+--config selects the BASELINE.json workload (index into its `configs`):
+  1 (default)  64 synthetic letter pages / GPU / step, CRAFT detect + TrOCR-base greedy            weak scaling
+  2            chunk of the 10k-page stream, TrOCR-base beam 5, FIXED page count split over ranks    strong scaling
+  3            high-density form pages (~800 crops / page), TrOCR-large, beam 3 (reference default)  weak scaling
+  4            LINE mode: 4096x4096 pages, CRAFT LINE preset + refiner line branch + line merge,
+               TrOCR-large beam 3                                                                  weak scaling
+
 A "step" is one pass of the whole path over one batch of pages per GPU.  `value` = pages/s with the page batch already
-resident in HBM; `e2e` = the same through host buffers (pinned pages -> device, word records -> host) every step.
-Under torchrun each rank runs its own batch (weak scaling: page i of the stream -> rank i mod world) and the packed
-word records are gathered with one NCCL all_gather pair inside the timed region.
+resident in HBM; `e2e` = the same pages as HOST ndarrays through the plugin call `OcrEngineB200.extract(frames)` —
+pinned staging, H2D, the device path, record D2H, detokenisation and the reference's result assembly
+({meta, words, lines} per page) all inside the timed region.  Under torchrun each rank runs its own shard
+(page i of the stream -> rank i mod world) and the packed word records are gathered with one NCCL all_gather pair inside
+the timed region of `value`.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -25,9 +34,24 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-METRIC = "pages/sec (CRAFT detect + TrOCR-base greedy ICR, 2550x3300 synthetic letter pages, ~510 word crops/page)"
-OUT_LD = 32           # tokens kept per word record
+OUT_LD = 32           # tokens kept per word record on the device-resident path (hypotheses here end after ~7 tokens;
+                      # longer ones are counted in config.truncated_records, the engine path keeps max_len_b + 1)
 MAX_LEN_B = 200       # task.py:266
+
+CONFIGS = {
+    1: dict(name="configs[1]", model="base", beam=1, pages=64, page="letter", preset="sparse", scaling="weak", refiner=False,
+            what="64 synthetic letter pages/GPU/step, CRAFT detect + TrOCR-base greedy ICR",
+            metric="pages/sec (CRAFT detect + TrOCR-base greedy ICR, 2550x3300 synthetic letter pages, ~510 word crops/page)"),
+    2: dict(name="configs[2]", model="base", beam=5, pages=64, page="letter", preset="sparse", scaling="strong", refiner=False,
+            what="64-page chunk of the 10k-page letter stream split over the ranks (page i -> rank i mod N), TrOCR-base beam 5, NCCL gather",
+            metric="pages/sec (10k-page stream, CRAFT detect + TrOCR-base beam-5 ICR, 2550x3300 synthetic letter pages)"),
+    3: dict(name="configs[3]", model="large", beam=3, pages=16, page="dense", preset="sparse", scaling="weak", refiner=False,
+            what="16 high-density form pages/GPU/step (~800 word crops/page), TrOCR-large beam 3, crops pooled into balanced batches",
+            metric="pages/sec (high-density form pages ~800 crops/page, CRAFT detect + TrOCR-large beam-3 ICR)"),
+    4: dict(name="configs[4]", model="large", beam=3, pages=8, page="4096", preset="line", scaling="weak", refiner=True,
+            what="8 synthetic 4096x4096 pages/GPU/step, LINE preset + refiner line branch + line merge, TrOCR-large beam 3",
+            metric="pages/sec (line-level mode, 4096x4096 pages, CRAFT + line merge + TrOCR-large beam-3 ICR)"),
+}
 
 
 def parse():
@@ -36,35 +60,68 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pages", type=int, default=64, help="pages per GPU per step (configs[1]: 64)")
-    ap.add_argument("--beam", type=int, default=1)
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
+    ap.add_argument("--pages", type=int, default=0, help="pages per GPU per step (strong-scaling configs: pages per step in total)")
+    ap.add_argument("--beam", type=int, default=0)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--crop-chunk", type=int, default=16384, help="max crops per decode batch (results do not depend on it)")
+    ap.add_argument("--no-second-dtype", action="store_true", help="skip the short second-dtype pass (the `bf16` / `fp16` sub-object)")
+    ap.add_argument("--crop-chunk", type=int, default=0, help="max crops per decode batch (results do not depend on it)")
     ap.add_argument("--encode-chunk", type=int, default=2048, help="crops per K9 + encoder pass inside a decode batch")
+    ap.add_argument("--ref-lines", type=int, default=2, help="reference arm: text lines of one page per step (bounded sample)")
+    ap.add_argument("--full-pages", action="store_true", help="reference arm: SURVEY 8d protocol (1 warm-up + 3 timed full pages)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------- inputs
-def make_pages(indices):
+def make_page(cfg, i):
     from synthetic import pages as synth
+    if cfg["page"] == "dense":
+        return synth.dense_page(i)
+    if cfg["page"] == "4096":
+        return synth.synth_page(i, height=4096, width=4096)
+    return synth.synth_page(i)
+
+
+def make_pages(cfg, indices):
     pages, words = [], 0
     for i in indices:
-        p, w = synth.synth_page(i)
+        p, w = make_page(cfg, i)
         pages.append(p)
         words += w
     return np.stack(pages), words
 
 
-def make_weights(dtype):
+def make_weights(cfg, dtype):
     """Seeded synthetic weights shared by both arms (synthetic/weights.py — data generators, not oracle code):
-    glyph-path CRAFT (text-like maps) and TrOCR-base with the pre-computed calibrated EOS row (hypotheses end after
-    ~6 tokens).  dtype: the 16-bit type the weights are rounded to once (None = keep fp32).  -> (craft_sd, trocr_sd, cfg)"""
+    glyph-path CRAFT (text-like maps), TrOCR with the pre-computed calibrated EOS row (hypotheses end after ~6 tokens)
+    and, for the line mode, a RefineNet whose output head is scaled into the threshold range.  dtype: the 16-bit type
+    the weights are rounded to once (None = keep fp32).  -> (craft_sd, trocr_sd, trocr_cfg, refine_sd or None)"""
     from synthetic import weights as sw
     craft_sd = sw.glyph_craft_state(0)
-    cfg = sw.trocr_base()
-    tsd = sw.apply_eos_row(sw.synth_trocr_state(cfg, 0, round_to=dtype), "trocr_base_seed0", round_to=dtype)
-    return craft_sd, tsd, cfg
+    tcfg = sw.trocr_base() if cfg["model"] == "base" else sw.trocr_large()
+    tsd = sw.apply_eos_row(sw.synth_trocr_state(tcfg, 0, round_to=dtype), f"trocr_{cfg['model']}_seed0", round_to=dtype)
+    rsd = sw.synth_refine_state(2, round_to=dtype, out_gain=6.0, out_bias=0.3) if cfg["refiner"] else None
+    return craft_sd, tsd, tcfg, rsd
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def workload(cfg, args, world, pages_step, extra=None):
+    w = {"workload": f"{cfg['name']}: {cfg['what']}", "pages_per_step": pages_step, "beam": args.beam or cfg["beam"],
+         "max_len_b": MAX_LEN_B, "trocr": cfg["model"], "psm": cfg["preset"], "line_refiner": cfg["refiner"],
+         "weights": "seeded synthetic (glyph-path CRAFT, EOS-calibrated TrOCR)", "parallelism": f"dp{world}"}
+    w.update(extra or {})
+    return w
 
 
 # ----------------------------------------------------------------------------------------------------- clocks
@@ -106,103 +163,179 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(page, craft_sd, tsd, cfg, beam, strip_rows=1650, n_crops=24):
-    """(The only place bench.py executes oracle/ code.)  One bounded sample of the reference's CPU path on one page: K1 + CRAFT.forward + getDetBoxes + crop/resample on a
-    horizontal strip of `strip_rows` page rows, TrOCR (encoder + search) on `n_crops` of the strip's crops, both
-    extrapolated to the full page.  Returns (seconds per page, crops per page estimate, detail dict)."""
-    from oracle import craft_net, craft_post, resample, trocr
-    ph = page.shape[0]
-    strip = np.ascontiguousarray(page[150:150 + strip_rows])
+# (The only place bench.py executes oracle/ code: the CPU port of the reference path, timed as the baseline.)
+def _debug_writes(strip, frags, y, out_dir):
+    """The reference's unconditional debug I/O on the critical path (SURVEY 8d variant i): the float canvas PNG
+    (craft_box_processor.py:100), three score-map PNGs (craft_utils.py:40-43), one JPEG per crop (:533-535), the overlay
+    PNG + JPEG and the stacked PNG (:540-550).  Written like the reference does, to a scratch directory."""
+    import cv2
+    os.makedirs(out_dir, exist_ok=True)
     t0 = time.perf_counter()
-    x, ratio = resample.craft_input(strip)
+    cv2.imwrite(os.path.join(out_dir, "image.png"), strip)
+    for k in range(3):
+        m = (np.clip(y[0, ..., min(k, 1)].numpy(), 0, 1) * 255).astype(np.uint8)
+        cv2.imwrite(os.path.join(out_dir, f"map_{k}.png"), m)
+    for i, f in enumerate(frags):
+        cv2.imwrite(os.path.join(out_dir, f"0_{i}.jpg"), f)
+    cv2.imwrite(os.path.join(out_dir, "txt_overlay.png"), strip)
+    cv2.imwrite(os.path.join(out_dir, "txt_overlay.jpg"), strip, [cv2.IMWRITE_JPEG_QUALITY, 100])
+    cv2.imwrite(os.path.join(out_dir, "stacked.png"), np.hstack((strip, strip)))
+    return time.perf_counter() - t0
+
+
+def cpu_reference_pass(image, craft_sd, tsd, tcfg, cfg, beam, debug_dir=None, canvas=None):
+    """The reference's CPU path on `image` (a page or a strip of one), ALL of its crops recognised: K1 + CRAFT.forward +
+    getDetBoxes + adjust + rects + crops (+ line merge in LINE mode) + PIL resample + TrOCR encoder + search + result
+    assembly.  `canvas`: canvas_size of resize_aspect_ratio — a strip of a page is resized with the PAGE's ratio, not its
+    own.  Returns (seconds, crops, detail)."""
+    from oracle import craft_net, craft_post, lines as olines, resample, trocr
+    from marie_icr_b200.pipeline import PSM_PRESETS
+    tt, lt, low = PSM_PRESETS[cfg["preset"]]
+    t0 = time.perf_counter()
+    x, ratio = resample.craft_input(image, canvas_size=canvas)
     xin = torch.from_numpy(x).permute(2, 0, 1)[None]
     with torch.no_grad():
         y, _ = craft_net.craft_forward(craft_sd, xin)
     t1 = time.perf_counter()
-    det, _, _ = craft_post.det_boxes_cv(y[0, ..., 0].numpy(), y[0, ..., 1].numpy(), 0.7, 0.45, 0.3)
+    det, _, _ = craft_post.det_boxes_cv(y[0, ..., 0].numpy(), y[0, ..., 1].numpy(), tt, lt, low)
     adj = craft_post.adjust_result_coordinates([b.copy() for b in det], 1 / ratio, 1 / ratio)
-    rects = craft_post.boxes_to_rects(adj, strip.shape[0], strip.shape[1])
-    frags = [craft_post.crop_rect(strip, r) for r in rects]
+    rects = craft_post.boxes_to_rects(adj, image.shape[0], image.shape[1])
+    frags = [craft_post.crop_rect(image, r) for r in rects]
+    if cfg["preset"] == "line" and rects:
+        olines.line_merge([list(map(int, r)) for r in rects])
     t2 = time.perf_counter()
-    sample = frags[:n_crops] if frags else []
-    if sample:
-        chw = torch.stack([torch.from_numpy(resample.fragment_to_input(f)) for f in sample])
+    n = len(frags)
+    for i0 in range(0, n, 64):                                   # batchify (trocr_ocr_processor.py:318)
+        chw = torch.stack([torch.from_numpy(resample.fragment_to_input(f)) for f in frags[i0:i0 + 64]])
         with torch.no_grad():
-            trocr.recognize(tsd, cfg, chw, beam=beam, max_len_b=MAX_LEN_B)
+            trocr.recognize(tsd, tcfg, chw, beam=beam, max_len_b=MAX_LEN_B)
     t3 = time.perf_counter()
-    scale = ph / strip_rows
-    crops_page = len(frags) * scale
-    per_crop = (t3 - t2) / max(len(sample), 1)
-    sec_page = (t1 - t0) * scale + (t2 - t1) * scale + per_crop * crops_page
-    return sec_page, crops_page, dict(craft_s=(t1 - t0) * scale, post_crop_s=(t2 - t1) * scale, trocr_s_per_crop=per_crop)
+    writes = _debug_writes(image, frags, y, debug_dir) if debug_dir else None
+    return t3 - t0, n, dict(craft_s=t1 - t0, post_crop_s=t2 - t1, trocr_s=t3 - t2, debug_writes_s=writes)
+
+
+def reference_strip(cfg, page, lines):
+    """`lines` text lines of a synthetic page: rows [first baseline - 50, + lines * pitch) and the page fraction they stand for."""
+    pitch = 52 if cfg["page"] == "dense" else 70
+    first = 190                                              # synthetic/pages.py: margin 150 + 40
+    total_lines = len(range(first, page.shape[0] - 150, pitch))
+    lines = max(1, min(lines, total_lines))
+    y0 = first - 50
+    strip = np.ascontiguousarray(page[y0:y0 + lines * pitch])
+    # the page is resized by canvas / max(H, W) with canvas = W (craft_box_processor.py:96-99); the strip keeps that ratio
+    ph, pw = page.shape[:2]
+    canvas = int(round(max(strip.shape[:2]) * min(1.0, pw / max(ph, pw))))
+    return strip, lines / total_lines, lines, total_lines, canvas
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
-    pages, _ = make_pages([0])
-    craft_sd, tsd, cfg = make_weights(None)
-    secs, crops = [], []
-    for i in range(args.warmup + args.steps):
-        s, c, detail = cpu_reference_step(pages[0], craft_sd, tsd, cfg, args.beam)
-        if i >= args.warmup:
-            secs.append(s)
-            crops.append(c)
-    sec_page = float(np.mean(secs))
-    value = 1.0 / sec_page
-    sample = ("per step: K1+CRAFT.forward+getDetBoxes+crops on a 1650-row strip (half) of one letter page, TrOCR-base (fp32) on 24 "
-              "of its crops; extrapolated x2 rows and to all crops of the page")
+    cfg = CONFIGS[args.config]
+    beam = args.beam or cfg["beam"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    craft_sd, tsd, tcfg, _ = make_weights(cfg, None)
+    page, _ = make_page(cfg, 0)
+    pages_ours = args.pages or cfg["pages"]
+    pages_step_ours = pages_ours if cfg["scaling"] == "strong" else pages_ours * world
+    if args.full_pages:
+        # SURVEY 8d CPU protocol: one warm-up page, then >= 3 timed full pages with ALL their crops; variant (ii) = debug
+        # writes stubbed (the timed path), variant (i) = plus the reference's unconditional debug image writes, timed on
+        # the same pages right after the pass.
+        import tempfile
+        secs, crops, writes, details = [], [], [], []
+        with tempfile.TemporaryDirectory() as d:
+            for i in range(1 + max(3, args.steps)):
+                p, _ = make_page(cfg, i)
+                s, c, det = cpu_reference_pass(p, craft_sd, tsd, tcfg, cfg, beam, debug_dir=d)
+                print(f"[reference full page {i}] {s:.1f} s, {c} crops, {det}", file=sys.stderr, flush=True)
+                if i >= 1:
+                    secs.append(s)
+                    crops.append(c)
+                    writes.append(det["debug_writes_s"])
+                    details.append(det)
+        sec_page, frac, sample = float(np.mean(secs)), 1.0, (
+            f"SURVEY 8d protocol: 1 warm-up + {len(secs)} timed FULL pages (all crops, fp32, {cores} threads); "
+            "value = variant (ii) debug writes stubbed; variant (i) in cpu_baseline.with_debug_writes")
+        extra = {"with_debug_writes": {"value": 1.0 / float(np.mean(np.add(secs, writes))), "unit": "pages/s",
+                                       "debug_writes_s_per_page": float(np.mean(writes))},
+                 "per_page_s": secs, "detail": details[-1]}
+        steps, warm = len(secs), 1
+    else:
+        strip, frac, nl, tl, canvas = reference_strip(cfg, page, args.ref_lines)
+        secs, crops = [], []
+        for i in range(args.warmup + args.steps):
+            s, c, detail = cpu_reference_pass(strip, craft_sd, tsd, tcfg, cfg, beam, canvas=canvas)
+            if i >= args.warmup:
+                secs.append(s)
+                crops.append(c)
+        sec_page = float(np.mean(secs))
+        sample = (f"per step: {nl} of the {tl} text lines of one page ({strip.shape[0]} rows x {strip.shape[1]} px) through the whole "
+                  f"CPU path, ALL {int(np.mean(crops))} crops of the strip recognised (fp32, {cores} threads); ms_per_step is the measured "
+                  f"time of that sample, value = {frac:.4f} page / step time (no per-stage extrapolation)")
+        extra = {"detail": detail}
+        steps, warm = args.steps, args.warmup
+    value = frac / sec_page
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec_page * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "pages/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec_page * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 64 synthetic letter pages/GPU/step, CRAFT detect + TrOCR-base greedy ICR",
-                   "pages_per_step": 1, "beam": args.beam, "crops_per_page": float(np.mean(crops))},
-        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
-                         "detail": detail},
+        "config": workload(cfg, args, world, pages_step_ours, {"reference_pages_per_step": frac}),
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": cores, "cpu": cpu_model(), "kind": "port", "sample": sample,
+                         "what": "CPU port (oracle/) of the reference algorithm; the reference's own GPU path needs fairseq/timm",
+                         **extra},
         "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "crops_per_s": value * float(np.mean(crops)),
+        "crops_per_s": float(np.mean(crops)) / sec_page,
     }
     emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
+def build_arm(args, cfg, ctx, local_rank, dtype_name):
+    """Loads the weights in `dtype_name` and returns (pipeline, engine)."""
+    from marie_icr_b200 import ops, weights
+    from marie_icr_b200.boxes import BoxProcessorCraftB200
+    from marie_icr_b200.bpe import SyntheticDetokenizer
+    from marie_icr_b200.document import TrOcrProcessorB200
+    from marie_icr_b200.engine import OcrEngineB200
+    from marie_icr_b200.pipeline import PagePipeline
+    ctx.set_dtype(dtype_name)
+    dt = ctx.torch_dtype
+    beam = args.beam or cfg["beam"]
+    craft_sd, tsd, tcfg, rsd = make_weights(cfg, dt)
+    # beam >= 2 keeps a cross-attention K/V cache of 28 MB per crop (12 layers x 577 x 2 x 1024 x 2 B): bound the decode batch
+    crop_chunk = args.crop_chunk or (16384 if beam == 1 else 2048)
+    micro = 8 if cfg["page"] != "4096" else 2
+    pipe = PagePipeline(device=local_rank, craft_blob=weights.pack_craft(craft_sd, dt), trocr_blob=weights.pack_trocr(tsd, tcfg, dt),
+                        micro_batch=micro, crop_chunk=crop_chunk, encode_chunk=args.encode_chunk)
+    box = BoxProcessorCraftB200(pipeline=pipe, device=local_rank, line_refiner_state_dict=rsd)
+    icr = TrOcrProcessorB200(pipeline=pipe, device=local_rank, beam=beam, max_len_b=MAX_LEN_B, detokenizer=SyntheticDetokenizer())
+    return pipe, OcrEngineB200(box_processor=box, default_ocr_processor=icr)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from marie_icr_b200 import weights
+    from marie_icr_b200 import ops as _ops
     from marie_icr_b200._lib import Context
     from marie_icr_b200.dist import gather_records, shard_indices
-    from marie_icr_b200.pipeline import PSM_PRESETS, RECORD_HEAD, PagePipeline
+    from marie_icr_b200.pipeline import PSM_PRESETS
+    from marie_icr_b200.plugin_api import PSMode
 
+    cfg = CONFIGS[args.config]
+    beam = args.beam or cfg["beam"]
     torch.cuda.set_device(local_rank)
     ctx = Context.get(local_rank)
-    ctx.set_dtype(args.dtype)
-    dt = ctx.torch_dtype
-    # page i of the stream -> rank i mod world; every rank holds `pages` pages per step (weak scaling)
-    idx = shard_indices(args.pages * world, rank, world)
-    pages_np, _ = make_pages(idx)
-    craft_sd, tsd, cfg = make_weights(dt)
-    pipe = PagePipeline(device=local_rank, craft_blob=weights.pack_craft(craft_sd, dt),
-                        trocr_blob=weights.pack_trocr(tsd, cfg, dt), micro_batch=8, crop_chunk=args.crop_chunk, encode_chunk=args.encode_chunk)
+    # page i of the stream -> rank i mod world.  weak: every rank holds `pages` pages per step; strong: `pages` in total.
+    pages_arg = args.pages or cfg["pages"]
+    pages_step = pages_arg if cfg["scaling"] == "strong" else pages_arg * world
+    idx = shard_indices(pages_step, rank, world)
+    pages_np, _ = make_pages(cfg, idx)
+    frames = [pages_np[i] for i in range(pages_np.shape[0])]
     pages_host = torch.from_numpy(pages_np).pin_memory()
     pages_dev = pages_host.cuda(non_blocking=True)
     page_ids = torch.tensor(idx, dtype=torch.int32, device="cuda")
-    kw = dict(preset=PSM_PRESETS["sparse"], beam=args.beam, max_len_b=MAX_LEN_B, out_ld=OUT_LD)
-
-    def step_device():
-        rec, counts = pipe.run_device(pages_dev, **kw)
-        if rec.shape[0]:
-            rec[:, 0] = page_ids[rec[:, 0].long()]          # local page slot -> global page id
-        return gather_records(rec) if world > 1 else rec, counts
-
-    def step_host():
-        dev = pages_host.cuda(non_blocking=True)
-        rec, counts = pipe.run_device(dev, **kw)
-        if rec.shape[0]:
-            rec[:, 0] = page_ids[rec[:, 0].long()]
-        rec = gather_records(rec) if world > 1 else rec
-        return rec.cpu(), counts
+    psm = {"sparse": PSMode.SPARSE, "line": PSMode.LINE}[cfg["preset"]]
 
     def barrier():
         if world > 1:
@@ -210,6 +343,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """-> (max-over-ranks ms for `steps` calls, this rank's own ms, last result)"""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -217,42 +351,89 @@ def run_ours(args, rank, world, local_rank):
             out = fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        own = e0.elapsed_time(e1)
+        ms = torch.tensor([own], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out
+        return float(ms.item()), own, out
 
-    for _ in range(args.warmup):
-        step_device()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launches
-    from marie_icr_b200 import ops as _ops
-    st0 = _ops.trocr_stats(local_rank)
-    ctx.profile(True)
-    pipe.timer.reset(True)
-    ms, (rec, counts) = timed(step_device, args.steps)
-    stages = pipe.timer.collect()
-    pipe.timer.reset(False)
-    prof = ctx.profile_read()
-    ctx.profile(False)
-    launches = ctx.launches - launches0
-    st1 = _ops.trocr_stats(local_rank)
-    dec_steps = (st1["decode_steps"] - st0["decode_steps"]) / max(1, st1["decode_calls"] - st0["decode_calls"])
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, (rec_h, _) = timed(step_host, max(1, min(args.steps, 2)))
-    e2e_steps = max(1, min(args.steps, 2))
+    def arm(dtype_name, steps, warmup, full):
+        pipe, engine = build_arm(args, cfg, ctx, local_rank, dtype_name)
+        engine.record_tokens = None
+        kw = dict(preset=PSM_PRESETS[cfg["preset"]], beam=beam, max_len_b=MAX_LEN_B, out_ld=OUT_LD, line_refiner=cfg["refiner"])
+        gather_ms = []
 
-    n_crops_local = int(sum(counts))
+        def step_device():
+            rec, counts = pipe.run_device(pages_dev, **kw)
+            if rec.shape[0]:
+                rec[:, 0] = page_ids[rec[:, 0].long()]          # local page slot -> global page id
+            if world > 1:
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                rec = gather_records(rec)
+                g1.record()
+                gather_ms.append((g0, g1))
+            return rec, counts
+
+        def step_engine():
+            return engine.extract(frames, pms_mode=psm)
+
+        for _ in range(warmup):
+            step_device()
+        res = {}
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and full:
+            sampler.start()
+        gather_ms.clear()
+        launches0 = ctx.launches
+        st0 = _ops.trocr_stats(local_rank)
+        if full:
+            ctx.profile(True)
+            pipe.timer.reset(True)
+        ms, own_ms, (rec, counts) = timed(step_device, steps)
+        if full:
+            res["stages"] = pipe.timer.collect()
+            pipe.timer.reset(False)
+            res["prof"] = ctx.profile_read()
+            ctx.profile(False)
+        res["launches"] = ctx.launches - launches0
+        st1 = _ops.trocr_stats(local_rank)
+        res["dec_steps"] = (st1["decode_steps"] - st0["decode_steps"]) / max(1, st1["decode_calls"] - st0["decode_calls"])
+        res["clocks"] = sampler.stop() if (rank == 0 and full) else None
+        torch.cuda.synchronize()
+        res["gather_ms"] = float(np.mean([a.elapsed_time(b) for a, b in gather_ms])) if gather_ms else 0.0
+        res["ms"], res["own_ms"], res["rec"], res["counts"] = ms, own_ms, rec, counts
+        res["truncated"] = int((rec[:, 6] > OUT_LD).sum().item()) if rec.shape[0] else 0
+        # end to end through the plugin call, host ndarrays in, page records out
+        step_engine()                                           # staging buffer / allocator warm-up
+        e2e_steps = max(1, min(steps, 2))
+        t_host0 = time.perf_counter()
+        ms_e2e, _, pages_out = timed(step_engine, e2e_steps)
+        res["e2e_wall_ms"] = (time.perf_counter() - t_host0) * 1e3 / e2e_steps
+        res["ms_e2e"], res["e2e_steps"] = ms_e2e, e2e_steps
+        res["words_out"] = sum(len(p["words"]) for p in pages_out)
+        res["d2h"] = int(sum(counts)) * (8 + MAX_LEN_B + 1) * 4
+        return res
+
+    r = arm(args.dtype, args.steps, args.warmup, True)
+    second = None
+    if not args.no_second_dtype:
+        other = "bf16" if args.dtype == "fp16" else "fp16"
+        r2 = arm(other, max(1, min(args.steps, 2)), 1, False)
+        second = (other, r2)
+
+    n_crops_local = int(sum(r["counts"]))
     tot = torch.tensor([n_crops_local], device="cuda", dtype=torch.int64)
+    per_rank = torch.tensor([r["own_ms"] / args.steps, r["gather_ms"]], device="cuda", dtype=torch.float64)
+    per_rank_all = [per_rank]
     if world > 1:
         dist.all_reduce(tot)
+        per_rank_all = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(per_rank_all, per_rank)
     crops_step = int(tot.item())
-    pages_step = args.pages * world
-    sec_step = ms / 1e3 / args.steps
+    sec_step = r["ms"] / 1e3 / args.steps
     value = pages_step / sec_step
-    sec_e2e = ms_e2e / 1e3 / e2e_steps
+    sec_e2e = r["ms_e2e"] / 1e3 / r["e2e_steps"]
     if rank != 0:
         return
     peaks = {}
@@ -263,55 +444,70 @@ def run_ours(args, rank, world, local_rank):
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "MEASURED_PEAKS.json (sustained)" if peaks else "fallback"
+    peak_src = "MEASURED_PEAKS.json (sustained)" if peaks else "fallback (B200_PROFILING.md)"
+    prof = r["prof"]
     achieved = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
-    # DRAM traffic of the dominant tap-GEMM launch (encoder fc1) from the committed ncu --set full capture
     traffic, traffic_detail = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_tap_gemm_traffic.json")) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_per_launch"]
-        traffic_detail = {"unit": "bytes per launch (dram read + write)", "launch": tj["kernel"],
-                          "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
-                          "source": "profiles/r01_tap_gemm_traffic.json"}
-    except Exception:
-        pass
-    st_ms, st_units = stages["ms"], stages["units"]
+    for name in ("r02_tap_gemm_traffic.json", "r01_tap_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_detail = {"unit": "bytes per launch (dram read + write)", "launch": tj["kernel"],
+                              "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"], "source": "profiles/" + name}
+            break
+        except Exception:
+            continue
+    st_ms, st_units = r["stages"]["ms"], r["stages"]["units"]
     per_step = {k: v / args.steps for k, v in st_ms.items()}
-    # algorithmic bytes per unit: K1 55.7 MB/page, K5-K7 20.3 MB/page, K9 ~0.9 MB/crop
+    # algorithmic bytes per unit: K1 = H*W*3 + 3*H32*W32*2, K5-K7 = 16 B / heat-map px, K9 ~ 0.9 MB / crop
+    from marie_icr_b200.ops import craft_canvas_dims
+    ph, pw = pages_np.shape[1:3]
+    _, _, oh, ow, _ = craft_canvas_dims(ph, pw)
     hbm = {}
-    for name, bytes_unit in (("k1_preprocess", 55.72e6), ("k5_7_post", 20.32e6), ("k9_crops", 0.90e6)):
+    for name, bytes_unit in (("k1_preprocess", ph * pw * 3 + 3 * oh * ow * 2), ("k5_7_post", 16 * (oh // 2) * (ow // 2)),
+                             ("k9_crops", 0.90e6)):
         if st_ms.get(name):
             gbs = bytes_unit * st_units[name] / (st_ms[name] * 1e-3) / 1e9
-            hbm[name] = {"achieved_gbs": gbs, "frac": gbs / hbm_peak}
+            hbm[name] = {"achieved_gbs": gbs, "frac": gbs / hbm_peak, "algorithmic_bytes_per_unit": bytes_unit}
     line = {
-        "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": cfg["metric"], "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "configs[1]: 64 synthetic letter pages/GPU/step, CRAFT detect + TrOCR-base greedy ICR",
-                   "pages_per_step": pages_step, "page": "2550x3300x3 u8", "crops_per_step": crops_step, "beam": args.beam,
-                   "max_len_b": MAX_LEN_B, "trocr": "base (ViT 768/12 + decoder 1024/12, vocab 50265)",
-                   "weights": "seeded synthetic (glyph-path CRAFT, EOS-calibrated TrOCR)", "parallelism": f"dp{world}",
-                   "l2": "inputs larger than L2 (1.6 GB of pages per step)", "decoder_steps_per_chunk": dec_steps},
+        "config": workload(cfg, args, world, pages_step, {
+            "page": f"{pw}x{ph}x3 u8", "crops_per_step": crops_step, "decoder_steps_per_chunk": r["dec_steps"],
+            "l2": f"inputs larger than L2 ({pages_np.nbytes / 1e9:.2f} GB of pages per GPU per step)",
+            "truncated_records": r["truncated"]}),
         "crops_per_s": crops_step / sec_step,
         "e2e": {"value": pages_step / sec_e2e, "unit": "pages/s", "h2d_bytes_per_step": int(pages_host.numel()),
-                "d2h_bytes_per_step": int(rec_h.numel() * 4 / max(world, 1)), "crops_per_s": crops_step / sec_e2e},
-        "gpu_launches": int(launches),
+                "d2h_bytes_per_step": r["d2h"], "crops_per_s": crops_step / sec_e2e, "ms_per_step": sec_e2e * 1e3,
+                "host_wall_ms_per_step": r["e2e_wall_ms"], "words_out_rank0": r["words_out"],
+                "api": "OcrEngineB200.extract(list of host ndarrays) -> [{meta, words, lines}] (detokenise + assemble included)"},
+        "gpu_launches": int(r["launches"]),
         "roofline": {"kernel": "tap_gemm_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
                      "traffic_detail": traffic_detail, "peak_source": peak_src, "launches": prof["launches"],
-                     "share_of_step": prof["ms"] / ms if ms else None},
+                     "share_of_step": prof["ms"] / r["own_ms"] if r["own_ms"] else None},
         "stages_ms_per_step": per_step, "hbm_stages": hbm,
-        "clocks": clocks,
+        "per_rank": {"step_ms": [float(t[0]) for t in per_rank_all], "gather_ms": [float(t[1]) for t in per_rank_all]},
+        "clocks": r["clocks"],
     }
+    if second is not None:
+        other, r2 = second
+        s2 = r2["ms"] / 1e3 / max(1, min(args.steps, 2))
+        line[other] = {"value": pages_step / s2, "unit": "pages/s", "ms_per_step": s2 * 1e3, "steps": max(1, min(args.steps, 2)),
+                       "warmup": 1, "e2e": pages_step / (r2["ms_e2e"] / 1e3 / r2["e2e_steps"]),
+                       "note": f"same kernels, same step with the 16-bit element type switched to {other} (weights re-rounded)"}
     if not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
-        craft32, tsd32, cfg32 = make_weights(None)
-        t0 = time.perf_counter()
-        s, c, detail = cpu_reference_step(pages_np[0], craft32, tsd32, cfg32, args.beam)
-        line["cpu_baseline"] = {"value": 1.0 / s, "unit": "pages/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "one pass: K1+CRAFT+getDetBoxes+crops on a 1650-row strip (half) of one page, TrOCR-base "
-                                          "fp32 on 24 crops, extrapolated to the page (%.1f s measured)" % (time.perf_counter() - t0),
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        craft32, tsd32, tcfg32, _ = make_weights(cfg, None)
+        strip, frac, nl, tl, canvas = reference_strip(cfg, pages_np[0], args.ref_lines)
+        cpu_reference_pass(strip[:, :640].copy(), craft32, tsd32, tcfg32, cfg, beam, canvas=canvas)   # thread-pool warm-up
+        s, c, detail = cpu_reference_pass(strip, craft32, tsd32, tcfg32, cfg, beam, canvas=canvas)
+        line["cpu_baseline"] = {"value": frac / s, "unit": "pages/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
+                                "sample": f"one pass over {nl} of the {tl} text lines of one page ({c} crops, all recognised, fp32): "
+                                          f"{s:.1f} s measured = {frac:.4f} page",
                                 "detail": detail}
     emit(line)
 

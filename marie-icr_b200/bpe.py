@@ -15,16 +15,20 @@ SPECIALS = (0, 1, 2, 3)   # <s>, <pad>, </s>, <unk>
 class SyntheticDetokenizer:
     """id -> 1-3 letters; ids whose slot is 0 mod 7 start a new word (leading space), like GPT-2's 'Ġ' tokens."""
 
-    def decode(self, ids):
-        out = []
-        for t in ids:
-            t = int(t)
-            if t in SPECIALS:
-                continue
+    def __init__(self):
+        self._piece = {}
+
+    def piece(self, t):
+        p = self._piece.get(t)
+        if p is None:
             k = t - 4
-            s = chr(97 + k % 26) + (chr(97 + (k // 26) % 26) if k % 3 else "") + (chr(97 + (k // 676) % 26) if k % 5 == 0 else "")
-            out.append((" " if k % 7 == 0 and out else "") + s)
-        return "".join(out)
+            p = ((" " if k % 7 == 0 else "") + chr(97 + k % 26) + (chr(97 + (k // 26) % 26) if k % 3 else "")
+                 + (chr(97 + (k // 676) % 26) if k % 5 == 0 else ""))
+            self._piece[t] = p
+        return p
+
+    def decode(self, ids):
+        return "".join([self.piece(int(t)) for t in ids if int(t) not in SPECIALS]).lstrip(" ")
 
 
 def _bytes_to_unicode():

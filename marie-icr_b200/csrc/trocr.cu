@@ -59,6 +59,7 @@ struct TrocrModel {
     // self-attention K / V caches of the decode in flight: their own allocation, sized for `kv_cap` steps and grown on demand
     // (a cache for max_len = 200 steps is 81 GB at 8192 rows; hypotheses are a handful of tokens long)
     void* kv_arena = nullptr; size_t kv_bytes = 0;
+    void* rec_enc = nullptr; size_t rec_enc_bytes = 0;      // mb_trocr_recognize: encoder states of one chunk (kept between calls)
     unsigned long long decode_calls = 0, decode_steps = 0, decode_rows = 0;
     bool ln_fold = true;          // encoder LayerNorms folded into qkv / fc1 when the blob carries the folded tensors (MB_LNFOLD=0 disables)
 };
@@ -1210,6 +1211,7 @@ void mb_free_trocr(mb_ctx* ctx) {
     ctx->trocr->blob.release();
     if (ctx->trocr->arena) cudaFree(ctx->trocr->arena);
     if (ctx->trocr->kv_arena) cudaFree(ctx->trocr->kv_arena);
+    if (ctx->trocr->rec_enc) cudaFree(ctx->trocr->rec_enc);
     delete ctx->trocr;
     ctx->trocr = nullptr;
 }
@@ -1435,12 +1437,18 @@ extern "C" int mb_trocr_recognize(mb_ctx* ctx, const void* patches_dev, int n, i
     MB_REQUIRE(ctx, n > 0 && beam >= 1 && beam <= MAX_BEAM, "trocr_recognize: bad arguments");
     if (chunk <= 0) chunk = 512;
     const int D = m->enc_dim, T = m->tokens;
-    void* enc_out = nullptr;
     const int cmax = n < chunk ? n : chunk;
-    if (cudaMalloc(&enc_out, (size_t)cmax * T * D * 2) != cudaSuccess) {
-        cudaGetLastError();
-        return mb_set_err(ctx, MB_ERR_OOM, "trocr_recognize: encoder output buffer");
+    const size_t need = (size_t)cmax * T * D * 2;
+    if (need > m->rec_enc_bytes) {                       // grown on demand, never per call
+        if (m->rec_enc) cudaFree(m->rec_enc);
+        m->rec_enc = nullptr; m->rec_enc_bytes = 0;
+        if (cudaMalloc(&m->rec_enc, need) != cudaSuccess) {
+            cudaGetLastError();
+            return mb_set_err(ctx, MB_ERR_OOM, "trocr_recognize: encoder output buffer");
+        }
+        m->rec_enc_bytes = need;
     }
+    void* enc_out = m->rec_enc;
     int rc = 0;
     for (int i0 = 0; i0 < n && !rc; i0 += chunk) {
         const int c = n - i0 < chunk ? n - i0 : chunk;
@@ -1449,6 +1457,5 @@ extern "C" int mb_trocr_recognize(mb_ctx* ctx, const void* patches_dev, int n, i
             rc = mb_trocr_decode(ctx, enc_out, c, beam, max_len_b, tokens_out_dev + (size_t)i0 * out_ld, out_ld,
                                  lengths_dev + i0, scores_dev + i0, nullptr, stream);
     }
-    cudaFree(enc_out);
     return rc;
 }

@@ -49,15 +49,19 @@ class OcrEngineB200:
         regions = [] if regions is None else regions
         if isinstance(frames, np.ndarray) and frames.ndim == 3:
             frames = [frames]
+        batched = (not len(regions) and isinstance(self.box_processor, BoxProcessorCraftB200)
+                   and isinstance(self.icr_processor, TrOcrProcessorB200)
+                   and self.box_processor.pipeline is self.icr_processor.pipeline
+                   and pms_mode in (PSMode.SPARSE, PSMode.LINE, PSMode.MULTI_LINE)
+                   and all(isinstance(f, np.ndarray) and f.ndim == 3 and f.dtype == np.uint8 for f in frames)
+                   and len({f.shape for f in frames}) == 1 and not kwargs.get("crop_to_content", False))
+        if batched:
+            # the batched path copies the caller's frames once, straight into its pinned staging buffer (the deep copy of
+            # ocr_engine.py:118 and the H2D source in one) and never writes to them
+            return self._extract_batched(frames, pms_mode, coordinate_format)
         ro_frames = copy_frames(frames)
         if len(regions):
             return self._extract_regions(ro_frames, queue_id, hash_frames_fast(ro_frames), pms_mode, regions)
-        batched = (isinstance(self.box_processor, BoxProcessorCraftB200) and isinstance(self.icr_processor, TrOcrProcessorB200)
-                   and self.box_processor.pipeline is self.icr_processor.pipeline
-                   and pms_mode in (PSMode.SPARSE, PSMode.LINE, PSMode.MULTI_LINE)
-                   and len({f.shape for f in ro_frames}) == 1 and not kwargs.get("crop_to_content", False))
-        if batched:
-            return self._extract_batched(ro_frames, pms_mode, coordinate_format)
         return self._extract_pagewise(ro_frames, queue_id, "0", pms_mode, coordinate_format,
                                       crop=bool(kwargs.get("crop_to_content", False)))
 
@@ -80,12 +84,13 @@ class OcrEngineB200:
         return results
 
     def _extract_batched(self, frames, pms_mode, coordinate_format):
-        import torch
         pipe = self.box_processor.pipeline
-        pages = torch.from_numpy(np.stack(frames)).pin_memory()
         icr = self.icr_processor
-        rec, counts = pipe.run_host(pages, preset=PSM_PRESETS[pms_mode.value], beam=icr.beam, max_len_b=icr.max_len_b,
-                                    out_ld=icr.max_len_b + 1)
+        refiner = bool(getattr(self.box_processor, "line_refiner", False))
+        line_boxes = []
+        rec, counts = pipe.run_frames(frames, preset=PSM_PRESETS[pms_mode.value], beam=icr.beam, max_len_b=icr.max_len_b,
+                                      out_ld=getattr(self, "record_tokens", None) or icr.max_len_b + 1,
+                                      line_refiner=refiner, want_lines=line_boxes)
         words = records_to_words(rec, icr.detok)
         results, k = [], 0
         for i, img in enumerate(frames):
@@ -100,7 +105,7 @@ class OcrEngineB200:
                 lines = [w["line"] for w in page_words]
                 res = [{"confidence": w["confidence"], "id": f"img-{j}", "text": w["text"]} for j, w in enumerate(page_words)]
                 result = assemble_result(meta, boxes, lines, res)
-            self._finish(result, i, lines, [], coordinate_format)
+            self._finish(result, i, lines, line_boxes[i] if refiner else [], coordinate_format)
             results.append(result)
         return results
 

@@ -91,9 +91,11 @@ class PagePipeline:
         self.has_trocr = True
 
     # ------------------------------------------------------------------------------------------ detection
-    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False, line_refiner=False):
+    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False, line_refiner=False, ready=None):
         """pages_dev [n,H,W,3] u8 (BGR) on the device -> dict with per-crop `rects` [N,4] i32 (x,y,w,h), `page_idx`
-        [N] i32, `boxes` [N,4,2] f32 (page coordinates, adjustResultCoordinates output), `counts` (host list)."""
+        [N] i32, `boxes` [N,4,2] f32 (page coordinates, adjustResultCoordinates output), `counts` (host list).
+        ready(i0, i1): optional hook called before pages [i0, i1) are first read (run_frames: the compute stream waits
+        there for the copy stream's H2D of that micro-batch)."""
         if not self.has_craft:
             raise RuntimeError("CRAFT weights are not loaded")
         n, ph, pw, _ = pages_dev.shape
@@ -105,6 +107,8 @@ class PagePipeline:
         for i0 in range(0, n, self.micro_batch):
             chunk = pages_dev[i0:i0 + self.micro_batch]
             m = chunk.shape[0]
+            if ready is not None:
+                ready(i0, i0 + m)
             t = self.timer.start()
             x, ratio = ops.page_preprocess(chunk)
             self.timer.stop("k1_preprocess", t, m)
@@ -202,10 +206,14 @@ class PagePipeline:
         return tokens, lengths, scores
 
     # ------------------------------------------------------------------------------------------ whole path
-    def run_device(self, pages_dev, preset=PSM_PRESETS["sparse"], beam=1, max_len_b=200, out_ld=32):
+    def run_device(self, pages_dev, preset=PSM_PRESETS["sparse"], beam=1, max_len_b=200, out_ld=32, line_refiner=False,
+                   ready=None, want_lines=None):
         """Pages already in HBM -> packed per-word records [N, RECORD_HEAD + out_ld] i32 on the device
-        (page, x, y, w, h, line=-1, length, score bits, tokens...) and the per-page counts (host)."""
-        det = self.detect(pages_dev, preset)
+        (page, x, y, w, h, line, length, score bits, tokens...) and the per-page counts (host).  line = -1
+        (find_line_number over an empty line list, as in the reference) unless `line_refiner` runs the refiner's line
+        branch (craft_box_processor.py:150-217): then the merged line boxes are appended per page to `want_lines` (a
+        list) and every word gets its line number (line_processor.py:15-45)."""
+        det = self.detect(pages_dev, preset, line_refiner=line_refiner, ready=ready)
         n = det["rects"].shape[0]
         rec = torch.empty((n, RECORD_HEAD + out_ld), dtype=torch.int32, device=pages_dev.device)
         if n:
@@ -213,10 +221,72 @@ class PagePipeline:
             rec[:, 0] = det["page_idx"]
             rec[:, 1:5] = det["rects"]
             rec[:, 5] = -1                       # find_line_number(lines_bboxes=[], box) == -1 (line_processor.py:21-45)
+            if line_refiner:
+                from . import lines as _lines
+                rects_h = det["rects"].cpu().numpy()
+                ids, k = np.full((n,), -1, np.int32), 0
+                for j, c in enumerate(det["counts"]):
+                    if c and len(det["lines"][j]):
+                        ids[k:k + c] = _lines.find_line_numbers(det["lines"][j], rects_h[k:k + c])
+                    k += c
+                rec[:, 5] = torch.from_numpy(ids).to(rec.device)
             rec[:, 6] = lengths
             rec[:, 7] = scores.view(torch.int32)
             rec[:, RECORD_HEAD:] = tokens
+        if want_lines is not None and line_refiner:
+            want_lines.extend(det["lines"])
         return rec, det["counts"]
+
+    def run_frames(self, frames, **kw):
+        """Host frames (list of equally sized [H,W,3] u8 BGR arrays — what OcrEngine.extract receives) -> records on the
+        host.  The frames are copied ONCE, into a pinned staging buffer kept by the pipeline (this is also the deep copy
+        the reference makes, ocr_engine.py:118,416-433), by a helper thread one micro-batch ahead; each micro-batch
+        goes to the device on a copy stream while the previous one is in K1 / CRAFT on the compute stream."""
+        import threading
+        n = len(frames)
+        shape = (n,) + tuple(frames[0].shape)
+        dev = torch.device("cuda", self.device)
+        numel = int(np.prod(shape))
+        if getattr(self, "_stage", None) is None or self._stage.numel() < numel:
+            self._stage = torch.empty((numel,), dtype=torch.uint8).pin_memory()
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        stage = self._stage[:numel].view(shape)
+        stage_np = stage.numpy()
+        pages_dev = torch.empty(shape, dtype=torch.uint8, device=dev)
+        mb = self.micro_batch
+        staged = [threading.Event() for _ in range(0, n, mb)]
+
+        def stager():
+            for k, i0 in enumerate(range(0, n, mb)):
+                for i in range(i0, min(i0 + mb, n)):
+                    np.copyto(stage_np[i], frames[i])
+                staged[k].set()
+
+        th = threading.Thread(target=stager, daemon=True)
+        th.start()
+        compute = torch.cuda.current_stream(dev)
+        copied = {}
+
+        def issue(k):
+            if k < len(staged) and k not in copied:
+                staged[k].wait()
+                i0 = k * mb
+                with torch.cuda.stream(self._copy_stream):
+                    pages_dev[i0:i0 + mb].copy_(stage[i0:i0 + mb], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                copied[k] = ev
+
+        def ready(i0, i1):
+            k = i0 // mb
+            issue(k)
+            issue(k + 1)                      # next micro-batch's H2D runs under this one's CRAFT
+            compute.wait_event(copied[k])
+
+        self._copy_stream.wait_stream(compute)           # pages_dev allocation ordering
+        rec, counts = self.run_device(pages_dev, ready=ready, **kw)
+        th.join()
+        return rec.cpu(), counts
 
     def run_host(self, pages_pinned, **kw):
         """Host pages ([n,H,W,3] u8, ideally pinned) -> records on the host; H2D and D2H inside."""
@@ -228,17 +298,27 @@ class PagePipeline:
 def records_to_words(rec, detok, page=None):
     """Host records -> list of dicts {page, box [x,y,w,h], line, text, confidence, tokens} in detector order.
     Text is upper-cased and the confidence is round(round(exp(score), 6), 4) as in
-    marie/document/trocr_ocr_processor.py:159-160,338-341."""
-    import math
+    marie/document/trocr_ocr_processor.py:159-160,338-341 (exp in float32 like torch.exp on the fp32 score).
+    A hypothesis longer than the record's token field (only possible with an explicit, small out_ld) is flagged
+    `truncated` instead of silently losing its tail."""
     rec = rec.numpy() if hasattr(rec, "numpy") else np.asarray(rec)
+    if page is not None:
+        rec = rec[rec[:, 0] == page]
+    n = rec.shape[0]
+    if n == 0:
+        return []
+    out_ld = rec.shape[1] - RECORD_HEAD
+    lens = rec[:, 6]
+    conf = np.exp(np.ascontiguousarray(rec[:, 7]).view(np.float32)).tolist()
+    head = rec[:, :RECORD_HEAD].tolist()
+    toks = rec[:, RECORD_HEAD:].tolist()
     out = []
-    for r in rec:
-        if page is not None and int(r[0]) != page:
-            continue
-        ln = int(r[6])
-        toks = [int(t) for t in r[RECORD_HEAD:RECORD_HEAD + ln]]
-        score = float(np.array([r[7]], dtype=np.int32).view(np.float32)[0])
-        conf = round(round(math.exp(score), 6), 4) if ln else 0.0
-        out.append(dict(page=int(r[0]), box=[int(v) for v in r[1:5]], line=int(r[5]), tokens=toks,
-                        text=detok.decode(toks).upper(), confidence=conf))
+    for h, t, c in zip(head, toks, conf):
+        ln = h[6]
+        t = t[:ln]
+        w = dict(page=h[0], box=h[1:5], line=h[5], tokens=t, text=detok.decode(t).upper(),
+                 confidence=round(round(c, 6), 4) if ln else 0.0)
+        if ln > out_ld:
+            w["truncated"] = True
+        out.append(w)
     return out

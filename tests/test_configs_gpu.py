@@ -73,7 +73,15 @@ def test_beam5_matches_oracle_tiny(cuda_ctx):
         if got == h[0]["tokens"].tolist():
             exact += 1
             assert abs(float(scores[i]) - h[0]["score"]) <= 2e-2
-    assert exact >= len(ref) - 1, f"{exact}/{len(ref)}"
+            continue
+        # beam protocol of tests/test_parity_scale_gpu.py: a differing top hypothesis must be a near-tied finalist of the
+        # oracle's, or score at least as well as the oracle's best
+        alt = [k for k, hk in enumerate(h) if hk["tokens"].tolist() == got]
+        if alt:
+            assert h[0]["score"] - h[alt[0]]["score"] <= 2e-2, (i, got, h[0]["score"], h[alt[0]]["score"])
+        else:
+            assert float(scores[i]) >= h[0]["score"] - 2e-2, (i, got, float(scores[i]), h[0]["score"])
+    print(f"beam 5 (tiny): {exact}/{len(ref)} top hypotheses identical")
 
 
 def test_4096_page_line_mode_and_dense_page(cuda_ctx):

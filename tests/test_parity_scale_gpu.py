@@ -7,9 +7,14 @@ e2e_page_*.json): oracle-K1 -> oracle-CRAFT -> cv2 getDetBoxes -> rects -> crops
 fp32 fairseq decoder -> the fairseq search (pinned against the reference's generator.py in
 tests/test_oracle_vs_reference.py).  Here the device runs its own detection, K9, encoder and search.
 
-Margin protocol (SURVEY.md hard part 5): a hypothesis whose every search decision had a margin above MARGIN nat in the
-oracle MUST be bit-identical; closer calls may order differently under 16-bit rounding and are counted, not excused
-silently: the rates are printed and written to gpurun_out/parity_scale.json.  Two weight flavours: the bench's weights as
+Margin protocol (SURVEY.md hard part 5).  Greedy: a hypothesis whose every arg-max had a top-1 / top-2 margin above
+MARGIN nat in the oracle MUST be bit-identical; closer calls may flip under 16-bit rounding and are counted, not excused
+silently.  Beam 5 orders 10 candidates out of 5 x 50265 every step — neighbouring candidates are almost never 0.05 nat
+apart, so the per-decision margin binds nothing there; instead every crop must fall in one of three classes: (1) top
+hypothesis identical; (2) the device's top hypothesis is another of the oracle's five finalists whose oracle score is
+within SCORE_TOL of the oracle's best (a rank flip among near-ties); (3) a hypothesis outside the oracle's finalists whose
+device score is at least the oracle's best minus SCORE_TOL (a near-tie at a pruning boundary led to an equally good or
+better hypothesis).  Anything else fails.  The rates are printed and written to gpurun_out/parity_scale.json.  Two weight flavours: the bench's weights as
 they are (random-init logits are nearly flat: most crops have a call closer than 0.05 nat) and the same weights with the
 vocabulary projection scaled by 8 ("sharp": the same greedy arg-max chain in exact arithmetic, margins of a trained
 model), where the protocol binds most crops.
@@ -62,6 +67,8 @@ def _compare(g, key, tokens, lengths, scores, dtype):
     n = len(want_l)
     tokens, lengths, scores = tokens.cpu().numpy(), lengths.cpu().numpy(), scores.cpu().numpy()
     exact = np.array([lengths[i] == want_l[i] and np.array_equal(tokens[i, :lengths[i]], want_t[i, :want_l[i]]) for i in range(n)])
+    if key + "_finalists" in g:
+        return _compare_beam(g, key, tokens, lengths, scores, exact, dtype)
     bound = margin > MARGIN[dtype]
     bound_fp16 = margin > 0.05
     bad = np.nonzero(bound & ~exact)[0]
@@ -73,6 +80,30 @@ def _compare(g, key, tokens, lengths, scores, dtype):
                  smallest_margin_of_a_mismatch=float(margin[~exact].min()) if (~exact).any() else None,
                  largest_margin_of_a_mismatch=float(margin[~exact].max()) if (~exact).any() else None,
                  max_score_err_on_exact=score_err, all_end_with_eos=bool(ended))
+    return stats, bad, score_err
+
+
+def _compare_beam(g, key, tokens, lengths, scores, exact, dtype):
+    ft, fs, want_s = g[key + "_finalists"], g[key + "_finalist_scores"], g[key + "_score"]
+    n, tol = len(want_s), SCORE_TOL[dtype]
+    flip = np.zeros(n, bool)        # class 2
+    better = np.zeros(n, bool)      # class 3
+    for i in np.nonzero(~exact)[0]:
+        got = tokens[i, :lengths[i]]
+        for j in range(ft.shape[1]):
+            L = int((ft[i, j] != 1).sum())
+            if L == len(got) and np.array_equal(ft[i, j, :L], got):
+                flip[i] = fs[i, 0] - fs[i, j] <= tol
+                break
+        else:
+            better[i] = scores[i] >= want_s[i] - tol
+    bad = np.nonzero(~(exact | flip | better))[0]
+    score_err = float(np.abs(scores[exact] - want_s[exact]).max()) if exact.any() else 0.0
+    ended = all(tokens[i, lengths[i] - 1] == 2 for i in range(n))
+    stats = dict(crops=int(n), exact=int(exact.sum()), exact_rate=float(exact.mean()), score_tol=tol,
+                 rank_flip_among_near_tied_finalists=int(flip.sum()), equally_good_outside_finalists=int(better.sum()),
+                 unexplained=int(len(bad)), max_score_err_on_exact=score_err, all_end_with_eos=bool(ended),
+                 bound_by_margin=0, bound_and_exact=0, bound_at_0p05=0, bound_at_0p05_and_exact=0, margin=None)
     return stats, bad, score_err
 
 
@@ -111,12 +142,17 @@ def _scale_case(ctx, dtype, model):
             torch.cuda.synchronize()
             stats, bad, score_err = _compare(g, tag + name, tokens, lengths, scores, dtype)
             case[tag + name] = stats
-            print(f"[{model} {dtype}] {tag + name}: exact {stats['exact']}/{stats['crops']} ({100 * stats['exact_rate']:.1f} %), "
-                  f"bound by margin > {MARGIN[dtype]}: {stats['bound_and_exact']}/{stats['bound_by_margin']} exact, "
-                  f"at 0.05: {stats['bound_at_0p05_and_exact']}/{stats['bound_at_0p05']}, score err {score_err:.2e}")
+            if "unexplained" in stats:
+                print(f"[{model} {dtype}] {tag + name}: exact {stats['exact']}/{stats['crops']} ({100 * stats['exact_rate']:.1f} %), "
+                      f"rank flips among near-tied finalists {stats['rank_flip_among_near_tied_finalists']}, equally good outside "
+                      f"the finalists {stats['equally_good_outside_finalists']}, unexplained {stats['unexplained']}, score err {score_err:.2e}")
+            else:
+                print(f"[{model} {dtype}] {tag + name}: exact {stats['exact']}/{stats['crops']} ({100 * stats['exact_rate']:.1f} %), "
+                      f"bound by margin > {MARGIN[dtype]}: {stats['bound_and_exact']}/{stats['bound_by_margin']} exact, "
+                      f"at 0.05: {stats['bound_at_0p05_and_exact']}/{stats['bound_at_0p05']}, score err {score_err:.2e}")
             if len(bad):
-                failures.append(f"{tag + name}: {len(bad)} crops with margin > {MARGIN[dtype]} differ, e.g. crop {int(bad[0])} "
-                                f"(margin {float(g[tag + name + '_margin'][bad[0]]):.3f})")
+                failures.append(f"{tag + name}: {len(bad)} crops outside the protocol, e.g. crop {int(bad[0])} "
+                                f"(margin {float(g[tag + name + '_margin'][bad[0]]):.4f})")
             if score_err > SCORE_TOL[dtype]:
                 failures.append(f"{tag + name}: score error {score_err}")
             if not stats["all_end_with_eos"]:

@@ -56,10 +56,12 @@ def crops_to_input(page, rects, dt):
                         for r in rects])
 
 
-def search(sd, cfg, enc, beam, max_len_b):
+def search(sd, cfg, enc, beam, max_len_b, finalists=None):
     margins = []
     with torch.no_grad():
         hyps = trocr.generate(sd, cfg, enc, beam=beam, max_len_b=max_len_b, margins=margins)
+    if finalists is not None:
+        finalists.extend(hyps)                # all `beam` finalised hypotheses per crop, best first
     return [h[0] for h in hyps], margins
 
 
@@ -98,7 +100,7 @@ def make_scale(model, dtype, n, chunk=64, max_len_b=200):
             enc = trocr.encoder_forward(sd, cfg, chw)
         for tag, w in (("", sd), ("sharp_", sd_sharp)):
             for name, beam in (("greedy", 1), ("beam5", 5)):
-                h, m = search(w, cfg, enc, beam, max_len_b)
+                h, m = search(w, cfg, enc, beam, max_len_b, finalists=res.setdefault(tag + name + "_all", []) if beam > 1 else None)
                 res.setdefault(tag + name, []).extend(h)
                 res.setdefault(tag + name + "_margin", []).extend(m)
         print(f"  {i0 + len(chw)}/{len(rects)} crops ({time.time() - t0:.1f} s)", flush=True)
@@ -109,6 +111,17 @@ def make_scale(model, dtype, n, chunk=64, max_len_b=200):
         out[key + "_len"] = np.array([len(h["tokens"]) for h in hyps], np.int32)
         out[key + "_score"] = np.array([h["score"] for h in hyps], np.float32)
         out[key + "_margin"] = np.array(res[key + "_margin"], np.float32)
+        if key + "_all" in res:
+            # every finalised hypothesis of the beam search (the parity test explains rank flips among near-tied finalists)
+            alls = res[key + "_all"]
+            width = max(len(h["tokens"]) for hs in alls for h in hs)
+            ft = np.full((len(alls), 5, width), trocr.PAD, np.int32)
+            fs = np.full((len(alls), 5), -np.inf, np.float32)
+            for i, hs in enumerate(alls):
+                for j, h in enumerate(hs[:5]):
+                    ft[i, j, :len(h["tokens"])] = h["tokens"].tolist()
+                    fs[i, j] = h["score"]
+            out[key + "_finalists"], out[key + "_finalist_scores"] = ft, fs
         print(key, "margin > 0.05:", int((out[key + "_margin"] > 0.05).sum()), "of", len(hyps), "mean length",
               float(out[key + "_len"].mean()))
     path = os.path.join(OUT, f"trocr_scale_{model}_{dtype}.npz")
