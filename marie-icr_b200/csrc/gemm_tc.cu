@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <unordered_map>
 #include <stdlib.h>
 
 namespace {
@@ -32,7 +33,9 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int BAR_BYTES = (2 * 8 + 4) * 8 + 32;   // mbarriers + TMEM pointer, keeps the staging tiles 16 B aligned
+constexpr int BAR_BYTES = 512;   // 2*8 ring + 4 accumulator mbarriers, the TMEM pointer slot, 8 per-warp residual mbarriers;
+                                 // 512 keeps the staging tiles aligned for the 64-byte TMA swizzle
+constexpr int RES_BAR_SLOT = 2 * MAX_STAGES + 5;   // first of the EPI_WARPS residual mbarriers (u64 slots after the pointer)
 
 struct KParams {
     int n, h, w;
@@ -74,6 +77,36 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float hx = 0.5f * x;
     return fmaf(fabsf(hx), e, hx);                      // hx * sign(x) * e == |hx| * e: the sign rides on the operand modifier
 }
+// The same GELU on a PAIR of values with packed fp32 arithmetic (FFMA2), re-parametrised so that no sign handling is
+// left: with u = min(|x|, 3.92*sqrt(2)) and t(u) = q(u/sqrt2)*(u/sqrt2) - 1 (a degree-6 polynomial in u, zero-free Horner
+// form), h = 2^t = erfc(|x|/sqrt2)/2 and GELU(x) = relu(x) - |x|*h.  Per pair: 2 FMNMX + 6 FFMA2 + 2 MUFU.EX2 + 2 FMUL +
+// 2 FMNMX + 1 FFMA2 = 7.5 instructions per value (12 in the scalar form); max |error| 3.4e-7.
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x2) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    const float U = 5.5437171645f;
+    const f32x2 u = pk2(fminf(fabsf(x0), U), fminf(fabsf(x1), U));
+    f32x2 t = fma2(pk2(2.7622238121693954e-05f, 2.7622238121693954e-05f), u, pk2(-0.0007199128158390522f, -0.0007199128158390522f));
+    t = fma2(t, u, pk2(0.007913792505860329f, 0.007913792505860329f));
+    t = fma2(t, u, pk2(-0.053146157413721085f, -0.053146157413721085f));
+    t = fma2(t, u, pk2(-0.4589747190475464f, -0.4589747190475464f));
+    t = fma2(t, u, pk2(-1.1511340141296387f, -1.1511340141296387f));
+    t = fma2(t, u, pk2(-1.0f, -1.0f));
+    float t0, t1, h0, h1;
+    upk2(t, t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(t1));
+    return fma2(pk2(fabsf(x0) * h0, fabsf(x1) * h1), pk2(-1.0f, -1.0f), pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+}
+template <int ACT> __device__ __forceinline__ f32x2 apply_act2(f32x2 x) {
+    if (ACT == MB_ACT_GELU) return gelu_erf2(x);
+    if (ACT == MB_ACT_RELU) {
+        float a, b;
+        upk2(x, a, b);
+        return pk2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    }
+    return x;
+}
 template <int ACT> __device__ __forceinline__ float apply_act(float x) {
     if (ACT == MB_ACT_RELU) return fmaxf(x, 0.0f);
     if (ACT == MB_ACT_GELU) return gelu_erf(x);
@@ -88,10 +121,16 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2t(float a, float b)
 // each CTA loads its own A tile and half of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256: rows
 // 0..127 accumulate in the leader's TMEM, 128..255 in the peer's), completions are multicast to both CTAs' mbarriers.
 // Per SM and k-block that is 32 KB through shared memory instead of 48 KB, and six pipeline stages instead of four.
-template <int ACT, int OUT, bool RES, bool F16, bool CG2, bool LNF = false>
+// TMAOUT = true (16-bit output with TMA-compatible pitch): the epilogue works row-per-lane straight out of TMEM — bias /
+// LayerNorm fold / activation / residual with packed fp32 arithmetic — writes the 16-bit tile once into a 64-byte-swizzled
+// staging tile and hands it to the TMA (cp.async.bulk.tensor store, ragged edges clipped by the tensor map); the residual
+// tile arrives the same way (TMA load, one chunk ahead).  No fp32 staging round trip, no per-thread global address
+// arithmetic, no separate ragged path.
+template <int ACT, int OUT, bool RES, bool F16, bool CG2, bool LNF = false, bool TMAOUT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const KParams p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                const __grid_constant__ CUtensorMap tmRes, const KParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024 B alignment is required by the 128B swizzle; do not trust the declared alignment alone.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -115,6 +154,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (TMAOUT) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+        if (TMAOUT && RES) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRes) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
@@ -125,6 +166,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[i]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp
         }
+        if (TMAOUT && RES)
+            for (int i = 0; i < EPI_WARPS; ++i) mbar_init(smem_u32(&bars[RES_BAR_SLOT + i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -243,6 +286,147 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 if (as == 0) aphase ^= 1;
             }
         }
+    } else if (warp >= 4 && TMAOUT) {
+        // ------------------------------------------------------------ epilogue, TMA-store form (8 warps)
+        // Warp e owns TMEM lane quarter (warp & 3) = 32 tile rows, one row per lane, and every second 32-column chunk.
+        const int ew = warp - 4;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        uint8_t* stg_out = smem_stage + ew * STAGE_TILE_BYTES;           // 32 rows x 64 B, 64-byte swizzle: TMA store source
+        uint8_t* stg_res = stg_out + 2048;                                // same layout: TMA load destination (residual)
+        const uint32_t res_bar = smem_u32(&bars[RES_BAR_SLOT + ew]);
+        uint32_t rphase = 0;
+        const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+            const int bt = tile / tiles_per_batch;
+            const int trem = tile - bt * tiles_per_batch;
+            const int nt = trem % p.n_tiles;
+            const int mt = trem / p.n_tiles;
+            const int wt = mt % p.w_tiles;
+            const int rest = mt / p.w_tiles;
+            const int hh = rest % p.h;
+            const int nn = rest / p.h;
+            const int nbase = bt * p.out_col_stride;
+            const int wrow = wt * BLOCK_M + q * 32;                  // w coordinate of this warp's first row
+            const long long pix0 = ((long long)nn * p.h + hh) * p.w + wrow;
+            const int rows_valid = min(32, p.w - wrow);
+            const int ntile0 = nt * p.block_n;
+            const int n_chunks = (p.block_n + 31) >> 5;
+            auto chunk_active = [&](int ci) { return ci < n_chunks && ntile0 + ci * 32 < p.n_out && rows_valid > 0; };
+            f32x2 nm2 = 0, rstd2 = 0;
+            if (LNF) {
+                const float2 st = lane < rows_valid ? __ldg(p.ln_stats + pix0 + lane) : make_float2(0.f, 0.f);
+                nm2 = pk2(st.x, st.x);
+                rstd2 = pk2(st.y, st.y);
+            }
+            if (RES && chunk_active(half) && lane == 0) {
+                mbar_arrive_expect_tx(res_bar, 2048);
+                tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, nbase + ntile0 + half * 32, wrow, hh, nn);
+            }
+            mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+            uint32_t v[32];
+            bool released = false;
+            if (chunk_active(half)) tmem_ld32(taddr + (uint32_t)(half * 32), v);
+#pragma unroll 1
+            for (int ci = half; chunk_active(ci); ci += 2) {
+                const int n0 = ntile0 + ci * 32;
+                uint32_t rr[16];
+                if (RES) {
+                    mbar_wait(res_bar, rphase, p.diag, 5);
+                    rphase ^= 1;
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        const uint4 t = *reinterpret_cast<const uint4*>(stg_res + sw_row + ((c ^ sw_x) << 4));
+                        rr[4 * c] = t.x; rr[4 * c + 1] = t.y; rr[4 * c + 2] = t.z; rr[4 * c + 3] = t.w;
+                    }
+                    __syncwarp();
+                    if (chunk_active(ci + 2) && lane == 0) {          // next residual chunk: lands under this chunk's arithmetic
+                        mbar_arrive_expect_tx(res_bar, 2048);
+                        tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, nbase + n0 + 64, wrow, hh, nn);
+                    }
+                }
+                tmem_wait_ld();
+                const bool full = n0 + 32 <= p.n_out;
+                uint32_t o[16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (full) {
+                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + n0) + k);
+                        if (LNF) c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c + nbase + n0) + k);
+                    } else {
+                        const int j = n0 + 4 * k;
+                        if (p.bias != nullptr) {
+                            if (j < p.n_out) b4.x = __ldg(p.bias + nbase + j);
+                            if (j + 1 < p.n_out) b4.y = __ldg(p.bias + nbase + j + 1);
+                            if (j + 2 < p.n_out) b4.z = __ldg(p.bias + nbase + j + 2);
+                            if (j + 3 < p.n_out) b4.w = __ldg(p.bias + nbase + j + 3);
+                        }
+                        if (LNF) {
+                            if (j < p.n_out) c4.x = __ldg(p.ln_c + nbase + j);
+                            if (j + 1 < p.n_out) c4.y = __ldg(p.ln_c + nbase + j + 1);
+                            if (j + 2 < p.n_out) c4.z = __ldg(p.ln_c + nbase + j + 2);
+                            if (j + 3 < p.n_out) c4.w = __ldg(p.ln_c + nbase + j + 3);
+                        }
+                    }
+                    f32x2 xa = pk2(v[4 * k], v[4 * k + 1]), xb = pk2(v[4 * k + 2], v[4 * k + 3]);
+                    const f32x2 ba = pk2(b4.x, b4.y), bb = pk2(b4.z, b4.w);
+                    if (LNF) {       // rstd * (acc - mean * c) + b'
+                        xa = fma2(fma2(nm2, pk2(c4.x, c4.y), xa), rstd2, ba);
+                        xb = fma2(fma2(nm2, pk2(c4.z, c4.w), xb), rstd2, bb);
+                    } else {
+                        xa = add2(xa, ba);
+                        xb = add2(xb, bb);
+                    }
+                    xa = apply_act2<ACT>(xa);
+                    xb = apply_act2<ACT>(xb);
+                    if (RES) {
+                        const float2 r0 = unpack2t<F16>(rr[2 * k]), r1 = unpack2t<F16>(rr[2 * k + 1]);
+                        xa = add2(xa, pk2(r0.x, r0.y));
+                        xb = add2(xb, pk2(r1.x, r1.y));
+                    }
+                    float f0, f1, f2, f3;
+                    upk2(xa, f0, f1);
+                    upk2(xb, f2, f3);
+                    o[2 * k] = pack2t<F16>(f0, f1);
+                    o[2 * k + 1] = pack2t<F16>(f2, f3);
+                }
+                // the accumulators of this chunk are consumed: next chunk's TMEM load overlaps the store sequence; after
+                // the last chunk the accumulator buffer goes back to the MMA warp before the stores are even issued
+                if (chunk_active(ci + 2)) {
+                    tmem_ld32(taddr + (uint32_t)((ci + 2) * 32), v);
+                } else {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+                    released = true;
+                }
+                if (lane == 0) bulk_wait_group_read0();              // this warp's previous store has read the staging tile
+                __syncwarp();
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(stg_out + sw_row + ((c ^ sw_x) << 4)) =
+                        make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tmOut, smem_u32(stg_out), nbase + n0, wrow, hh, nn);
+                    bulk_commit_group();
+                }
+            }
+            if (!released) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+        if (lane == 0) bulk_wait_group0();     // the staging tile must outlive the last store's read
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (8 warps)
         // Warp e = warp-4 owns TMEM lane quarter (warp & 3) — the 32 tile rows it may read — and every second
@@ -475,6 +659,63 @@ int encode_wgt_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int ktot, int 
     return 0;
 }
 
+// NHWC 16-bit output / residual map for the TMA epilogue: dims {C, W, H, N}, box {32, 32, 1, 1}, 64-byte swizzle
+int encode_io_map(mb_ctx* ctx, CUtensorMap* m, const void* base, long long c, long long ld, int n, int h, int w, int f16) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                    strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled(io c=%lld ld=%lld n=%d h=%d w=%d) -> %d", c, ld, n, h, w, (int)r);
+    return 0;
+}
+
+// Descriptor cache: the same (buffer, shape) pairs come back every layer / step / page batch (arena pointers are stable),
+// so a tensor map is encoded once instead of three to five driver calls per launch.
+struct MapKey {
+    const void* base; long long a, b; int kind, n, h, w, f16;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && a == o.a && b == o.b && kind == o.kind && n == o.n && h == o.h && w == o.w && f16 == o.f16;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t x = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        auto mix = [&x](long long v) { x ^= (size_t)v + 0x9E3779B97F4A7C15ull + (x << 6) + (x >> 2); };
+        mix(k.a); mix(k.b); mix(k.kind); mix(k.n); mix(k.h); mix(k.w); mix(k.f16);
+        return x;
+    }
+};
+struct MapCache {
+    std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
+    std::mutex mu;
+};
+MapCache& map_cache(mb_ctx* ctx) {
+    static std::mutex mu;
+    static std::unordered_map<mb_ctx*, MapCache*> all;
+    std::lock_guard<std::mutex> g(mu);
+    MapCache*& c = all[ctx];
+    if (!c) c = new MapCache();
+    return *c;
+}
+// kind 0: activation map (a = channels, b = pitch), 1: weight map (a = ktot, b = rows, n = block_n), 2: output / residual map
+template <class F> int cached_map(mb_ctx* ctx, CUtensorMap* out, const MapKey& key, F encode) {
+    MapCache& c = map_cache(ctx);
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.maps.find(key);
+    if (it != c.maps.end()) { *out = it->second; return 0; }
+    const int rc = encode(out);
+    if (rc) return rc;
+    if (c.maps.size() > 16384) c.maps.clear();
+    c.maps.emplace(key, *out);
+    return 0;
+}
+
 }  // namespace
 
 void mb_profile_drain(mb_ctx* ctx) {
@@ -572,24 +813,52 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     MB_REQUIRE(ctx, !lnf || (g.ln_c && g.out_mode == MB_OUT_BF16 && !g.residual && g.taps == 1 && g.n == 1 && g.h == 1),
                "tap_gemm: the LayerNorm fold needs a plain 16-bit-output GEMM without residual");
 
-    CUtensorMap tmA0, tmA1, tmB;
-    int rc = encode_act_map(ctx, &tmA0, g.a0, g.batches > 1 ? g.a0_ld : g.c0, g.a0_ld, g.n, g.h, g.w, ctx->f16);
+    const bool res = g.residual != nullptr;
+    const bool h = ctx->f16 != 0;
+    // TMA-store epilogue: 16-bit row-major output whose pitch / base the TMA can address (and the same for the residual);
+    // block-diagonal batches need whole chunks per batch (a box must not spill into the next batch's columns)
+    const long long out_cols = (long long)(p.batches - 1) * g.out_col_stride + g.n_out;
+    const char* epi_env = getenv("MB_EPI_TMA");
+    const bool tma_out = !(epi_env && epi_env[0] == '0') && !cg2 && g.out_mode == MB_OUT_BF16 && g.out_ld % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && out_cols >= 32 &&
+                         (p.batches == 1 || g.n_out % 32 == 0) &&
+                         (!res || (g.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0));
+
+    CUtensorMap tmA0, tmA1, tmB, tmOut, tmRes;
+    const int a0c = g.batches > 1 ? g.a0_ld : g.c0;
+    int rc = cached_map(ctx, &tmA0, MapKey{g.a0, a0c, g.a0_ld, 0, g.n, g.h, g.w, ctx->f16},
+                        [&](CUtensorMap* m) { return encode_act_map(ctx, m, g.a0, a0c, g.a0_ld, g.n, g.h, g.w, ctx->f16); });
     if (rc) return rc;
     if (g.c1 > 0) {
         MB_REQUIRE(ctx, g.a1 != nullptr, "tap_gemm: c1>0 but a1 null");
-        rc = encode_act_map(ctx, &tmA1, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w, ctx->f16);
+        rc = cached_map(ctx, &tmA1, MapKey{g.a1, g.c1, g.a1_ld, 0, g.n, g.h, g.w, ctx->f16},
+                        [&](CUtensorMap* m) { return encode_act_map(ctx, m, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w, ctx->f16); });
         if (rc) return rc;
     } else {
         tmA1 = tmA0;
     }
-    rc = encode_wgt_map(ctx, &tmB, g.wgt, g.taps * (g.c0 + g.c1), g.n_rows_w, cg2 ? block_n / 2 : block_n, ctx->f16);
+    const int ktot = g.taps * (g.c0 + g.c1), bn_box = cg2 ? block_n / 2 : block_n;
+    rc = cached_map(ctx, &tmB, MapKey{g.wgt, ktot, g.n_rows_w, 1, bn_box, 0, 0, ctx->f16},
+                    [&](CUtensorMap* m) { return encode_wgt_map(ctx, m, g.wgt, ktot, g.n_rows_w, bn_box, ctx->f16); });
     if (rc) return rc;
+    tmOut = tmB;
+    tmRes = tmB;
+    if (tma_out) {
+        rc = cached_map(ctx, &tmOut, MapKey{g.out, out_cols, g.out_ld, 2, g.n, g.h, g.w, ctx->f16},
+                        [&](CUtensorMap* m) { return encode_io_map(ctx, m, g.out, out_cols, g.out_ld, g.n, g.h, g.w, ctx->f16); });
+        if (rc) return rc;
+        if (res) {
+            rc = cached_map(ctx, &tmRes, MapKey{g.residual, out_cols, g.res_ld, 2, g.n, g.h, g.w, ctx->f16}, [&](CUtensorMap* m) {
+                return encode_io_map(ctx, m, g.residual, out_cols, g.res_ld, g.n, g.h, g.w, ctx->f16);
+            });
+            if (rc) return rc;
+        }
+    }
 
     const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const KParams);
     KernelFn fn = nullptr;
-    const bool res = g.residual != nullptr;
-    const bool h = ctx->f16 != 0;
 #define MB_PICK(A, O, R)                                                                               \
     if (g.act == (A) && g.out_mode == (O) && res == (R))                                               \
         fn = h ? (KernelFn)tap_gemm_kernel<A, O, R, true, false> : (KernelFn)tap_gemm_kernel<A, O, R, false, false>;
@@ -610,6 +879,16 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     MB_PICKL(MB_ACT_NONE) MB_PICKL(MB_ACT_GELU)
     if (lnf && g.act == MB_ACT_RELU) fn = nullptr;
 #undef MB_PICKL
+    if (tma_out && fn) {
+#define MB_PICKT(A, R, L)                                                                                            \
+    if (g.act == (A) && res == (R) && lnf == (L))                                                                    \
+        fn = h ? (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, true, false, L, true>                                 \
+               : (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, false, false, L, true>;
+        MB_PICKT(MB_ACT_NONE, false, false) MB_PICKT(MB_ACT_NONE, true, false) MB_PICKT(MB_ACT_RELU, false, false)
+        MB_PICKT(MB_ACT_RELU, true, false) MB_PICKT(MB_ACT_GELU, false, false) MB_PICKT(MB_ACT_GELU, true, false)
+        MB_PICKT(MB_ACT_NONE, false, true) MB_PICKT(MB_ACT_GELU, false, true)
+#undef MB_PICKT
+    }
 #undef MB_PICK
 #undef MB_PICK2
     if (!fn)
@@ -637,9 +916,9 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MB_CUDA(ctx, cudaLaunchKernelEx(&cfg, fn, tmA0, tmA1, tmB, p));
+        MB_CUDA(ctx, cudaLaunchKernelEx(&cfg, fn, tmA0, tmA1, tmB, tmOut, tmRes, p));
     } else {
-        fn<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, p);
+        fn<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB, tmOut, tmRes, p);
     }
     if (ctx->profile) {
         cudaEventRecord(ev1, stream);

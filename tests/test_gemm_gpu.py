@@ -98,3 +98,46 @@ def test_gemm_block_diagonal(cuda_ctx, dtype16):
     att = ops.gemm16_batched(ctx, wv, heads, 64, E, E, 64, 64, H, bias=bias)
     ref2 = torch.einsum("rhe,hde->rhd", ctx.float().view(R, heads, E), wv.float().view(heads, 64, E)).reshape(R, H) + bias
     _close(att, ref2, "per-head V-side projection")
+
+
+@pytest.mark.parametrize("M,N,K", [(700, 768, 256), (37, 96, 128), (1154, 2304, 768), (300, 80, 64)])
+def test_tma_epilogue_equals_register_epilogue(cuda_ctx, dtype16, M, N, K):
+    """The TMA-store epilogue (row-per-lane, packed fp32, 64-byte-swizzled staging, ragged edges clipped by the tensor
+    map) against the register / fp32-staging epilogue it replaces (MB_EPI_TMA=0): bit-identical for bias / ReLU /
+    residual (same operation order), within the output rounding for the re-parametrised GELU; in-place residual too."""
+    import os
+    from marie_icr_b200 import ops
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda").to(dtype16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(dtype16)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(dtype16)
+
+    def run(**kw):
+        outs = []
+        for flag in ("1", "0"):
+            os.environ["MB_EPI_TMA"] = flag
+            try:
+                outs.append(ops.gemm16(a, w, **kw))
+            finally:
+                os.environ.pop("MB_EPI_TMA", None)
+        return outs
+
+    for kw in (dict(), dict(bias=bias), dict(bias=bias, act=ops.ACT_RELU), dict(bias=bias, residual=res),
+               dict(bias=bias, act=ops.ACT_RELU, residual=res)):
+        new, old = run(**kw)
+        assert torch.equal(new, old), (sorted(kw), (new.float() - old.float()).abs().max().item())
+    new, old = run(bias=bias, act=ops.ACT_GELU)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    _close(new, ref, "gelu (TMA epilogue)")
+    assert (new.float() - old.float()).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    # in place: the residual stream is both residual and output (x += proj(...)), as the encoder uses it
+    x = res.clone()
+    os.environ["MB_EPI_TMA"] = "1"
+    try:
+        from marie_icr_b200._lib import c_int, c_ll, cur_stream, ptr
+        cuda_ctx.call("mb_gemm16", ptr(a), c_ll(K), ptr(w), c_int(N), c_int(M), c_int(N), c_int(K), ptr(bias), c_int(0),
+                      ptr(x), c_ll(N), ptr(x), c_ll(N), c_int(0), cur_stream())
+    finally:
+        os.environ.pop("MB_EPI_TMA", None)
+    assert torch.equal(x, ops.gemm16(a, w, bias=bias, residual=res))

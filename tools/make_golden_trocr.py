@@ -29,7 +29,6 @@ from synthetic import weights as sw  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 SPARSE = (0.7, 0.45, 0.3)
-SHARP = 8.0
 
 
 def oracle_detect(page, dt, preset=SPARSE):
@@ -86,26 +85,20 @@ def make_scale(model, dtype, n, chunk=64, max_len_b=200):
         rects.append(r)
     rects, pidx = np.concatenate(rects), np.asarray(pidx, np.int32)
     sd, cfg = trocr_weights(model, dt)
-    # two flavours of the same weights: as the bench uses them, and with the vocabulary projection scaled by SHARP (a power
-    # of two: exact in 16 bit).  Random-init logits are almost flat (top-1/top-2 gaps of ~0.01 nat, confidence ~0.001);
-    # the scaled projection has the same greedy arg-max chain in exact arithmetic but decision margins SHARP times
-    # larger, like a trained model's (SURVEY.md hard part 5c) — there nearly every crop is bound by the margin protocol.
-    sd_sharp = dict(sd)
-    sd_sharp["decoder.output_projection.weight"] = sd["decoder.output_projection.weight"] * SHARP
     res = {}
     for i0 in range(0, len(rects), chunk):
         chw = torch.cat([crops_to_input(pages[p], rects[i0:i0 + chunk][pidx[i0:i0 + chunk] == p], dt)
                          for p in sorted(set(pidx[i0:i0 + chunk].tolist()))])
         with torch.no_grad():
             enc = trocr.encoder_forward(sd, cfg, chw)
-        for tag, w in (("", sd), ("sharp_", sd_sharp)):
+        for tag, w in (("", sd),):
             for name, beam in (("greedy", 1), ("beam5", 5)):
                 h, m = search(w, cfg, enc, beam, max_len_b, finalists=res.setdefault(tag + name + "_all", []) if beam > 1 else None)
                 res.setdefault(tag + name, []).extend(h)
                 res.setdefault(tag + name + "_margin", []).extend(m)
         print(f"  {i0 + len(chw)}/{len(rects)} crops ({time.time() - t0:.1f} s)", flush=True)
-    out = dict(page_index=pidx, rects=rects, max_len_b=np.int32(max_len_b), sharp=np.float32(SHARP))
-    for key in ("greedy", "beam5", "sharp_greedy", "sharp_beam5"):
+    out = dict(page_index=pidx, rects=rects, max_len_b=np.int32(max_len_b))
+    for key in ("greedy", "beam5"):
         hyps = res[key]
         out[key + "_tokens"] = pad_tokens(hyps, max(len(h["tokens"]) for h in hyps))
         out[key + "_len"] = np.array([len(h["tokens"]) for h in hyps], np.int32)
@@ -142,7 +135,6 @@ def make_e2e(dtype="fp16", beam=1):
     page, _ = synth.synth_page(0, **geom)
     rects = oracle_detect(page, dt)
     sd, cfg = trocr_weights("base", dt)
-    sd["decoder.output_projection.weight"] = sd["decoder.output_projection.weight"] * SHARP      # see make_scale
     chw = crops_to_input(page, rects, dt)
     with torch.no_grad():
         enc = trocr.encoder_forward(sd, cfg, chw)
@@ -175,7 +167,7 @@ def make_e2e(dtype="fp16", beam=1):
     result["meta"].update(page=0, lines=lines, lines_bboxes=[], format="xywh")     # ocr_engine.py:200-217
     path = os.path.join(OUT, f"e2e_page_{dtype}_beam{beam}.json")
     with open(path, "w") as f:
-        json.dump(dict(page_geometry=geom, dtype=dtype, beam=beam, sharp=SHARP, rects=boxes, margins=[float(m) for m in margins],
+        json.dump(dict(page_geometry=geom, dtype=dtype, beam=beam, rects=boxes, margins=[float(m) for m in margins],
                        tokens=[h["tokens"].tolist() for h in hyps], result=result), f)
     print("wrote", path, len(boxes), "words")
 
