@@ -12,23 +12,25 @@ import os
 SPECIALS = (0, 1, 2, 3)   # <s>, <pad>, </s>, <unk>
 
 
+class _Pieces(dict):
+    """token id -> text piece, filled on demand (decode is one dict lookup per token)"""
+
+    def __missing__(self, t):
+        k = int(t) - 4
+        p = ((" " if k % 7 == 0 else "") + chr(97 + k % 26) + (chr(97 + (k // 26) % 26) if k % 3 else "")
+             + (chr(97 + (k // 676) % 26) if k % 5 == 0 else ""))
+        self[t] = p
+        return p
+
+
 class SyntheticDetokenizer:
     """id -> 1-3 letters; ids whose slot is 0 mod 7 start a new word (leading space), like GPT-2's 'Ġ' tokens."""
 
     def __init__(self):
-        self._piece = {}
-
-    def piece(self, t):
-        p = self._piece.get(t)
-        if p is None:
-            k = t - 4
-            p = ((" " if k % 7 == 0 else "") + chr(97 + k % 26) + (chr(97 + (k // 26) % 26) if k % 3 else "")
-                 + (chr(97 + (k // 676) % 26) if k % 5 == 0 else ""))
-            self._piece[t] = p
-        return p
+        self._piece = _Pieces({t: "" for t in SPECIALS})
 
     def decode(self, ids):
-        return "".join([self.piece(int(t)) for t in ids if int(t) not in SPECIALS]).lstrip(" ")
+        return "".join(map(self._piece.__getitem__, ids)).lstrip(" ")
 
 
 def _bytes_to_unicode():

@@ -58,6 +58,7 @@ struct KParams {
     const float2* ln_stats;   // LNF: per row (-mean, rstd)
     const float* ln_c;        // LNF: per column sum_k W'[n, k]
     unsigned int* diag;
+    unsigned backoff;         // ns slept between polls of the long waits (0 = poll continuously)
 };
 
 // exact-erf GELU (timm nn.GELU).  erf(z) = 1 - 2^q(z) for z in [0, 3.92] with a degree-6 polynomial q fitted to
@@ -218,7 +219,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
                     const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
                     for (int kb = 0; kb < kb_per_tap; ++kb) {
-                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.diag, 1);
+                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.diag, 1, p.backoff);
                         const uint32_t fb = smem_u32(&full_bar[stage]);
                         const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                         const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
@@ -325,7 +326,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 mbar_arrive_expect_tx(res_bar, 2048);
                 tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, nbase + ntile0 + half * 32, wrow, hh, nn);
             }
-            mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
+            mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4, p.backoff);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
             uint32_t v[32];
@@ -481,7 +482,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     rres[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + (pix0 + i * 4 + rr) * p.res_ld + nbase + n0c + kk * 4));
             };
             if (RES && chunk_fast(half)) load_res(half);
-            mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4);
+            mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4, p.backoff);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
             uint32_t v[32];
@@ -809,6 +810,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.a_col_stride = g.a_col_stride; p.w_row_stride = g.w_row_stride; p.out_col_stride = g.out_col_stride;
     p.ln_stats = reinterpret_cast<const float2*>(g.ln_stats); p.ln_c = g.ln_c;
     p.diag = ctx->dev_diag;
+    { const char* e = getenv("MB_SPIN_SLEEP"); p.backoff = e ? (unsigned)atoi(e) : 0u; }
     const bool lnf = g.ln_stats != nullptr;
     MB_REQUIRE(ctx, !lnf || (g.ln_c && g.out_mode == MB_OUT_BF16 && !g.residual && g.taps == 1 && g.n == 1 && g.h == 1),
                "tap_gemm: the LayerNorm fold needs a plain 16-bit-output GEMM without residual");

@@ -20,7 +20,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* diag, int who) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* diag, int who, unsigned backoff_ns = 0) {
     uint32_t done = 0;
     unsigned int spins = 0;
     while (true) {
@@ -32,6 +32,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
+        if (backoff_ns) __nanosleep(backoff_ns);   // long waits (accumulator / ring slot): do not burn issue slots polling
         if (++spins > (1u << 24)) {   // a lost arrival must fault, never hang the box
             if (diag) atomicExch(diag, 0xDEAD0000u | (unsigned)who);
             __trap();

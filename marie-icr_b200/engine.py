@@ -84,30 +84,65 @@ class OcrEngineB200:
         return results
 
     def _extract_batched(self, frames, pms_mode, coordinate_format):
+        import queue
+        import threading
         pipe = self.box_processor.pipeline
         icr = self.icr_processor
         refiner = bool(getattr(self.box_processor, "line_refiner", False))
         line_boxes = []
-        rec, counts = pipe.run_frames(frames, preset=PSM_PRESETS[pms_mode.value], beam=icr.beam, max_len_b=icr.max_len_b,
-                                      out_ld=getattr(self, "record_tokens", None) or icr.max_len_b + 1,
-                                      line_refiner=refiner, want_lines=line_boxes)
-        words = records_to_words(rec, icr.detok)
-        results, k = [], 0
-        for i, img in enumerate(frames):
-            page_words = words[k:k + counts[i]]
-            k += counts[i]
-            meta = {"imageSize": {"width": img.shape[1], "height": img.shape[0]}, "page": 0, "lang": "en"}
-            if not page_words:
-                result = {"meta": meta, "words": [], "lines": []}
-                lines = []
-            else:
-                boxes = [w["box"] for w in page_words]
-                lines = [w["line"] for w in page_words]
-                res = [{"confidence": w["confidence"], "id": f"img-{j}", "text": w["text"]} for j, w in enumerate(page_words)]
-                result = assemble_result(meta, boxes, lines, res)
-            self._finish(result, i, lines, line_boxes[i] if refiner else [], coordinate_format)
-            results.append(result)
-        return results
+        # Host post-processing (records -> words -> the reference's page records) runs on a helper thread, one decode
+        # batch behind the GPU: only the last batch's share is left once the device is done.
+        blocks = queue.Queue()
+        state = {"words": [], "counts": None, "results": [], "done": 0, "error": None}
+
+        def assemble_ready(final=False):
+            counts = state["counts"]
+            while counts is not None and len(state["results"]) < len(counts):
+                i = len(state["results"])
+                c = counts[i]
+                if state["done"] + c > len(state["words"]) or (refiner and not final):
+                    return                               # page i is not complete yet (line boxes arrive at the end)
+                page_words = state["words"][state["done"]:state["done"] + c]
+                state["done"] += c
+                img = frames[i]
+                meta = {"imageSize": {"width": img.shape[1], "height": img.shape[0]}, "page": 0, "lang": "en"}
+                if not page_words:
+                    result, lines = {"meta": meta, "words": [], "lines": []}, []
+                else:
+                    boxes = [w["box"] for w in page_words]
+                    lines = [w["line"] for w in page_words]
+                    res = [{"confidence": w["confidence"], "id": f"img-{j}", "text": w["text"]} for j, w in enumerate(page_words)]
+                    result = assemble_result(meta, boxes, lines, res)
+                self._finish(result, i, lines, line_boxes[i] if refiner else [], coordinate_format)
+                state["results"].append(result)
+
+        def worker():
+            try:
+                while True:
+                    item = blocks.get()
+                    if item is None:
+                        return
+                    block, counts = item
+                    state["counts"] = counts
+                    state["words"].extend(records_to_words(block, icr.detok))
+                    assemble_ready()
+            except Exception as ex:                      # surfaced on the caller's thread below
+                state["error"] = ex
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        try:
+            _, counts = pipe.run_frames(frames, preset=PSM_PRESETS[pms_mode.value], beam=icr.beam, max_len_b=icr.max_len_b,
+                                        out_ld=getattr(self, "record_tokens", None) or icr.max_len_b + 1,
+                                        line_refiner=refiner, want_lines=line_boxes, sink=lambda b, c: blocks.put((b, c)))
+        finally:
+            blocks.put(None)
+            th.join()
+        if state["error"] is not None:
+            raise state["error"]
+        state["counts"] = counts
+        assemble_ready(final=True)
+        return state["results"]
 
     # region / field extraction (__process_extract_regions, ocr_engine.py:223-414): every region is cropped, padded
     # with 4 white pixels, run through the box processor in its own PSM (cached by content), and the fragments of a

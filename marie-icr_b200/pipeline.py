@@ -150,8 +150,9 @@ class PagePipeline:
         return res
 
     # ------------------------------------------------------------------------------------------ recognition
-    def recognize_crops(self, pages_dev, rects, page_idx, beam=1, max_len_b=200, out_ld=32):
-        """Crops addressed by (page, rect) -> (tokens [N,out_ld] i32, lengths [N] i32, scores [N] f32) on the device."""
+    def recognize_crops(self, pages_dev, rects, page_idx, beam=1, max_len_b=200, out_ld=32, on_batch=None):
+        """Crops addressed by (page, rect) -> (tokens [N,out_ld] i32, lengths [N] i32, scores [N] f32) on the device.
+        on_batch(i0, m): optional hook called after every decode batch, when rows [i0, i0+m) of the outputs are final."""
         if not self.has_trocr:
             raise RuntimeError("TrOCR weights are not loaded")
         n = rects.shape[0]
@@ -185,6 +186,8 @@ class PagePipeline:
             tokens[i0:i0 + m] = t
             lengths[i0:i0 + m] = l
             scores[i0:i0 + m] = s
+            if on_batch is not None:
+                on_batch(i0, m, tokens, lengths, scores)
         return tokens, lengths, scores
 
     def recognize_fragments(self, fragments, beam=1, max_len_b=200, out_ld=32):
@@ -207,17 +210,17 @@ class PagePipeline:
 
     # ------------------------------------------------------------------------------------------ whole path
     def run_device(self, pages_dev, preset=PSM_PRESETS["sparse"], beam=1, max_len_b=200, out_ld=32, line_refiner=False,
-                   ready=None, want_lines=None):
+                   ready=None, want_lines=None, sink=None):
         """Pages already in HBM -> packed per-word records [N, RECORD_HEAD + out_ld] i32 on the device
         (page, x, y, w, h, line, length, score bits, tokens...) and the per-page counts (host).  line = -1
         (find_line_number over an empty line list, as in the reference) unless `line_refiner` runs the refiner's line
         branch (craft_box_processor.py:150-217): then the merged line boxes are appended per page to `want_lines` (a
-        list) and every word gets its line number (line_processor.py:15-45)."""
+        list) and every word gets its line number (line_processor.py:15-45).  sink(block, counts): optional consumer of
+        the finished records, called with a host copy of every decode batch's rows (in order) as soon as they are final."""
         det = self.detect(pages_dev, preset, line_refiner=line_refiner, ready=ready)
         n = det["rects"].shape[0]
         rec = torch.empty((n, RECORD_HEAD + out_ld), dtype=torch.int32, device=pages_dev.device)
         if n:
-            tokens, lengths, scores = self.recognize_crops(pages_dev, det["rects"], det["page_idx"], beam, max_len_b, out_ld)
             rec[:, 0] = det["page_idx"]
             rec[:, 1:5] = det["rects"]
             rec[:, 5] = -1                       # find_line_number(lines_bboxes=[], box) == -1 (line_processor.py:21-45)
@@ -230,9 +233,15 @@ class PagePipeline:
                         ids[k:k + c] = _lines.find_line_numbers(det["lines"][j], rects_h[k:k + c])
                     k += c
                 rec[:, 5] = torch.from_numpy(ids).to(rec.device)
-            rec[:, 6] = lengths
-            rec[:, 7] = scores.view(torch.int32)
-            rec[:, RECORD_HEAD:] = tokens
+
+            def on_batch(i0, m, tokens, lengths, scores):
+                rec[i0:i0 + m, 6] = lengths[i0:i0 + m]
+                rec[i0:i0 + m, 7] = scores[i0:i0 + m].view(torch.int32)
+                rec[i0:i0 + m, RECORD_HEAD:] = tokens[i0:i0 + m]
+                if sink is not None:             # records of a finished decode batch leave for the host while the next one runs
+                    sink(rec[i0:i0 + m].cpu().numpy(), det["counts"])
+
+            self.recognize_crops(pages_dev, det["rects"], det["page_idx"], beam, max_len_b, out_ld, on_batch=on_batch)
         if want_lines is not None and line_refiner:
             want_lines.extend(det["lines"])
         return rec, det["counts"]
@@ -286,7 +295,7 @@ class PagePipeline:
         self._copy_stream.wait_stream(compute)           # pages_dev allocation ordering
         rec, counts = self.run_device(pages_dev, ready=ready, **kw)
         th.join()
-        return rec.cpu(), counts
+        return (rec.cpu() if kw.get("sink") is None else None), counts
 
     def run_host(self, pages_pinned, **kw):
         """Host pages ([n,H,W,3] u8, ideally pinned) -> records on the host; H2D and D2H inside."""
@@ -311,7 +320,7 @@ def records_to_words(rec, detok, page=None):
     lens = rec[:, 6]
     conf = np.exp(np.ascontiguousarray(rec[:, 7]).view(np.float32)).tolist()
     head = rec[:, :RECORD_HEAD].tolist()
-    toks = rec[:, RECORD_HEAD:].tolist()
+    toks = rec[:, RECORD_HEAD:RECORD_HEAD + max(1, min(out_ld, int(lens.max())))].tolist()    # only the columns in use
     out = []
     for h, t, c in zip(head, toks, conf):
         ln = h[6]
