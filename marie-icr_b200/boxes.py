@@ -69,6 +69,29 @@ class BoxProcessorCraftB200(BoxProcessor):
     def psm_multiline(self, image):
         return self._predict(image, "multiline")
 
+    def extract_bounding_boxes_batch(self, _id, key, images, psm=PSMode.SPARSE):
+        """extract_bounding_boxes for several images of ONE shape in one pass of the batched kernels (K1 / CRAFT in
+        micro-batches, one K5-K7 launch set for all): the region path of the engine (ocr_engine.py:223-414) groups its
+        padded region overlays by (mode, shape) and calls this once per group.  Returns one result tuple per image,
+        identical to what extract_bounding_boxes returns for it."""
+        if not len(images):
+            return []
+        if psm in (PSMode.RAW_LINE, PSMode.WORD) or self.line_refiner or len({im.shape for im in images}) != 1:
+            return [self.extract_bounding_boxes(_id, key, im, psm) for im in images]
+        if psm not in (PSMode.SPARSE, PSMode.LINE, PSMode.MULTI_LINE):
+            raise Exception(f"PSM mode not supported : {psm}")
+        pages = torch.from_numpy(np.ascontiguousarray(np.stack(images))).to(self.device)
+        det = self.pipeline.detect(pages, PSM_PRESETS[psm.value])
+        rects_all, boxes_all = det["rects"].cpu().numpy(), det["boxes"].cpu().numpy()
+        out, k = [], 0
+        for image, c in zip(images, det["counts"]):
+            rects, bboxes = rects_all[k:k + c], boxes_all[k:k + c]
+            k += c
+            fragments = [image[y:y + h + 1, x:x + w + 1].copy() for x, y, w, h in rects.tolist()]
+            out.append(([list(r) for r in rects.tolist()], fragments, [-1] * c,
+                        {"bboxes": bboxes, "polys": [b for b in bboxes], "heatmap": None}, []))
+        return out
+
     # ------------------------------------------------------------------ extract_bounding_boxes (:431-562)
     def extract_bounding_boxes(self, _id, key, img, psm=PSMode.SPARSE):
         if img is None:

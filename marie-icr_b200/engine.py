@@ -157,6 +157,31 @@ class OcrEngineB200:
         pages = {}
         for region in regions:
             pages.setdefault(region["pageIndex"], []).append(region)
+
+        def overlay_of(img, region):
+            x, y, w, h = region["x"], region["y"], region["w"], region["h"]
+            if w == 0 or h == 0 or y + h > img.shape[0] or x + w > img.shape[1]:
+                return None
+            overlay = np.full((h + 8, w + 8, 3), 255, np.uint8)
+            overlay[4:h + 4, 4:w + 4] = img[y:y + h, x:x + w]
+            mode = PSMode.from_value(region["mode"]) if "mode" in region else pms_mode
+            return overlay, mode, (mode.value, overlay.shape, hash_frames_fast([overlay]))
+
+        # pass 1: every overlay that still needs detection, grouped by (mode, shape) -> one batched detector pass per group
+        todo = {}
+        for page_index, page_regions in pages.items():
+            for region in page_regions:
+                ov = overlay_of(frames[page_index], region)
+                if ov is not None and ov[2] not in self.bbox_cache and ov[1] not in (PSMode.WORD, PSMode.RAW_LINE):
+                    todo.setdefault((ov[1], ov[0].shape), {})[ov[2]] = ov[0]
+        batch_fn = getattr(self.box_processor, "extract_bounding_boxes_batch", None)
+        if batch_fn is not None:
+            for (mode, _), group in todo.items():
+                keys = list(group)
+                for k, res in zip(keys, batch_fn(queue_id, checksum, [group[k] for k in keys], psm=mode)):
+                    self.bbox_cache[k] = res
+
+        # pass 2: the reference's loop (results of pass 1 are found in the cache)
         bbox_results_batch = []
         for page_index, page_regions in pages.items():
             img = frames[page_index]
@@ -166,16 +191,14 @@ class OcrEngineB200:
                 rid = region["id"]
                 region_ids.append(rid)
                 x, y, w, h = region["x"], region["y"], region["w"], region["h"]
-                if w == 0 or h == 0 or y + h > img.shape[0] or x + w > img.shape[1]:
+                ov = overlay_of(img, region)
+                if ov is None:
                     output.append({"id": rid, "text": "", "confidence": 0.0})
                     continue
                 xb, yb = min(x, xb), min(y, yb)
                 wb = max(x + w, xb + wb) - xb
                 hb = max(y + h, hb + yb) - yb
-                overlay = np.full((h + 8, w + 8, 3), 255, np.uint8)
-                overlay[4:h + 4, 4:w + 4] = img[y:y + h, x:x + w]
-                mode = PSMode.from_value(region["mode"]) if "mode" in region else pms_mode
-                key = (mode.value, overlay.shape, hash_frames_fast([overlay]))
+                overlay, mode, key = ov
                 if key not in self.bbox_cache:
                     self.bbox_cache[key] = self.box_processor.extract_bounding_boxes(queue_id, checksum, overlay, psm=mode)
                 bbox_results_batch.append(self.bbox_cache[key])

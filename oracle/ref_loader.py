@@ -436,3 +436,34 @@ def load_bpe():
 
     _cache["bpe"] = make
     return make
+
+
+def load_region_loop():
+    """OcrEngine.__process_extract_regions (marie/ocr/ocr_engine.py:223-414) extracted from the source (the module pulls
+    the whole `marie` package) and executed as a plain function over stand-in `self` / processors.  Returns
+    run(frames, regions, pms_mode, box_processor, icr_processor, PSMode) -> {"regions": [...], "extended": [...]}."""
+    if "region_loop" in _cache:
+        return _cache["region_loop"]
+    import ast
+    from itertools import chain
+    import numpy as np
+    iu = load_image_utils()
+    path = os.path.join(REF_ROOT, "marie", "ocr", "ocr_engine.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "OcrEngine")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name.endswith("__process_extract_regions"))
+    fn.name = "process_extract_regions"
+    for a in fn.args.args:                       # `box_processor: BoxProcessor` / `icr_processor: OcrProcessor`
+        a.annotation = None
+    code = compile(ast.Module(body=[fn], type_ignores=[]), path, "exec")
+
+    def run(frames, regions, pms_mode, box_processor, icr_processor, PSMode):
+        ns = dict(np=np, chain=chain, hash_frames_fast=iu.hash_frames_fast, crop_to_content=iu.crop_to_content, PSMode=PSMode,
+                  bbox_cache={}, encodeToBase64=lambda im: "")
+        exec(code, ns)
+        me = types.SimpleNamespace(logger=logging.getLogger("oracle.ref"))
+        return ns["process_extract_regions"](me, frames, "q", "c", pms_mode, regions, box_processor, icr_processor)
+
+    _cache["region_loop"] = run
+    return run

@@ -310,3 +310,85 @@ def test_string_path_fragments(tmp_path):
     cv2.imwrite(path, img)
     assert np.array_equal(_load_fragment(path), img) and np.array_equal(_load_fragment(img), img)
     assert _load_fragment(img[:, :, 0]).shape == (12, 17, 3)
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8f ranks 3 and 4
+class _CountingEngine:
+    """stands in for OcrEngineB200: returns MockOcrEngine-style page records (marie/ocr/mock_ocr_engine.py:46-52)"""
+
+    def __init__(self):
+        self.calls = 0
+
+    def extract(self, frames, pms_mode=None, coordinate_format=None, regions=None, **kw):
+        self.calls += 1
+        if regions:
+            return {"regions": [{"id": r["id"], "text": "X", "confidence": 0.5} for r in regions], "extended": []}
+        return [{"meta": {"imageSize": {"width": int(f.shape[1]), "height": int(f.shape[0])}, "page": i, "lang": "en",
+                          "lines": [-1], "lines_bboxes": [], "format": "xywh"},
+                 "words": [{"id": 0, "text": "W", "confidence": np.float32(0.25), "box": np.array([1, 2, 3, 4]), "line": np.int64(-1),
+                            "word_index": 0}],
+                 "lines": [{"line": 1, "wordids": [0], "text": "W", "bbox": [1, 2, 3, 4], "confidence": 0.25}]} for i, f in enumerate(frames)]
+
+
+def test_executor_wrapper_and_on_disk_json(tmp_path):
+    """TextExtractionExecutorB200.extract mirrors text_extraction_executor.py:125-260 (validation, payload handling,
+    envelope) and ocr_frames' JSON cache (components.py:643-656): the second request is served from
+    results/<prefix>.json, `force` re-runs, regions go to <prefix>.regions.json, numpy values are serialised."""
+    import json
+    from marie_icr_b200.executor import TextExtractionExecutorB200
+    eng = _CountingEngine()
+    ex = TextExtractionExecutorB200(engine=eng, workspace=str(tmp_path))
+    frames = [np.full((40, 30, 3), 255, np.uint8), np.full((40, 30, 3), 200, np.uint8)]
+    assert ex.extract([], {"job_id": "j"}) == {"error": "empty payload"}
+    with pytest.raises(ValueError, match="Job ID"):
+        ex.extract(frames, {})
+    assert ex.extract(frames, {"job_id": "j"}) == {"error": "empty payload"}
+    p = {"job_id": "j1", "ref_id": "doc_0001.tif", "ref_type": "pid", "payload": {"mode": "sparse", "args": {"return_ocr": True}}}
+    r = ex.extract(frames, p)
+    assert r["status"] == "succeeded" and r["metadata"]["pages"] == "2" and eng.calls == 1
+    assert r["metadata"]["ocr"][1]["words"][0]["box"] == [1, 2, 3, 4] and r["metadata"]["ocr"][1]["meta"]["page"] == 1
+    path = tmp_path / "generators" / "pid" / "doc_0001" / "results" / "doc_0001.json"
+    on_disk = json.loads(path.read_text())
+    assert on_disk == r["metadata"]["ocr"]
+    assert path.read_text().startswith('[\n  {\n    "meta": {')            # store_json_object formatting (json.py:19-30)
+    assert ex.extract(frames, p)["metadata"]["ocr"] == on_disk and eng.calls == 1            # served from disk
+    ex.extract(frames, {**p, "force": True})
+    assert eng.calls == 2
+    p2 = {**p, "payload": {"regions": [{"id": "7", "pageIndex": "0", "x": "1", "y": 2, "w": 5, "h": 5}], "return_ocr": True}}
+    r2 = ex.extract(frames, p2)
+    assert r2["metadata"]["ocr"]["regions"] == [{"id": "7", "text": "X", "confidence": 0.5}]
+    assert (path.parent / "doc_0001.regions.json").exists()
+    assert "ocr" not in ex.extract(frames, {**p, "payload": {}})["metadata"]
+    bad = ex.extract(frames, {**p, "payload": {"regions": [{"id": "a", "pageIndex": 0, "x": 0, "y": 0, "w": 1, "h": 1}]}})
+    assert bad["status"] == "error" and "invalid literal" in bad["error"][0]
+
+
+def test_frames_from_tiff_and_burst(tmp_path):
+    """Multi-page TIFF -> frames (marie/utils/docs.py:201-256,372-379) and burst to one bitonal Group-4 TIFF per page
+    named <prefix>_<page:05>.<suffix> (components.py:529-565)."""
+    import cv2
+    from PIL import Image
+    from marie_icr_b200.ingest import burst_frames, document_type, frames_from_file, load_image
+    rng = np.random.default_rng(4)
+    pages = [rng.integers(0, 256, (50, 40, 3), dtype=np.uint8), rng.integers(0, 256, (50, 40), dtype=np.uint8),
+             rng.integers(0, 256, (30, 60, 3), dtype=np.uint8)]
+    src = str(tmp_path / "doc.tif")
+    assert cv2.imwritemulti(src, pages)
+    assert document_type(src) == "tiff"
+    frames = frames_from_file(src)
+    assert [f.shape for f in frames] == [(50, 40, 3), (50, 40, 3), (30, 60, 3)]
+    assert np.array_equal(frames[0], pages[0][:, :, ::-1])                       # the reference's BGR2RGB pass over cv2's frames
+    assert np.array_equal(frames[1], np.repeat(pages[1][:, :, None], 3, 2))
+    png = str(tmp_path / "one.png")
+    cv2.imwrite(png, pages[2])
+    ok, single = load_image(png)
+    assert ok and len(single) == 1 and np.array_equal(single[0], pages[2][:, :, ::-1])   # PIL RGB
+    with pytest.raises(FileNotFoundError):
+        frames_from_file(str(tmp_path / "missing.tif"))
+    names = burst_frames("s3://bucket/doc.tif", frames, str(tmp_path / "assets"))
+    assert [n.split("/")[-1] for n in names] == ["doc_00001.tif", "doc_00002.tif", "doc_00003.tif"]
+    im = Image.open(names[0])
+    assert im.mode == "1" and im.size == (40, 50) and im.info.get("compression") == "group4"
+    before = [os.path.getmtime(n) for n in names]
+    burst_frames("s3://bucket/doc.tif", frames, str(tmp_path / "assets"))         # same page count: skipped
+    assert before == [os.path.getmtime(n) for n in names]

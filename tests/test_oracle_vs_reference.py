@@ -253,3 +253,50 @@ def test_detokenizer_against_reference_bpe_decode(tmp_path):
         # fairseq Dictionary.string with extra_symbols_to_ignore = {eos}: bos / eos dropped, everything else joined by ' '
         hypo_str = " ".join(detok.symbols[t] for t in ids if t not in (0, 2))
         assert detok.decode(ids) == ref.decode(hypo_str), ids
+
+
+def test_convert_frames_and_json_store_against_reference(tmp_path):
+    """ingest.convert_frames / load_image's TIFF branch and executor.store_json_object against the reference's own
+    functions (marie/utils/docs.py:183-256 extracted from the source — the module imports PyPDF4 / docarray;
+    marie/utils/json.py:19-30 loaded behind a stub for its numpy encoder import)."""
+    import ast
+    import json
+    import os
+    import cv2
+    from marie_icr_b200 import ingest
+    from marie_icr_b200.executor import store_json_object
+    path = os.path.join(ref_loader.REF_ROOT, "marie", "utils", "docs.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("convert_frames", "load_image")]
+    for fn in fns:
+        fn.returns = None
+    from PIL import Image
+    ns = dict(cv2=cv2, np=np, Image=Image, List=list, get_document_type=lambda p: ingest.document_type(p), load_pdf_frames=None)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    rng = np.random.default_rng(8)
+    pages = [rng.integers(0, 256, (21, 33, 3), dtype=np.uint8), rng.integers(0, 256, (21, 33), dtype=np.uint8)]
+    src = str(tmp_path / "d.tif")
+    cv2.imwritemulti(src, pages)
+    ok_ref, ref_frames = ns["load_image"](src)
+    ok, frames = ingest.load_image(src)
+    assert ok == ok_ref and len(frames) == len(ref_frames) and all(np.array_equal(a, b) for a, b in zip(frames, ref_frames))
+    png = str(tmp_path / "p.png")
+    cv2.imwrite(png, pages[0])
+    assert np.array_equal(ingest.load_image(png)[1][0], ns["load_image"](png)[1][0])
+    # store_json_object: same bytes as the reference writes for a page record holding numpy values
+    spec_path = os.path.join(ref_loader.REF_ROOT, "marie", "utils", "json.py")
+    with open(spec_path) as f:
+        jtree = ast.parse(f.read())
+    keep = [n for n in jtree.body if isinstance(n, ast.FunctionDef) and n.name == "store_json_object"]
+    enc_path = os.path.join(ref_loader.REF_ROOT, "marie", "numpyencoder.py")
+    enc_ns = {}
+    src_enc = open(enc_path).read().replace("np.float_, ", "").replace("np.complex_, ", "")   # aliases removed in NumPy 2
+    exec(compile(src_enc, enc_path, "exec"), enc_ns)
+    jns = dict(json=json, os=os, EnhancedJSONEncoder=enc_ns["NumpyEncoder"])
+    exec(compile(ast.Module(body=keep, type_ignores=[]), spec_path, "exec"), jns)
+    record = [{"meta": {"imageSize": {"width": np.int64(3), "height": 4}, "page": 0}, "words": [{"id": np.int32(0), "text": "É", "confidence": np.float32(0.5), "box": np.array([1, 2, 3, 4])}]}]
+    a, b = str(tmp_path / "a.json"), str(tmp_path / "b.json")
+    jns["store_json_object"](record, a)
+    store_json_object(record, b)
+    assert open(a).read() == open(b).read()

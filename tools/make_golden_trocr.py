@@ -172,10 +172,82 @@ def make_e2e(dtype="fp16", beam=1):
     print("wrote", path, len(boxes), "words")
 
 
+def make_regions(dtype="fp16"):
+    """Region / field extraction golden: the REFERENCE's own __process_extract_regions (marie/ocr/ocr_engine.py:223-414,
+    executed from its source) over oracle-backed processors — detection = oracle chain + the reference's own per-box loop
+    (craft_box_processor.py:499-537), recognition = oracle TrOCR behind the reference's OcrProcessor.recognize."""
+    import math
+    from oracle import ref_loader
+    sys.path.insert(0, os.path.join(ROOT, "marie-icr_b200"))
+    from bpe import SyntheticDetokenizer
+    from plugin_api import PSMode
+    dt = DT[dtype]
+    geom = dict(height=660, width=510, scale=0.8, line_pitch=48, gap=24, margin=30)
+    frames = [synth.synth_page(i, **geom)[0] for i in range(2)]
+    rects0 = oracle_detect(frames[0], dt)
+    sd, cfg = trocr_weights("base", dt)
+    detok = SyntheticDetokenizer()
+    box_loop = ref_loader.load_box_loop()
+    margins_log = []
+
+    class Box:
+        def extract_bounding_boxes(self, _id, key, img, psm=PSMode.SPARSE):
+            if psm in (PSMode.WORD, PSMode.RAW_LINE):                          # craft_box_processor.py:453-476
+                return [[0, 0, img.shape[1], img.shape[0]]], [img.copy()], [0], dict(), []
+            preset = {"sparse": SPARSE, "line": (0.4, 0.2, 0.3), "multiline": (0.6, 0.3, 0.3)}[psm.value]
+            x, ratio = resample.craft_input(img)
+            xin = torch.from_numpy(np.ascontiguousarray(x)).to(dt).float().permute(2, 0, 1)[None]
+            with torch.no_grad():
+                y, _ = craft_net.craft_forward(sw.glyph_craft_state(0), xin)
+            det, _, _ = craft_post.det_boxes_cv(y[0, ..., 0].numpy(), y[0, ..., 1].numpy(), *preset)
+            adj = craft_post.adjust_result_coordinates([b.copy() for b in det], 1 / ratio, 1 / ratio)
+            rects, frags, lines = box_loop(img, list(adj), [], "/tmp/fragments/regions")
+            return [list(map(int, r)) for r in rects], frags, lines, {"bboxes": adj}, []
+
+    Ref = ref_loader.load_ocr_processor()
+
+    class Icr(Ref):
+        def __init__(self):
+            pass
+
+        def is_available(self):
+            return True
+
+        def recognize_from_fragments(self, frags, **kw):
+            chw = torch.stack([torch.from_numpy(np.ascontiguousarray(resample.fragment_to_input(f))).to(dt).float() for f in frags])
+            with torch.no_grad():
+                hyps, margins = search(sd, cfg, trocr.encoder_forward(sd, cfg, chw), 1, 200)
+            margins_log.append([float(m) for m in margins])
+            return [{"confidence": round(round(math.exp(float(np.float32(h["score"]))), 6), 4), "id": f"img-{k}",
+                     "text": detok.decode(h["tokens"].tolist()).upper()} for k, h in enumerate(hyps)]
+
+    regions = []
+    for k in (0, 3, 7, 12, 20, 31):                                        # single words as WORD-mode fields
+        x, y, w, h = (int(v) for v in rects0[k])
+        regions.append({"id": f"w{k}", "pageIndex": 0, "x": x, "y": y, "w": w, "h": h, "mode": "word"})
+    regions.append({"id": "line", "pageIndex": 0, "x": 10, "y": 20, "w": 480, "h": 90, "mode": "raw_line"})
+    # page 1: detector-mode regions (two of one shape -> one batched detector pass on the device) and the skipped-region quirk
+    regions.append({"id": "s0", "pageIndex": 1, "x": 8, "y": 24, "w": 200, "h": 64, "mode": "sparse"})
+    regions.append({"id": "s1", "pageIndex": 1, "x": 8, "y": 120, "w": 200, "h": 64, "mode": "sparse"})
+    regions.append({"id": "zero", "pageIndex": 1, "x": 5, "y": 5, "w": 0, "h": 10})
+    regions.append({"id": "oob", "pageIndex": 1, "x": 400, "y": 600, "w": 300, "h": 100})
+    result = ref_loader.load_region_loop()([f.copy() for f in frames], regions, PSMode.SPARSE, Box(), Icr(), PSMode)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden import jsonable
+    out = dict(page_geometry=geom, dtype=dtype, regions=regions, margins=margins_log,
+               result={"regions": result["regions"], "extended": [jsonable(e) for e in result["extended"]]})
+    path = os.path.join(OUT, f"regions_{dtype}.json")
+    with open(path, "w") as f:
+        json.dump(out, f)
+    print("wrote", path, result["regions"])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     os.chdir("/tmp")
     if sys.argv[1] == "scale":
         make_scale(sys.argv[2], sys.argv[3], int(sys.argv[4]))
+    elif sys.argv[1] == "regions":
+        make_regions(*(sys.argv[2:3] or ["fp16"]))
     else:
         make_e2e(*(sys.argv[2:3] or ["fp16"]), beam=int(sys.argv[3]) if len(sys.argv) > 3 else 1)
