@@ -64,8 +64,9 @@ def test_beam5_matches_oracle_tiny(cuda_ctx):
     sd = _setup(cfg, torch.float16, 11)
     patches, _ = _inputs(_fragments(9, seed=12), torch.float16)
     enc = ops.trocr_encode(patches)
+    margins = []
     with torch.no_grad():
-        ref = trocr.generate(sd, cfg, enc.float().cpu(), beam=5, max_len_b=20)
+        ref = trocr.generate(sd, cfg, enc.float().cpu(), beam=5, max_len_b=20, margins=margins)
     toks, lens, scores, _ = ops.trocr_decode(enc, beam=5, max_len_b=20)
     exact = 0
     for i, h in enumerate(ref):
@@ -74,13 +75,9 @@ def test_beam5_matches_oracle_tiny(cuda_ctx):
             exact += 1
             assert abs(float(scores[i]) - h[0]["score"]) <= 2e-2
             continue
-        # beam protocol of tests/test_parity_scale_gpu.py: a differing top hypothesis must be a near-tied finalist of the
-        # oracle's, or score at least as well as the oracle's best
-        alt = [k for k, hk in enumerate(h) if hk["tokens"].tolist() == got]
-        if alt:
-            assert h[0]["score"] - h[alt[0]]["score"] <= 2e-2, (i, got, h[0]["score"], h[alt[0]]["score"])
-        else:
-            assert float(scores[i]) >= h[0]["score"] - 2e-2, (i, got, float(scores[i]), h[0]["score"])
+        # margin protocol (tests/test_parity_scale_gpu.py): a differing top hypothesis needs a close call somewhere on the
+        # oracle's search path — two of the 11 best cumulative candidate scores within 0.02 nat at some step
+        assert margins[i] <= 0.02, (i, got, h[0]["tokens"].tolist(), margins[i])
     print(f"beam 5 (tiny): {exact}/{len(ref)} top hypotheses identical")
 
 
