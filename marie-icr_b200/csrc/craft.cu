@@ -10,6 +10,7 @@
 // Skip taps (SURVEY.md hard part 9): relu2_2 / relu3_2 / relu4_3 are post-ReLU (in-place ReLU of the next slice),
 // relu5_3 = BN(conv5_2) without ReLU, fc6/fc7 have no activation.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include "blob.cuh"
 
 struct CraftLayer {
@@ -77,17 +78,20 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const bf16* __restrict__ i
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int c8 = 0; c8 < 8; ++c8) {
-        float4 a0 = *reinterpret_cast<const float4*>(sb + c8 * 8);
-        float4 a1 = *reinterpret_cast<const float4*>(sb + c8 * 8 + 4);
+        // packed fp32 arithmetic (FFMA2): two output channels per instruction, same per-channel operation order
+        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(sb + c8 * 8);
+        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(sb + c8 * 8 + 4);
+        f32x2 p0 = b01.x, p1 = b01.y, p2 = b23.x, p3 = b23.y;
 #pragma unroll
         for (int k = 0; k < 27; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * 64 + c8 * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * 64 + c8 * 8 + 4);
-            a0.x = fmaf(v[k], w0.x, a0.x); a0.y = fmaf(v[k], w0.y, a0.y);
-            a0.z = fmaf(v[k], w0.z, a0.z); a0.w = fmaf(v[k], w0.w, a0.w);
-            a1.x = fmaf(v[k], w1.x, a1.x); a1.y = fmaf(v[k], w1.y, a1.y);
-            a1.z = fmaf(v[k], w1.z, a1.z); a1.w = fmaf(v[k], w1.w, a1.w);
+            const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(sw + k * 64 + c8 * 8);
+            const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(sw + k * 64 + c8 * 8 + 4);
+            const f32x2 vv = pk2(v[k], v[k]);
+            p0 = fma2(vv, w01.x, p0); p1 = fma2(vv, w01.y, p1);
+            p2 = fma2(vv, w23.x, p2); p3 = fma2(vv, w23.y, p3);
         }
+        float4 a0, a1;
+        upk2(p0, a0.x, a0.y); upk2(p1, a0.z, a0.w); upk2(p2, a1.x, a1.y); upk2(p3, a1.z, a1.w);
         uint4 r;
         r.x = pack2(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f), f16);
         r.y = pack2(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f), f16);

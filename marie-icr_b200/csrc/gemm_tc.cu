@@ -30,12 +30,16 @@ constexpr int NUM_THREADS = 384;          // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 
 constexpr int EPI_WARPS = 8;
 constexpr int STAGE_TILE_BYTES = 32 * 32 * 4;   // per epilogue warp: 32 rows x 32 fp32 columns
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int HALO_ROWS = BLOCK_M + 2;                  // 3x3 convolutions: one A tile with a one-pixel halo serves dx = -1, 0, +1
+constexpr int HALO_BYTES = HALO_ROWS * BLOCK_K * 2;     // 16640 B delivered by the TMA
+constexpr int A_HALO_STAGE_BYTES = 17 * 1024;           // ... in a 1024-byte aligned slot
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 512;   // 2*8 ring + 4 accumulator mbarriers, the TMEM pointer slot, 8 per-warp residual mbarriers;
                                  // 512 keeps the staging tiles aligned for the 64-byte TMA swizzle
 constexpr int RES_BAR_SLOT = 2 * MAX_STAGES + 5;   // first of the EPI_WARPS residual mbarriers (u64 slots after the pointer)
+constexpr int BRES_BAR_SLOT = RES_BAR_SLOT + EPI_WARPS;   // "resident weights have landed"
 
 struct KParams {
     int n, h, w;
@@ -59,6 +63,10 @@ struct KParams {
     const float* ln_c;        // LNF: per column sum_k W'[n, k]
     unsigned int* diag;
     unsigned backoff;         // ns slept between polls of the long waits (0 = poll continuously)
+    // 3x3 (dilation 1) convolutions: a stage holds the A tile of one image row WITH a one-pixel halo (130 pixel rows) and
+    // the three dx taps are three MMAs on the same tile, the operand start shifted by one 128-byte row each — a third of
+    // the A traffic from L2.  bres: the whole weight matrix (9 taps x kb blocks) stays resident in shared memory.
+    int halo, bres;
 };
 
 // exact-erf GELU (timm nn.GELU).  erf(z) = 1 - 2^q(z) for z in [0, 3.92] with a degree-6 polynomial q fitted to
@@ -138,12 +146,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                                                ~static_cast<uintptr_t>(1023));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int b_stage_bytes = (CG2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
+    const int b_slot_bytes = (CG2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
+    const int b_stage_bytes = p.halo ? (p.bres ? 0 : 3 * b_slot_bytes) : b_slot_bytes;
+    const int a_stage_bytes = p.halo ? A_HALO_STAGE_BYTES : A_STAGE_BYTES;
     const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
     const bool leader = crank == 0;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + p.stages * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage_bytes);
+    uint8_t* smem_b = smem + p.stages * a_stage_bytes;
+    uint8_t* smem_bres = smem_b + p.stages * b_stage_bytes;            // resident weights (halo mode, small layers)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bres + (p.bres ? 9 * (p.kb0 + p.kb1) * b_slot_bytes : 0));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + MAX_STAGES;
     uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;
@@ -169,6 +180,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         if (TMAOUT && RES)
             for (int i = 0; i < EPI_WARPS; ++i) mbar_init(smem_u32(&bars[RES_BAR_SLOT + i]), 1);
+        mbar_init(smem_u32(&bars[BRES_BAR_SLOT]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -195,14 +207,20 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int kb_per_tap = p.kb0 + p.kb1;
-    const int k_iters = p.taps * kb_per_tap;
+    const int k_iters = (p.halo ? 3 : p.taps) * kb_per_tap;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one lane)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+            const uint32_t tx_bytes = p.halo ? HALO_BYTES + b_stage_bytes : A_STAGE_BYTES + b_stage_bytes;
+            if (p.halo && p.bres && tile0 < total_tiles) {         // the whole weight matrix, once per CTA
+                const uint32_t rb = smem_u32(&bars[BRES_BAR_SLOT]);
+                mbar_arrive_expect_tx(rb, 9 * kb_per_tap * b_slot_bytes);
+                for (int i = 0; i < 9 * kb_per_tap; ++i)
+                    tma_load_2d(smem_u32(smem_bres + i * b_slot_bytes), &tmB, rb, i * BLOCK_K, 0);
+            }
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int bt = tile / tiles_per_batch;
                 const int trem = tile - bt * tiles_per_batch;
@@ -215,6 +233,28 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const int nn = rest / p.h;
                 const int w0 = wt * BLOCK_M;
                 const int acol = bt * p.a_col_stride, wrow = bt * p.w_row_stride + (CG2 ? (int)crank * (p.block_n / 2) : 0);
+                if (p.halo) {
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        for (int kb = 0; kb < kb_per_tap; ++kb) {
+                            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.diag, 1, p.backoff);
+                            const uint32_t fb = smem_u32(&full_bar[stage]);
+                            const uint32_t sa = smem_u32(smem_a + stage * a_stage_bytes);
+                            mbar_arrive_expect_tx(fb, tx_bytes);
+                            if (kb < p.kb0)
+                                tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K + acol, w0 - 1, hh + dyi - 1, nn);
+                            else
+                                tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 - 1, hh + dyi - 1, nn);
+                            if (!p.bres) {
+                                const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
+                                for (int dxi = 0; dxi < 3; ++dxi)
+                                    tma_load_2d(sb + dxi * b_slot_bytes, &tmB, fb, ((dyi * 3 + dxi) * kb_per_tap + kb) * BLOCK_K,
+                                                nt * p.block_n + wrow);
+                            }
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < p.taps; ++tap) {
                     const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
                     const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
@@ -255,6 +295,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
+            bool bres_ready = false;
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1, p.diag, 2);
                 tcgen05_fence_after();
@@ -262,6 +303,33 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase, p.diag, 3);
                     tcgen05_fence_after();
+                    if (p.halo) {
+                        if (p.bres && !bres_ready) {
+                            mbar_wait(smem_u32(&bars[BRES_BAR_SLOT]), 0, p.diag, 6);
+                            tcgen05_fence_after();
+                            bres_ready = true;
+                        }
+                        const uint32_t sa = smem_u32(smem_a + stage * a_stage_bytes);
+                        const int dyi = it / kb_per_tap, kb = it - dyi * kb_per_tap;
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            // rows dxi .. dxi+127 of the halo tile: the operand starts one 128-byte row further.  The 128-byte
+                            // swizzle is a function of the absolute shared-memory address (TMA wrote it that way), so the
+                            // descriptor needs no base offset (measured: setting it breaks the result)
+                            const uint64_t adesc = make_smem_desc(sa + (uint32_t)dxi * 128u);
+                            const uint32_t sbp = p.bres ? smem_u32(smem_bres + ((dyi * 3 + dxi) * kb_per_tap + kb) * b_slot_bytes)
+                                                        : smem_u32(smem_b + stage * b_stage_bytes + dxi * b_slot_bytes);
+                            const uint64_t bdesc = make_smem_desc(sbp);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                          (it > 0 || dxi > 0 || k > 0) ? 1u : 0u);
+                        }
+                        tcgen05_commit(smem_u32(&empty_bar[stage]));
+                        if (it == k_iters - 1) tcgen05_commit(smem_u32(&tmem_full_bar[as]));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes));
 #pragma unroll
@@ -628,12 +696,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC activation map: dims {C, W, H, N}, box {64, 128, 1, 1}
-int encode_act_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int c, int ld, int n, int h, int w, int f16) {
+int encode_act_map(mb_ctx* ctx, CUtensorMap* m, const bf16* base, int c, int ld, int n, int h, int w, int f16, int box_rows = BLOCK_M) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
-    cuuint32_t box[4] = {BLOCK_K, BLOCK_M, 1, 1};
+    cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -797,10 +865,25 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     if (gemm2_env < 0) { const char* e = getenv("MB_GEMM2"); gemm2_env = (e && e[0] == '1') ? 1 : 0; }
     const bool cg2 = gemm2_env == 1 && g.ln_stats == nullptr && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
                      (g.batches <= 1);
-    const int stage_bytes = A_STAGE_BYTES + (cg2 ? block_n / 2 : block_n) * BLOCK_K * 2;
+    // halo mode: 3x3 / dilation 1 convolutions (one A load per image row instead of three); small layers also keep the whole
+    // weight matrix in shared memory.  MB_HALO=0 switches it off (A/B timing).
+    const char* halo_env = getenv("MB_HALO");
+    const int b_slot = (cg2 ? block_n / 2 : block_n) * BLOCK_K * 2;
+    const int kb_tap = (g.c0 + g.c1) / BLOCK_K;
+    p.halo = (g.taps == 9 && g.dil == 1 && !cg2 && (g.batches <= 1) && !(halo_env && halo_env[0] == '0')) ? 1 : 0;
+    const int bres_bytes = 9 * kb_tap * b_slot;
+    const char* bres_env = getenv("MB_BRES");
+    p.bres = (p.halo && p.n_tiles == 1 && bres_bytes <= 80 * 1024 && !(bres_env && bres_env[0] == '0')) ? 1 : 0;
+    const int stage_bytes = p.halo ? A_HALO_STAGE_BYTES + (p.bres ? 0 : 3 * b_slot) : A_STAGE_BYTES + b_slot;
     const int bar_bytes = BAR_BYTES + EPI_WARPS * STAGE_TILE_BYTES;
-    int stages = (SMEM_LIMIT - 1024 - bar_bytes) / stage_bytes;
+    int stages = (SMEM_LIMIT - 1024 - bar_bytes - (p.bres ? bres_bytes : 0)) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (p.halo && stages < 2) {                       // wide N tiles: three B slots per stage do not leave a ring
+        p.halo = p.bres = 0;
+        stages = (SMEM_LIMIT - 1024 - bar_bytes) / (A_STAGE_BYTES + b_slot);
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+    }
+    const int stage_bytes_final = p.halo ? stage_bytes : A_STAGE_BYTES + b_slot;
     p.stages = stages;
     p.bias = g.bias; p.act = g.act;
     p.residual = g.residual; p.res_ld = g.res_ld;
@@ -828,13 +911,14 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
 
     CUtensorMap tmA0, tmA1, tmB, tmOut, tmRes;
     const int a0c = g.batches > 1 ? g.a0_ld : g.c0;
-    int rc = cached_map(ctx, &tmA0, MapKey{g.a0, a0c, g.a0_ld, 0, g.n, g.h, g.w, ctx->f16},
-                        [&](CUtensorMap* m) { return encode_act_map(ctx, m, g.a0, a0c, g.a0_ld, g.n, g.h, g.w, ctx->f16); });
+    const int a_rows = p.halo ? HALO_ROWS : BLOCK_M;
+    int rc = cached_map(ctx, &tmA0, MapKey{g.a0, a0c, g.a0_ld, p.halo ? 3 : 0, g.n, g.h, g.w, ctx->f16},
+                        [&](CUtensorMap* m) { return encode_act_map(ctx, m, g.a0, a0c, g.a0_ld, g.n, g.h, g.w, ctx->f16, a_rows); });
     if (rc) return rc;
     if (g.c1 > 0) {
         MB_REQUIRE(ctx, g.a1 != nullptr, "tap_gemm: c1>0 but a1 null");
-        rc = cached_map(ctx, &tmA1, MapKey{g.a1, g.c1, g.a1_ld, 0, g.n, g.h, g.w, ctx->f16},
-                        [&](CUtensorMap* m) { return encode_act_map(ctx, m, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w, ctx->f16); });
+        rc = cached_map(ctx, &tmA1, MapKey{g.a1, g.c1, g.a1_ld, p.halo ? 3 : 0, g.n, g.h, g.w, ctx->f16},
+                        [&](CUtensorMap* m) { return encode_act_map(ctx, m, g.a1, g.c1, g.a1_ld, g.n, g.h, g.w, ctx->f16, a_rows); });
         if (rc) return rc;
     } else {
         tmA1 = tmA0;
@@ -857,7 +941,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         }
     }
 
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes_final + (p.bres ? bres_bytes : 0) + bar_bytes;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const KParams);
     KernelFn fn = nullptr;
