@@ -505,9 +505,11 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             decode(item, q0, head, row_base);
             const int qb = it & 1;
             const uint32_t qpar = (uint32_t)(((it >> 1) & 1) ^ 1);
-            if (lane == 0) {
-                mbar_wait(smem_u32(&tail_empty[qb]), qpar, p.diag, 21);
-                mbar_wait(smem_u32(&q_empty[qb]), qpar, p.diag, 22);
+            // the whole warp walks the schedule (waits included); one elected lane issues — coordinates / addresses then live
+            // in uniform registers instead of going through an R2UR waterfall per TMA / MMA instruction
+            mbar_wait(smem_u32(&tail_empty[qb]), qpar, p.diag, 21);
+            mbar_wait(smem_u32(&q_empty[qb]), qpar, p.diag, 22);
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(smem_u32(&q_full[qb]), TILE_BYTES);
                 tma_load_2d(smem_u32(sQ + qb * TILE_BYTES), &tmQKV, smem_u32(&q_full[qb]), head * HD, row_base + q0);
             }
@@ -520,26 +522,32 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                              "l"(g) : "memory");
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&tail_full[qb])) : "memory");
-            if (lane == 0) {
+            {
                 auto load_k = [&](int j) {
                     mbar_wait(smem_u32(&k_empty[ks]), (kuse & 1) ^ 1, p.diag, 23);
-                    mbar_arrive_expect_tx(smem_u32(&k_full[ks]), KV_BYTES);
-                    tma_load_2d(smem_u32(sK + ks * KV_BYTES), &tmKV, smem_u32(&k_full[ks]), p.D + head * HD, row_base + j * KT);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(smem_u32(&k_full[ks]), KV_BYTES);
+                        tma_load_2d(smem_u32(sK + ks * KV_BYTES), &tmKV, smem_u32(&k_full[ks]), p.D + head * HD, row_base + j * KT);
+                    }
+                    __syncwarp();
                     if (++ks == PK_STAGES) { ks = 0; ++kuse; }
                 };
                 load_k(0);
                 for (int j = 0; j < n_tiles; ++j) {
                     if (j + 1 < n_tiles) load_k(j + 1);       // K runs one tile ahead of V: S(j+1) is issued before P V (j)
                     mbar_wait(smem_u32(&v_empty[vs]), (vuse & 1) ^ 1, p.diag, 24);
-                    mbar_arrive_expect_tx(smem_u32(&v_full[vs]), KV_BYTES);
-                    tma_load_2d(smem_u32(sV + vs * KV_BYTES), &tmKV, smem_u32(&v_full[vs]), 2 * p.D + head * HD, row_base + j * KT);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(smem_u32(&v_full[vs]), KV_BYTES);
+                        tma_load_2d(smem_u32(sV + vs * KV_BYTES), &tmKV, smem_u32(&v_full[vs]), 2 * p.D + head * HD, row_base + j * KT);
+                    }
+                    __syncwarp();
                     if (++vs == PV_STAGES) { vs = 0; ++vuse; }
                 }
             }
             __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t ab_fmt = F16 ? 0u : ((1u << 7) | (1u << 10));
             const uint32_t idesc_qk = (1u << 4) | ab_fmt | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
             const uint32_t idesc_pv = (1u << 4) | ab_fmt | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
@@ -552,11 +560,14 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                 tcgen05_fence_after();
                 const uint64_t kd = make_smem_desc(smem_u32(sK + ks * KV_BYTES));
                 const uint32_t d = tmem_base + (uint32_t)((jj & 1) * KT);
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(d, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-                tcgen05_commit(smem_u32(&k_empty[ks]));
-                tcgen05_commit(smem_u32(&s_full[jj & 1]));
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_bf16(d, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+                    tcgen05_commit(smem_u32(&k_empty[ks]));
+                    tcgen05_commit(smem_u32(&s_full[jj & 1]));
+                }
+                __syncwarp();
                 if (++ks == PK_STAGES) { ks = 0; ++kuse; }
             };
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -573,12 +584,15 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                     tcgen05_fence_after();
                     const uint64_t vd = make_smem_desc(smem_u32(sV + vs * KV_BYTES));
                     const uint64_t pd0 = make_smem_desc(smem_u32(sP + (jt & 1) * P_BYTES));
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < KT / 16; ++k)
-                        umma_bf16(tmem_base + O_COL, pd0 + (uint64_t)(2 * k), vd + (uint64_t)((k * 2048) >> 4), idesc_pv,
-                                  (j > 0 || k > 0) ? 1u : 0u);
-                    tcgen05_commit(smem_u32(&v_empty[vs]));
-                    tcgen05_commit(smem_u32(&pv_done[jt & 1]));
+                        for (int k = 0; k < KT / 16; ++k)
+                            umma_bf16(tmem_base + O_COL, pd0 + (uint64_t)(2 * k), vd + (uint64_t)((k * 2048) >> 4), idesc_pv,
+                                      (j > 0 || k > 0) ? 1u : 0u);
+                        tcgen05_commit(smem_u32(&v_empty[vs]));
+                        tcgen05_commit(smem_u32(&pv_done[jt & 1]));
+                    }
+                    __syncwarp();
                     if (++vs == PV_STAGES) { vs = 0; ++vuse; }
                 }
             }

@@ -210,16 +210,19 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int k_iters = (p.halo ? 3 : p.taps) * kb_per_tap;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (one lane)
-        if (lane == 0) {
+        // ------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = p.halo ? HALO_BYTES + b_stage_bytes : A_STAGE_BYTES + b_stage_bytes;
             if (p.halo && p.bres && tile0 < total_tiles) {         // the whole weight matrix, once per CTA
                 const uint32_t rb = smem_u32(&bars[BRES_BAR_SLOT]);
-                mbar_arrive_expect_tx(rb, 9 * kb_per_tap * b_slot_bytes);
-                for (int i = 0; i < 9 * kb_per_tap; ++i)
-                    tma_load_2d(smem_u32(smem_bres + i * b_slot_bytes), &tmB, rb, i * BLOCK_K, 0);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(rb, 9 * kb_per_tap * b_slot_bytes);
+                    for (int i = 0; i < 9 * kb_per_tap; ++i)
+                        tma_load_2d(smem_u32(smem_bres + i * b_slot_bytes), &tmB, rb, i * BLOCK_K, 0);
+                }
+                __syncwarp();
             }
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int bt = tile / tiles_per_batch;
@@ -239,17 +242,21 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.diag, 1, p.backoff);
                             const uint32_t fb = smem_u32(&full_bar[stage]);
                             const uint32_t sa = smem_u32(smem_a + stage * a_stage_bytes);
-                            mbar_arrive_expect_tx(fb, tx_bytes);
-                            if (kb < p.kb0)
-                                tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K + acol, w0 - 1, hh + dyi - 1, nn);
-                            else
-                                tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 - 1, hh + dyi - 1, nn);
-                            if (!p.bres) {
-                                const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
-                                for (int dxi = 0; dxi < 3; ++dxi)
-                                    tma_load_2d(sb + dxi * b_slot_bytes, &tmB, fb, ((dyi * 3 + dxi) * kb_per_tap + kb) * BLOCK_K,
-                                                nt * p.block_n + wrow);
+                            const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
+                            if (elect_one_sync()) {
+                                mbar_arrive_expect_tx(fb, tx_bytes);
+                                if (kb < p.kb0)
+                                    tma_load_4d(sa, &tmA0, fb, kb * BLOCK_K + acol, w0 - 1, hh + dyi - 1, nn);
+                                else
+                                    tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 - 1, hh + dyi - 1, nn);
+                                if (!p.bres) {
+#pragma unroll
+                                    for (int dxi = 0; dxi < 3; ++dxi)
+                                        tma_load_2d(sb + dxi * b_slot_bytes, &tmB, fb, ((dyi * 3 + dxi) * kb_per_tap + kb) * BLOCK_K,
+                                                    nt * p.block_n + wrow);
+                                }
                             }
+                            __syncwarp();
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -263,6 +270,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         const uint32_t fb = smem_u32(&full_bar[stage]);
                         const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                         const uint32_t sb = smem_u32(smem_b + stage * b_stage_bytes);
+                        if (elect_one_sync()) {
                         if (CG2) {
                             // the leader's barrier collects the bytes of both CTAs
                             if (leader) mbar_arrive_expect_tx(fb, 2 * tx_bytes);
@@ -279,14 +287,16 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             tma_load_4d(sa, &tmA1, fb, (kb - p.kb0) * BLOCK_K, w0 + dx, hh + dy, nn);
                         tma_load_2d(sb, &tmB, fb, (tap * kb_per_tap + kb) * BLOCK_K, nt * p.block_n + wrow);
                         }
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0 && leader) {
+        // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+        if (leader) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
             const uint32_t ab_fmt = p.f16 ? 0u : ((1u << 7) | (1u << 10));   // a/b format: 0 = f16, 1 = bf16
             const uint32_t idesc = (1u << 4) | ab_fmt |
@@ -311,6 +321,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         }
                         const uint32_t sa = smem_u32(smem_a + stage * a_stage_bytes);
                         const int dyi = it / kb_per_tap, kb = it - dyi * kb_per_tap;
+                        if (elect_one_sync()) {
 #pragma unroll
                         for (int dxi = 0; dxi < 3; ++dxi) {
                             // rows dxi .. dxi+127 of the halo tile: the operand starts one 128-byte row further.  The 128-byte
@@ -327,11 +338,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         }
                         tcgen05_commit(smem_u32(&empty_bar[stage]));
                         if (it == k_iters - 1) tcgen05_commit(smem_u32(&tmem_full_bar[as]));
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes));
+                    if (elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 elements = 32 B along K inside the swizzle row: +2 in 16 B units
@@ -349,6 +363,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     tcgen05_commit(smem_u32(&empty_bar[stage]));     // frees the smem slot when MMAs retire
                     if (it == k_iters - 1) tcgen05_commit(smem_u32(&tmem_full_bar[as]));
                     }
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 as ^= 1;

@@ -55,6 +55,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// One lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops with the WHOLE
+// warp and only the issue itself sits under elect: the descriptor / coordinate arithmetic then lives in uniform
+// registers.  (With the whole loop under `lane == 0` the compiler had to move every operand of every UTCHMMA / UTMALDG
+// from vector to uniform registers through an ELECT / R2UR waterfall: 17 instructions per MMA, ~85 cycles against the
+// 32-cycle tensor time of a 128 x 64 x 16 MMA — the issuer, not the tensor pipe, set the pace of the narrow layers.)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }

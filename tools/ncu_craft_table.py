@@ -1,6 +1,6 @@
-"""ncu CSV (launch list of tools/gpu_probe_craft.py, one craft_forward) -> markdown per-layer table.
-usage: python tools/ncu_craft_table.py gpurun_out/ncu_craft.csv NPAGES > profiles/r02_craft_layers_ncu.md"""
-import csv, sys
+"""ncu CSV (long format: one row per launch and metric) of tools/gpu_probe_craft.py -> markdown per-layer table of the
+LAST craft_forward in the log.  usage: python tools/ncu_craft_table.py gpurun_out/ncu_craft.csv NPAGES"""
+import collections, csv, sys
 LAYERS = [("conv1_1", 3, 64, 9, 1), ("conv1_2", 64, 64, 9, 1), ("pool1", 0, 0, 0, 2), ("conv2_1", 64, 128, 9, 2), ("conv2_2", 128, 128, 9, 2),
           ("pool2", 0, 0, 0, 4), ("conv3_1", 128, 256, 9, 4), ("conv3_2", 256, 256, 9, 4), ("conv3_3", 256, 256, 9, 4), ("pool3", 0, 0, 0, 8),
           ("conv4_1", 256, 512, 9, 8), ("conv4_2", 512, 512, 9, 8), ("conv4_3", 512, 512, 9, 8), ("pool4", 0, 0, 0, 16),
@@ -11,20 +11,23 @@ LAYERS = [("conv1_1", 3, 64, 9, 1), ("conv1_2", 64, 64, 9, 1), ("pool1", 0, 0, 0
           ("cls1 (32->32)", 32, 32, 9, 2), ("cls2 (32->32)", 32, 32, 9, 2), ("cls3 (32->16)", 32, 16, 9, 2), ("cls4 (16->16)", 16, 16, 1, 2),
           ("cls5 (16->2)", 16, 2, 1, 2)]
 path, npages = sys.argv[1], int(sys.argv[2])
-rows = [r for r in csv.reader(open(path)) if r and r[0].isdigit()]
-hdr = next(r for r in csv.reader(open(path)) if r and r[0] == "ID")
-def col(name): return hdr.index(name)
-rows = rows[-len(LAYERS):]                       # the last craft_forward of the run
+launches = collections.OrderedDict()
+for r in csv.reader(open(path)):
+    if len(r) > 14 and r[0].isdigit():
+        launches.setdefault(int(r[0]), {"k": r[4]})[r[12]] = float(r[14].replace(",", ""))
+items = list(launches.values())
+start = [i for i, d in enumerate(items) if "conv1_1" in d["k"]][-1]
 H, W = 2560, 1984
-print(f"| layer | kernel | ms ({npages} pages) | real GFLOP/page | TFLOP/s (real) | tensor pipe active % | dram GB |")
-print("|---|---|---|---|---|---|---|")
+print(f"| layer | kernel | ms ({npages} pages) | real GFLOP/page | TFLOP/s (real) | tensor pipe active % | L2 throughput % | DRAM GB | DRAM TB/s |")
+print("|---|---|---|---|---|---|---|---|---|")
 tot_ms = tot_f = 0.0
-for (name, cin, cout, taps, div), r in zip(LAYERS, rows):
-    ms = float(r[col("gpu__time_duration.sum")]) / 1e6 if float(r[col("gpu__time_duration.sum")]) > 1e4 else float(r[col("gpu__time_duration.sum")])
+for (name, cin, cout, taps, div), d in zip(LAYERS, items[start:]):
+    ms = d["gpu__time_duration.sum"] / 1e6
     gf = 2.0 * cin * cout * taps * (H // div) * (W // div) / 1e9
-    kern = r[col("Kernel Name")].split("(")[0].replace("void <unnamed>::", "").replace("<unnamed>::", "")[:40]
-    tp = r[col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")] if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in hdr else ""
-    dr = float(r[col("dram__bytes_read.sum")]) + float(r[col("dram__bytes_write.sum")]) if "dram__bytes_read.sum" in hdr else 0
-    tot_ms += ms; tot_f += gf * npages
-    print(f"| {name} | `{kern}` | {ms:.3f} | {gf:.1f} | {gf * npages / ms / 1e3 if gf else 0:.0f} | {tp} | {dr / 1e9 if dr > 1e3 else dr:.2f} |")
-print(f"| **total** | | {tot_ms:.2f} | {tot_f / npages:.0f} | {tot_f / tot_ms / 1e3:.0f} | | |")
+    kern = d["k"].split("(")[0].replace("void <unnamed>::", "").replace("<unnamed>::", "")
+    dram = (d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)) / 1e9
+    tot_ms += ms
+    tot_f += gf * npages
+    print(f"| {name} | `{kern}` | {ms:.3f} | {gf:.1f} | {gf * npages / ms:.0f} | {d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):.1f} | "
+          f"{d.get('lts__throughput.avg.pct_of_peak_sustained_elapsed', 0):.0f} | {dram:.2f} | {dram / ms:.2f} |")
+print(f"| **total** | | {tot_ms:.2f} | {tot_f / npages:.0f} | {tot_f / tot_ms:.0f} | | | | |")
