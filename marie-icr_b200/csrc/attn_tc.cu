@@ -47,7 +47,29 @@ struct AttnParams {
     bf16* out;
     int f16;
     unsigned int* diag;
+    int poly;              // exp2 of every second score pair on the FMA pipe (packed polynomial) instead of MUFU
 };
+
+// exp2 of a PAIR of values on the FMA pipe: x = n + f with n = round(x), |f| <= 0.5 (magic-number rounding), a degree-4
+// polynomial for 2^f (max relative error 3.1e-6, far below the 16-bit rounding of P) in packed fp32, and the exponent
+// inserted with one integer shift-add.  x is clamped at -125, so tiny probabilities stay normal numbers.  The MUFU pipe
+// (16 ex2 / clk / SM) is what bounds the softmax warps; half of the scores take this route.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& y0, float& y1) {
+    const float MAGIC = 12582912.0f;                    // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer
+    const f32x2 x = pk2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const f32x2 t = add2(x, pk2(MAGIC, MAGIC));
+    const f32x2 n = add2(t, pk2(-MAGIC, -MAGIC));
+    const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), x);
+    f32x2 q = fma2(pk2(0.009600395517050074f, 0.009600395517050074f), f, pk2(0.05591689382504809f, 0.05591689382504809f));
+    q = fma2(q, f, pk2(0.24023718463104982f, 0.24023718463104982f));
+    q = fma2(q, f, pk2(0.6931219948398218f, 0.6931219948398218f));
+    q = fma2(q, f, pk2(1.0f, 1.0f));
+    float q0, q1, t0, t1;
+    upk2(q, q0, q1);
+    upk2(t, t0, t1);
+    y0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    y1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -68,7 +90,7 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2_raw(float lo, floa
 // One pass over a 64-key S tile of this thread's row: P = exp2(S * sc + ms) -> 16-bit -> shared memory (swizzled K-major
 // atom); returns the row's sum of P.  RAGGED masks keys >= valid (a partial last tile only).  TMEM loads are
 // software-pipelined: chunk c+1 is in flight while chunk c is processed.  Per score: FFMA, MUFU.EX2, FADD, half a pack.
-template <bool F16, bool RAGGED>
+template <bool F16, bool RAGGED, bool POLY = false>
 __device__ __forceinline__ float attn_pass_p(uint32_t t_s, uint8_t* pbuf, int row, int valid, float ms_, float sc,
                                              uint32_t* va, uint32_t* vb) {
     float lsum = 0.f;
@@ -86,8 +108,12 @@ __device__ __forceinline__ float attn_pass_p(uint32_t t_s, uint8_t* pbuf, int ro
         for (int i = 0; i < 32; i += 4) {
             pr[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), sc, ms_));
             pr[i + 1] = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), sc, ms_));
+            if (POLY) {
+                exp2_poly2(fmaf(__uint_as_float(cur[i + 2]), sc, ms_), fmaf(__uint_as_float(cur[i + 3]), sc, ms_), pr[i + 2], pr[i + 3]);
+            } else {
             pr[i + 2] = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), sc, ms_));
             pr[i + 3] = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), sc, ms_));
+            }
             if (RAGGED) {
                 if (c + i >= valid) pr[i] = 0.f;
                 if (c + i + 1 >= valid) pr[i + 1] = 0.f;
@@ -288,7 +314,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
             const bool ragged = valid < KT;                   // CTA-uniform: a partial last tile only
             if (j == 0) ms = -pass_max(t_s, valid) * sc;      // the row's reference
             float lt = ragged ? attn_pass_p<F16, true>(t_s, pbuf, row, valid, ms, sc, va, vb)
-                              : attn_pass_p<F16, false>(t_s, pbuf, row, valid, ms, sc, va, vb);
+                              : (p.poly ? attn_pass_p<F16, false, true>(t_s, pbuf, row, valid, ms, sc, va, vb)
+                                        : attn_pass_p<F16, false>(t_s, pbuf, row, valid, ms, sc, va, vb));
             if (__any_sync(0xffffffffu, !(lt <= 2048.f))) {
                 // re-base the rows that grew: the tile's maximum becomes the new reference (their largest probability
                 // of this tile becomes 1); everything accumulated so far shrinks by the same factor
@@ -643,7 +670,8 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                 const bool ragged = valid < KT;
                 if (j == 0) ms = -pass_max(t_s, valid) * sc;
                 float lt = ragged ? attn_pass_p<F16, true>(t_s, pbuf, row, valid, ms, sc, va, vb)
-                                  : attn_pass_p<F16, false>(t_s, pbuf, row, valid, ms, sc, va, vb);
+                                  : (p.poly ? attn_pass_p<F16, false, true>(t_s, pbuf, row, valid, ms, sc, va, vb)
+                                            : attn_pass_p<F16, false>(t_s, pbuf, row, valid, ms, sc, va, vb));
                 if (__any_sync(0xffffffffu, !(lt <= 2048.f))) {
                     const float ms_new = -pass_max(t_s, valid) * sc;
                     float f = 1.f;
@@ -799,6 +827,7 @@ int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D
     }
     AttnParams p;
     p.T = T; p.D = D; p.heads = heads; p.scale_log2e = scale_log2e; p.qkv = qkv; p.out = out; p.f16 = ctx->f16; p.diag = ctx->dev_diag;
+    { const char* e = getenv("MB_ATTN_POLY"); p.poly = e ? (e[0] != '0') : 0; }
     const int q_tiles = (T + TILE - 1) / TILE;
     const long long items = (long long)q_tiles * heads * n;
     if (persist && items < 0x7fffffffLL) {
