@@ -40,6 +40,8 @@ constexpr int BAR_BYTES = 512;   // 2*8 ring + 4 accumulator mbarriers, the TMEM
                                  // 512 keeps the staging tiles aligned for the 64-byte TMA swizzle
 constexpr int RES_BAR_SLOT = 2 * MAX_STAGES + 5;   // first of the EPI_WARPS residual mbarriers (u64 slots after the pointer)
 constexpr int BRES_BAR_SLOT = RES_BAR_SLOT + EPI_WARPS;   // "resident weights have landed"
+constexpr int COEF_BAR_SLOT = BRES_BAR_SLOT + 1;          // two "per-column coefficients of this tile are staged" mbarriers
+constexpr int COEF_RES_BYTES = 2 * 1024;                  // TMA epilogue with residual: two bias tiles behind the staging tiles
 
 struct KParams {
     int n, h, w;
@@ -141,9 +143,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                 const __grid_constant__ CUtensorMap tmRes, const KParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024 B alignment is required by the 128B swizzle; do not trust the declared alignment alone.
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    // 1024 B alignment is required by the 128B swizzle.  The kernel has no static shared memory, so the dynamic window
+    // starts at the declared alignment; a build that breaks this must fault, not corrupt operands (the host sizes the
+    // allocation without slack: the last kilobyte pays for the coefficient tiles of the TMA epilogue).
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) {
+        if (threadIdx.x == 0 && p.diag) atomicExch(p.diag, 0xDEAD00A1u);
+        __trap();
+    }
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int b_slot_bytes = (CG2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
@@ -181,6 +188,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (TMAOUT && RES)
             for (int i = 0; i < EPI_WARPS; ++i) mbar_init(smem_u32(&bars[RES_BAR_SLOT + i]), 1);
         mbar_init(smem_u32(&bars[BRES_BAR_SLOT]), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bars[COEF_BAR_SLOT + i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -371,9 +379,38 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 if (as == 0) aphase ^= 1;
             }
         }
+    } else if (warp == 3 && TMAOUT) {
+        // ------------------------------------------------------------ coefficient producer (TMA epilogue only)
+        // The epilogue works row-per-lane, so every lane needs ALL per-column coefficients of its chunk (bias; LayerNorm
+        // fold: c_n as well).  Read through L1 they cost the epilogue warps half their time (ncu, r02: 16 LDG.128 per chunk,
+        // every sector missing — the 227 KB carve-out leaves L1 a few KB — and stall_long_scoreboard on each FFMA2 that
+        // consumed them: the three K = 768 encoder GEMMs all ran at the same ~10.6 K cycles per tile, epilogue-bound).  This
+        // otherwise idle warp stages the tile's <= 256 bias (and c) values in shared memory one accumulator buffer ahead;
+        // the epilogue reads them as broadcast LDS.128.  Buffer `as` is free again when the epilogue warps have released
+        // TMEM buffer `as` (their coefficient reads precede that arrival), so the wait is the MMA warp's.
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+            const int bt = tile / tiles_per_batch;
+            const int nt = (tile - bt * tiles_per_batch) % p.n_tiles;
+            const int nbase = bt * p.out_col_stride, ntile0 = nt * p.block_n;
+            float* cb = RES ? reinterpret_cast<float*>(smem_stage + EPI_WARPS * STAGE_TILE_BYTES + as * (COEF_RES_BYTES / 2))
+                            : reinterpret_cast<float*>(smem_stage + as * STAGE_TILE_BYTES + 2048);
+            mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1, p.diag, 7, p.backoff);
+            for (int j = lane; j < p.block_n; j += 32) {
+                const bool in = ntile0 + j < p.n_out;
+                cb[j] = (in && p.bias != nullptr) ? __ldg(p.bias + nbase + ntile0 + j) : 0.f;
+                if (LNF) cb[256 + j] = in ? __ldg(p.ln_c + nbase + ntile0 + j) : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[COEF_BAR_SLOT + as]));
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
     } else if (warp >= 4 && TMAOUT) {
         // ------------------------------------------------------------ epilogue, TMA-store form (8 warps)
         // Warp e owns TMEM lane quarter (warp & 3) = 32 tile rows, one row per lane, and every second 32-column chunk.
+        static_assert(!(TMAOUT && RES && LNF), "the TMA epilogue keeps the LayerNorm-fold coefficients in the residual staging area");
         const int ew = warp - 4;
         const int q = warp & 3;
         const int half = ew >> 2;
@@ -382,85 +419,86 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t res_bar = smem_u32(&bars[RES_BAR_SLOT + ew]);
         uint32_t rphase = 0;
         const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int n_chunks = (p.block_n + 31) >> 5;
+        struct TileC { int ntile0, nbase, wrow, hh, nn, rows_valid; };
+        auto coords = [&](int tile) {
+            TileC t;
             const int bt = tile / tiles_per_batch;
             const int trem = tile - bt * tiles_per_batch;
             const int nt = trem % p.n_tiles;
             const int mt = trem / p.n_tiles;
             const int wt = mt % p.w_tiles;
             const int rest = mt / p.w_tiles;
-            const int hh = rest % p.h;
-            const int nn = rest / p.h;
-            const int nbase = bt * p.out_col_stride;
-            const int wrow = wt * BLOCK_M + q * 32;                  // w coordinate of this warp's first row
-            const long long pix0 = ((long long)nn * p.h + hh) * p.w + wrow;
-            const int rows_valid = min(32, p.w - wrow);
-            const int ntile0 = nt * p.block_n;
-            const int n_chunks = (p.block_n + 31) >> 5;
-            auto chunk_active = [&](int ci) { return ci < n_chunks && ntile0 + ci * 32 < p.n_out && rows_valid > 0; };
+            t.hh = rest % p.h;
+            t.nn = rest / p.h;
+            t.nbase = bt * p.out_col_stride;
+            t.wrow = wt * BLOCK_M + q * 32;                          // w coordinate of this warp's first row
+            t.rows_valid = min(32, p.w - t.wrow);
+            t.ntile0 = nt * p.block_n;
+            return t;
+        };
+        auto chunk_active = [&](const TileC& t, int ci) { return ci < n_chunks && t.ntile0 + ci * 32 < p.n_out && t.rows_valid > 0; };
+        auto issue_res = [&](const TileC& t, int ci) {
+            mbar_arrive_expect_tx(res_bar, 2048);
+            tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, t.nbase + t.ntile0 + ci * 32, t.wrow, t.hh, t.nn);
+        };
+        int as = 0;
+        uint32_t aphase = 0;
+        bool res_pending = false;        // this tile's first residual chunk was requested under the previous tile's last chunk
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+            const TileC t = coords(tile);
+            const long long pix0 = ((long long)t.nn * p.h + t.hh) * p.w + t.wrow;
             f32x2 nm2 = 0, rstd2 = 0;
             if (LNF) {
-                const float2 st = lane < rows_valid ? __ldg(p.ln_stats + pix0 + lane) : make_float2(0.f, 0.f);
+                const float2 st = lane < t.rows_valid ? __ldg(p.ln_stats + pix0 + lane) : make_float2(0.f, 0.f);
                 nm2 = pk2(st.x, st.x);
                 rstd2 = pk2(st.y, st.y);
             }
-            if (RES && chunk_active(half) && lane == 0) {
-                mbar_arrive_expect_tx(res_bar, 2048);
-                tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, nbase + ntile0 + half * 32, wrow, hh, nn);
-            }
+            if (RES && !res_pending && chunk_active(t, half) && lane == 0) issue_res(t, half);
+            res_pending = false;
             mbar_wait(smem_u32(&tmem_full_bar[as]), aphase, p.diag, 4, p.backoff);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
             uint32_t v[32];
             bool released = false;
-            if (chunk_active(half)) tmem_ld32(taddr + (uint32_t)(half * 32), v);
+            if (chunk_active(t, half)) tmem_ld32(taddr + (uint32_t)(half * 32), v);
+            mbar_wait(smem_u32(&bars[COEF_BAR_SLOT + as]), aphase, p.diag, 8);
+            const float* cb = RES ? reinterpret_cast<const float*>(smem_stage + EPI_WARPS * STAGE_TILE_BYTES + as * (COEF_RES_BYTES / 2))
+                                  : reinterpret_cast<const float*>(smem_stage + as * STAGE_TILE_BYTES + 2048);
 #pragma unroll 1
-            for (int ci = half; chunk_active(ci); ci += 2) {
-                const int n0 = ntile0 + ci * 32;
+            for (int ci = half; chunk_active(t, ci); ci += 2) {
+                const int n0 = t.ntile0 + ci * 32;
                 uint32_t rr[16];
                 if (RES) {
                     mbar_wait(res_bar, rphase, p.diag, 5);
                     rphase ^= 1;
 #pragma unroll
                     for (uint32_t c = 0; c < 4; ++c) {
-                        const uint4 t = *reinterpret_cast<const uint4*>(stg_res + sw_row + ((c ^ sw_x) << 4));
-                        rr[4 * c] = t.x; rr[4 * c + 1] = t.y; rr[4 * c + 2] = t.z; rr[4 * c + 3] = t.w;
+                        const uint4 x = *reinterpret_cast<const uint4*>(stg_res + sw_row + ((c ^ sw_x) << 4));
+                        rr[4 * c] = x.x; rr[4 * c + 1] = x.y; rr[4 * c + 2] = x.z; rr[4 * c + 3] = x.w;
                     }
                     __syncwarp();
-                    if (chunk_active(ci + 2) && lane == 0) {          // next residual chunk: lands under this chunk's arithmetic
-                        mbar_arrive_expect_tx(res_bar, 2048);
-                        tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, nbase + n0 + 64, wrow, hh, nn);
+                    // the next residual chunk lands under this chunk's arithmetic; after the tile's last chunk that is the
+                    // first chunk of the NEXT tile (its latency would otherwise sit in front of that tile's epilogue)
+                    if (chunk_active(t, ci + 2)) {
+                        if (lane == 0) issue_res(t, ci + 2);
+                    } else if (tile + tile_step < total_tiles) {
+                        const TileC tn = coords(tile + tile_step);
+                        if (chunk_active(tn, half)) {
+                            if (lane == 0) issue_res(tn, half);
+                            res_pending = true;
+                        }
                     }
                 }
                 tmem_wait_ld();
-                const bool full = n0 + 32 <= p.n_out;
                 uint32_t o[16];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (full) {
-                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + n0) + k);
-                        if (LNF) c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c + nbase + n0) + k);
-                    } else {
-                        const int j = n0 + 4 * k;
-                        if (p.bias != nullptr) {
-                            if (j < p.n_out) b4.x = __ldg(p.bias + nbase + j);
-                            if (j + 1 < p.n_out) b4.y = __ldg(p.bias + nbase + j + 1);
-                            if (j + 2 < p.n_out) b4.z = __ldg(p.bias + nbase + j + 2);
-                            if (j + 3 < p.n_out) b4.w = __ldg(p.bias + nbase + j + 3);
-                        }
-                        if (LNF) {
-                            if (j < p.n_out) c4.x = __ldg(p.ln_c + nbase + j);
-                            if (j + 1 < p.n_out) c4.y = __ldg(p.ln_c + nbase + j + 1);
-                            if (j + 2 < p.n_out) c4.z = __ldg(p.ln_c + nbase + j + 2);
-                            if (j + 3 < p.n_out) c4.w = __ldg(p.ln_c + nbase + j + 3);
-                        }
-                    }
+                    const float4 b4 = *reinterpret_cast<const float4*>(cb + ci * 32 + 4 * k);      // broadcast reads
                     f32x2 xa = pk2(v[4 * k], v[4 * k + 1]), xb = pk2(v[4 * k + 2], v[4 * k + 3]);
                     const f32x2 ba = pk2(b4.x, b4.y), bb = pk2(b4.z, b4.w);
                     if (LNF) {       // rstd * (acc - mean * c) + b'
+                        const float4 c4 = *reinterpret_cast<const float4*>(cb + 256 + ci * 32 + 4 * k);
                         xa = fma2(fma2(nm2, pk2(c4.x, c4.y), xa), rstd2, ba);
                         xb = fma2(fma2(nm2, pk2(c4.z, c4.w), xb), rstd2, bb);
                     } else {
@@ -482,7 +520,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 }
                 // the accumulators of this chunk are consumed: next chunk's TMEM load overlaps the store sequence; after
                 // the last chunk the accumulator buffer goes back to the MMA warp before the stores are even issued
-                if (chunk_active(ci + 2)) {
+                if (chunk_active(t, ci + 2)) {
                     tmem_ld32(taddr + (uint32_t)((ci + 2) * 32), v);
                 } else {
                     tcgen05_fence_before();
@@ -499,7 +537,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tmOut, smem_u32(stg_out), nbase + n0, wrow, hh, nn);
+                    tma_store_4d(&tmOut, smem_u32(stg_out), t.nbase + n0, t.wrow, t.hh, t.nn);
                     bulk_commit_group();
                 }
             }
@@ -892,11 +930,13 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.bres = (p.halo && p.n_tiles == 1 && bres_bytes <= 80 * 1024 && !(bres_env && bres_env[0] == '0')) ? 1 : 0;
     const int stage_bytes = p.halo ? A_HALO_STAGE_BYTES + (p.bres ? 0 : 3 * b_slot) : A_STAGE_BYTES + b_slot;
     const int bar_bytes = BAR_BYTES + EPI_WARPS * STAGE_TILE_BYTES;
-    int stages = (SMEM_LIMIT - 1024 - bar_bytes - (p.bres ? bres_bytes : 0)) / stage_bytes;
+    // (residual present: the TMA epilogue may need COEF_RES_BYTES behind the staging tiles; reserved whether or not it is taken)
+    const int coef_bytes = g.residual != nullptr ? COEF_RES_BYTES : 0;
+    int stages = (SMEM_LIMIT - bar_bytes - coef_bytes - (p.bres ? bres_bytes : 0)) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (p.halo && stages < 2) {                       // wide N tiles: three B slots per stage do not leave a ring
         p.halo = p.bres = 0;
-        stages = (SMEM_LIMIT - 1024 - bar_bytes) / (A_STAGE_BYTES + b_slot);
+        stages = (SMEM_LIMIT - bar_bytes - coef_bytes) / (A_STAGE_BYTES + b_slot);
         if (stages > MAX_STAGES) stages = MAX_STAGES;
     }
     const int stage_bytes_final = p.halo ? stage_bytes : A_STAGE_BYTES + b_slot;
@@ -957,7 +997,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         }
     }
 
-    const size_t smem = 1024 + (size_t)stages * stage_bytes_final + (p.bres ? bres_bytes : 0) + bar_bytes;
+    const size_t smem = (size_t)stages * stage_bytes_final + (p.bres ? bres_bytes : 0) + bar_bytes + coef_bytes;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const KParams);
     KernelFn fn = nullptr;
