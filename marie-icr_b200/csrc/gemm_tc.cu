@@ -40,7 +40,8 @@ constexpr int BAR_BYTES = 512;   // 2*8 ring + 4 accumulator mbarriers, the TMEM
                                  // 512 keeps the staging tiles aligned for the 64-byte TMA swizzle
 constexpr int RES_BAR_SLOT = 2 * MAX_STAGES + 5;   // first of the EPI_WARPS residual mbarriers (u64 slots after the pointer)
 constexpr int BRES_BAR_SLOT = RES_BAR_SLOT + EPI_WARPS;   // "resident weights have landed"
-constexpr int COEF_BAR_SLOT = BRES_BAR_SLOT + 1;          // two "per-column coefficients of this tile are staged" mbarriers
+constexpr int COEF_BAR_SLOT = BRES_BAR_SLOT + 1;          // two "per-column coefficients of this tile are staged" mbarriers,
+                                                          // then two "the epilogue warps have read them" (EPI_WARPS arrivals)
 constexpr int COEF_RES_BYTES = 2 * 1024;                  // TMA epilogue with residual: two bias tiles behind the staging tiles
 
 struct KParams {
@@ -188,7 +189,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (TMAOUT && RES)
             for (int i = 0; i < EPI_WARPS; ++i) mbar_init(smem_u32(&bars[RES_BAR_SLOT + i]), 1);
         mbar_init(smem_u32(&bars[BRES_BAR_SLOT]), 1);
-        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bars[COEF_BAR_SLOT + i]), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars[COEF_BAR_SLOT + i]), 1);
+            mbar_init(smem_u32(&bars[COEF_BAR_SLOT + 2 + i]), EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -386,8 +390,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         // every sector missing — the 227 KB carve-out leaves L1 a few KB — and stall_long_scoreboard on each FFMA2 that
         // consumed them: the three K = 768 encoder GEMMs all ran at the same ~10.6 K cycles per tile, epilogue-bound).  This
         // otherwise idle warp stages the tile's <= 256 bias (and c) values in shared memory one accumulator buffer ahead;
-        // the epilogue reads them as broadcast LDS.128.  Buffer `as` is free again when the epilogue warps have released
-        // TMEM buffer `as` (their coefficient reads precede that arrival), so the wait is the MMA warp's.
+        // the epilogue reads them as broadcast LDS.128.  Buffer `as` is free again when this CTA's eight epilogue warps have
+        // finished the tile that used it (a CTA-local barrier: in a CTA pair the TMEM release goes to the leader).
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = tile0; tile < total_tiles; tile += tile_step) {
@@ -396,7 +400,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int nbase = bt * p.out_col_stride, ntile0 = nt * p.block_n;
             float* cb = RES ? reinterpret_cast<float*>(smem_stage + EPI_WARPS * STAGE_TILE_BYTES + as * (COEF_RES_BYTES / 2))
                             : reinterpret_cast<float*>(smem_stage + as * STAGE_TILE_BYTES + 2048);
-            mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1, p.diag, 7, p.backoff);
+            mbar_wait(smem_u32(&bars[COEF_BAR_SLOT + 2 + as]), aphase ^ 1, p.diag, 7, p.backoff);
             for (int j = lane; j < p.block_n; j += 32) {
                 const bool in = ntile0 + j < p.n_out;
                 cb[j] = (in && p.bias != nullptr) ? __ldg(p.bias + nbase + ntile0 + j) : 0.f;
@@ -426,14 +430,16 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int bt = tile / tiles_per_batch;
             const int trem = tile - bt * tiles_per_batch;
             const int nt = trem % p.n_tiles;
-            const int mt = trem / p.n_tiles;
+            int mt = trem / p.n_tiles;
+            bool exists = true;
+            if (CG2) { mt = 2 * mt + (int)crank; exists = mt < p.m_tiles; mt = min(mt, p.m_tiles - 1); }
             const int wt = mt % p.w_tiles;
             const int rest = mt / p.w_tiles;
             t.hh = rest % p.h;
             t.nn = rest / p.h;
             t.nbase = bt * p.out_col_stride;
             t.wrow = wt * BLOCK_M + q * 32;                          // w coordinate of this warp's first row
-            t.rows_valid = min(32, p.w - t.wrow);
+            t.rows_valid = exists ? min(32, p.w - t.wrow) : 0;       // <= 0: ragged last tile / missing partner of a pair
             t.ntile0 = nt * p.block_n;
             return t;
         };
@@ -441,6 +447,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         auto issue_res = [&](const TileC& t, int ci) {
             mbar_arrive_expect_tx(res_bar, 2048);
             tma_load_4d(smem_u32(stg_res), &tmRes, res_bar, t.nbase + t.ntile0 + ci * 32, t.wrow, t.hh, t.nn);
+        };
+        // accumulator buffer back to the MMA warp (the pair leader's in two-CTA mode), coefficient tile back to warp 3
+        auto release_tile = [&](int a) {
+            if (CG2) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[a]), 0);
+            else mbar_arrive(smem_u32(&tmem_empty_bar[a]));
+            mbar_arrive(smem_u32(&bars[COEF_BAR_SLOT + 2 + a]));
         };
         int as = 0;
         uint32_t aphase = 0;
@@ -525,7 +537,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 } else {
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+                    if (lane == 0) release_tile(as);
                     released = true;
                 }
                 if (lane == 0) bulk_wait_group_read0();              // this warp's previous store has read the staging tile
@@ -544,7 +556,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             if (!released) {
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+                if (lane == 0) release_tile(as);
             }
             as ^= 1;
             if (as == 0) aphase ^= 1;
@@ -914,11 +926,22 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.kb0 = g.c0 / BLOCK_K; p.kb1 = g.c1 / BLOCK_K;
     p.block_n = block_n;
     p.n_out = g.n_out;
+    // TMA-store epilogue: 16-bit row-major output whose pitch / base the TMA can address (and the same for the residual);
+    // block-diagonal batches need whole chunks per batch (a box must not spill into the next batch's columns)
+    const bool res = g.residual != nullptr;
+    const bool lnf = g.ln_stats != nullptr;
+    const int nbatch = g.batches > 0 ? g.batches : 1;
+    const long long out_cols = (long long)(nbatch - 1) * g.out_col_stride + g.n_out;
+    const char* epi_env = getenv("MB_EPI_TMA");
+    const bool tma_out = !(epi_env && epi_env[0] == '0') && g.out_mode == MB_OUT_BF16 && g.out_ld % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && out_cols >= 32 &&
+                         (nbatch == 1 || g.n_out % 32 == 0) &&
+                         (!res || (g.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0));
     // two-CTA mode (cta_group::2): big 16-bit-output problems with full 256-wide N tiles; MB_GEMM2=0 disables it
     static int gemm2_env = -1;
     if (gemm2_env < 0) { const char* e = getenv("MB_GEMM2"); gemm2_env = (e && e[0] == '1') ? 1 : 0; }
-    const bool cg2 = gemm2_env == 1 && g.ln_stats == nullptr && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
-                     (g.batches <= 1);
+    const bool cg2 = gemm2_env == 1 && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
+                     (g.batches <= 1) && (!lnf || tma_out);
     // halo mode: 3x3 / dilation 1 convolutions (one A load per image row instead of three); small layers also keep the whole
     // weight matrix in shared memory.  MB_HALO=0 switches it off (A/B timing).
     const char* halo_env = getenv("MB_HALO");
@@ -950,21 +973,10 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.ln_stats = reinterpret_cast<const float2*>(g.ln_stats); p.ln_c = g.ln_c;
     p.diag = ctx->dev_diag;
     { const char* e = getenv("MB_SPIN_SLEEP"); p.backoff = e ? (unsigned)atoi(e) : 0u; }
-    const bool lnf = g.ln_stats != nullptr;
     MB_REQUIRE(ctx, !lnf || (g.ln_c && g.out_mode == MB_OUT_BF16 && !g.residual && g.taps == 1 && g.n == 1 && g.h == 1),
                "tap_gemm: the LayerNorm fold needs a plain 16-bit-output GEMM without residual");
 
-    const bool res = g.residual != nullptr;
     const bool h = ctx->f16 != 0;
-    // TMA-store epilogue: 16-bit row-major output whose pitch / base the TMA can address (and the same for the residual);
-    // block-diagonal batches need whole chunks per batch (a box must not spill into the next batch's columns)
-    const long long out_cols = (long long)(p.batches - 1) * g.out_col_stride + g.n_out;
-    const char* epi_env = getenv("MB_EPI_TMA");
-    const bool tma_out = !(epi_env && epi_env[0] == '0') && !cg2 && g.out_mode == MB_OUT_BF16 && g.out_ld % 8 == 0 &&
-                         (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && out_cols >= 32 &&
-                         (p.batches == 1 || g.n_out % 32 == 0) &&
-                         (!res || (g.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0));
-
     CUtensorMap tmA0, tmA1, tmB, tmOut, tmRes;
     const int a0c = g.batches > 1 ? g.a0_ld : g.c0;
     const int a_rows = p.halo ? HALO_ROWS : BLOCK_M;
@@ -1024,8 +1036,10 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     if (tma_out && fn) {
 #define MB_PICKT(A, R, L)                                                                                            \
     if (g.act == (A) && res == (R) && lnf == (L))                                                                    \
-        fn = h ? (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, true, false, L, true>                                 \
-               : (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, false, false, L, true>;
+        fn = cg2 ? (h ? (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, true, true, L, true>                           \
+                      : (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, false, true, L, true>)                         \
+                 : (h ? (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, true, false, L, true>                          \
+                      : (KernelFn)tap_gemm_kernel<A, MB_OUT_BF16, R, false, false, L, true>);
         MB_PICKT(MB_ACT_NONE, false, false) MB_PICKT(MB_ACT_NONE, true, false) MB_PICKT(MB_ACT_RELU, false, false)
         MB_PICKT(MB_ACT_RELU, true, false) MB_PICKT(MB_ACT_GELU, false, false) MB_PICKT(MB_ACT_GELU, true, false)
         MB_PICKT(MB_ACT_NONE, false, true) MB_PICKT(MB_ACT_GELU, false, true)

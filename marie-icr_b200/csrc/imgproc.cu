@@ -609,14 +609,235 @@ crop_resize_up_kernel(const CropDesc* __restrict__ crops, const int* __restrict_
     }   // crop loop
 }
 
+// ------------------------------------------------------------------------------------------------ K9, common case (v2)
+// The same filter, re-organised around the instruction count of the vertical pass (ncu, r01: 17.8 thread instructions per
+// output value at 56 % issue utilisation; two CTAs / SM, three CTA-wide phases per crop):
+//   * an up-scaled axis has at most FOUR taps (exhaustive over in_size = 1..384, tests/test_device_algorithms_cpu.py), so
+//     the u8 intermediate is stored as ROW QUADS, tmp[q][x*3+c] = rows 4q..4q+3 of one value in one 32-bit word, and a tap
+//     window at any row offset is one PRMT of two quad words;
+//   * every coefficient k (|k| < 2^23) is split exactly as k = k2*2^16 + k1*2^8 + k0 (k0, k1 unsigned bytes, k2 signed), the
+//     four taps of a digit sit in one word, and a value is THREE dp4a: sum k*v = (d2 << 16) + (d1 << 8) + d0;
+//   * consecutive output rows with the same first tap (a "run", 384 / h rows) share the window: a warp third owns a run,
+//     builds the windows of its 4 px x 3 channels once and walks the run with one coefficient fetch per row;
+//   * the horizontal pass keeps the thread's four coefficients in registers (thread = output column) and packs four rows
+//     with two saturating cvt.pack;
+//   * 72 KB and <= 56 registers: three CTAs per SM, so one crop's coefficient / horizontal phases run under another's
+//     vertical pass.  Tall crops are processed in bands of quads (one quad of overlap).
+// Bit-identical to the tap-by-tap form (and to Pillow): tests/test_imgproc_gpu.py.
+constexpr int UP2_THREADS = OUT;           // thread t = output column t (horizontal pass) = output row t (tables)
+constexpr int UP2_SMEM = 75 * 1024;        // three CTAs per SM
+constexpr int UP2_QWORDS = OUT * 3;        // words per row quad
+constexpr int UP2_FIXED = OUT * 16 + (OUT + 8) * 4 + 512 * 2 + 64;   // vtab | run_y0 | lut | warp counts
+
+__host__ __device__ inline size_t k9_up2_tables(int w) {
+    return (size_t)UP2_FIXED + (w > OUT ? (size_t)OUT * 8 + (size_t)OUT * k9_ksize(w) * 4 : 0);
+}
+__host__ __device__ inline bool k9_up2_ok(int w, int h) {
+    if (h > OUT || h <= 0 || w < 4) return false;
+    return k9_up2_tables(w) + (size_t)6 * UP2_QWORDS * 4 <= (size_t)UP2_SMEM;      // at least five quads + the spare
+}
+__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// bytes (lo .. hi) = sat_u8(a0), sat_u8(a1), sat_u8(a2), sat_u8(a3)
+__device__ __forceinline__ unsigned pack_sat4(int a0, int a1, int a2, int a3) {
+    unsigned hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3), "r"(a2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a1), "r"(a0), "r"(hi));
+    return d;
+}
+
+__global__ void __launch_bounds__(UP2_THREADS, 3)
+crop_resize_up2_kernel(const CropDesc* __restrict__ crops, const int* __restrict__ list, const int* __restrict__ count,
+                       bf16* __restrict__ out, int layout, int f16) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int4* vtab = reinterpret_cast<int4*>(smem);                                  // [OUT] (k0, k1, k2 digit words, ymin)
+    int* run_y0 = reinterpret_cast<int*>(vtab + OUT);                            // [n_runs + 1] first output row of a run
+    unsigned short* lut = reinterpret_cast<unsigned short*>(run_y0 + OUT + 8);   // [512]: index (v >> 22) + 128, clamped
+    int* wcnt = reinterpret_cast<int*>(lut + 512);                               // [16]
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    for (int i = t; i < 512; i += UP2_THREADS) {
+        int u = i - 128;
+        u = u < 0 ? 0 : (u > 255 ? 255 : u);
+        const float v = (((float)u / 255.0f) - 0.5f) / 0.5f;
+        lut[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+    const int n_list = *count;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int crop = list[li];
+        const CropDesc cd = crops[crop];
+        const int w = cd.w, h = cd.h;
+        const bool wide = w > OUT;
+        const int ks_h = k9_ksize(w);
+        int* hb = wcnt + 16;                                                     // wide crops only: [OUT][2], [OUT][ks_h]
+        int* hk = hb + OUT * 2;
+        unsigned* tmpw = reinterpret_cast<unsigned*>(smem + k9_up2_tables(w));
+        const int QB = (int)((UP2_SMEM - k9_up2_tables(w)) / (UP2_QWORDS * 4)) - 1;   // quads of a band (+ one spare behind)
+        __syncthreads();                                    // previous crop is done with the tables
+        // ---- tables: vertical digits for output row t, horizontal coefficients for output column t
+        int hx = 0, hk0 = 0, hk1 = 0, hk2 = 0, hk3 = 0;
+        {
+            int kk[5], ymin, n;
+            pil_coef_up(h, t, &ymin, &n, kk);
+            unsigned k0 = 0, k1 = 0, k2 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                k0 |= (unsigned)(kk[i] & 255) << (8 * i);
+                k1 |= (unsigned)((kk[i] >> 8) & 255) << (8 * i);
+                k2 |= (unsigned)((kk[i] >> 16) & 255) << (8 * i);
+            }
+            vtab[t] = make_int4((int)k0, (int)k1, (int)k2, ymin);
+            if (!wide) {
+                int xmin;
+                pil_coef_up(w, t, &xmin, &n, kk);
+                // the four-column window [hx, hx+4) stays inside the row (w >= 4): taps shifted, empty slots zero
+                hx = min(xmin, w - 4);
+                const int sh = xmin - hx;
+                hk0 = sh == 0 ? kk[0] : 0;
+                hk1 = sh == 0 ? kk[1] : (sh == 1 ? kk[0] : 0);
+                hk2 = sh == 0 ? kk[2] : (sh == 1 ? kk[1] : (sh == 2 ? kk[0] : 0));
+                hk3 = sh == 0 ? kk[3] : (sh == 1 ? kk[2] : (sh == 2 ? kk[1] : kk[0]));
+            } else {
+                pil_coef(w, t, ks_h, &hb[t * 2], &hb[t * 2 + 1], hk + t * ks_h);
+            }
+        }
+        __syncthreads();
+        // ---- runs of output rows with the same first tap (ymin is non-decreasing in y)
+        {
+            const bool first = t == 0 || vtab[t].w != vtab[t - 1].w;
+            const unsigned bal = __ballot_sync(0xffffffffu, first);
+            if (lane == 0) wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int base = 0, total = 0;
+#pragma unroll
+            for (int i = 0; i < UP2_THREADS / 32; ++i) {
+                const int c = wcnt[i];
+                base += i < warp ? c : 0;
+                total += c;
+            }
+            if (first) run_y0[base + __popc(bal & ((1u << lane) - 1u))] = t;
+            if (t == 0) { run_y0[total] = OUT; wcnt[12] = total; }
+        }
+        __syncthreads();
+        const int n_runs = wcnt[12];
+        const int t3 = warp % 3, rsel = warp / 3;
+        const int px4 = t3 * 128 + lane * 4;                 // this lane's four pixels in the vertical pass
+        const uint8_t* hsrc = cd.base + (long long)hx * 3;
+        for (int rb0 = 0; rb0 < n_runs;) {
+            // band: quads [bq0, bq0 + QB) are computed; a run needs quads q0 and q0 + 1 of its window
+            const int bq0 = vtab[run_y0[rb0]].w >> 2;
+            int lo = rb0, hi = n_runs;                      // first run whose q0 > bq0 + QB - 2 (binary search, CTA-uniform)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((vtab[run_y0[mid]].w >> 2) <= bq0 + QB - 2) lo = mid + 1; else hi = mid;
+            }
+            const int rb1 = lo;
+            const int nq = min(bq0 + QB, (h + 3) >> 2) - bq0;        // quads with source rows in this band
+            // ---- horizontal pass: thread = output column, item = row quad
+            if (!wide) {
+                for (int q = 0; q < nq; ++q) {
+                    int a[3][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int row = min((bq0 + q) * 4 + r, h - 1);
+                        const uint8_t* sp = hsrc + (long long)row * cd.pitch;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            a[c][r] = ((1 << (PREC_BITS - 1)) + sp[c] * hk0 + sp[3 + c] * hk1 + sp[6 + c] * hk2 + sp[9 + c] * hk3) >> PREC_BITS;
+                    }
+                    unsigned* d = tmpw + q * UP2_QWORDS + t * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d[c] = pack_sat4(a[c][0], a[c][1], a[c][2], a[c][3]);
+                }
+            } else {
+                const int xmin = hb[t * 2], n = hb[t * 2 + 1];
+                const int* k = hk + t * ks_h;
+                for (int q = 0; q < nq; ++q) {
+                    int a[3][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int row = min((bq0 + q) * 4 + r, h - 1);
+                        const uint8_t* sp = cd.base + (long long)row * cd.pitch + xmin * 3;
+                        int a0 = 1 << (PREC_BITS - 1), a1 = a0, a2 = a0;
+                        for (int x = 0; x < n; ++x) {
+                            const int kv = k[x];
+                            a0 += sp[x * 3 + 0] * kv; a1 += sp[x * 3 + 1] * kv; a2 += sp[x * 3 + 2] * kv;
+                        }
+                        a[0][r] = a0 >> PREC_BITS; a[1][r] = a1 >> PREC_BITS; a[2][r] = a2 >> PREC_BITS;
+                    }
+                    unsigned* d = tmpw + q * UP2_QWORDS + t * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d[c] = pack_sat4(a[c][0], a[c][1], a[c][2], a[c][3]);
+                }
+            }
+            __syncthreads();
+            // ---- vertical pass: warp third = 128 px of a run
+            for (int r = rb0 + rsel; r < rb1; r += 4) {
+                const int y0 = run_y0[r], y1 = run_y0[r + 1];
+                const int ymin = vtab[y0].w;
+                const int off = ymin & 3;
+                const uint4* tq = reinterpret_cast<const uint4*>(tmpw + ((ymin >> 2) - bq0) * UP2_QWORDS + px4 * 3);
+                unsigned win[12];
+                {
+                    const uint4 l0 = tq[0], l1 = tq[1], l2 = tq[2];
+                    const uint4 h0 = tq[UP2_QWORDS / 4], h1 = tq[UP2_QWORDS / 4 + 1], h2 = tq[UP2_QWORDS / 4 + 2];   // spare quad at the end
+                    const unsigned sel = 0x3210u + 0x1111u * (unsigned)off;
+                    const unsigned lw[12] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x, l2.y, l2.z, l2.w};
+                    const unsigned hw[12] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w};
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) win[j] = __byte_perm(lw[j], hw[j], sel);
+                }
+                for (int yy = y0; yy < y1; ++yy) {
+                    const int4 kv = vtab[yy];
+                    bf16* o;
+                    long long plane;
+                    if (layout == 0) {
+                        o = out + (long long)crop * 3 * OUT * OUT + (long long)yy * OUT + px4;
+                        plane = (long long)OUT * OUT;
+                    } else {
+                        const int patch = (yy >> 4) * 24 + (px4 >> 4);
+                        o = out + ((long long)crop * 576 + patch) * 768 + (yy & 15) * 16 + (px4 & 15);
+                        plane = 256;
+                    }
+                    // source order is B, G, R (value j = px*3 + c): plane 0 = R (c = 2), plane 1 = G, plane 2 = B
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        unsigned hv[4];
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            const unsigned wv = win[px * 3 + c];
+                            const int d0 = dp4a_uu((unsigned)kv.x, wv, 1 << (PREC_BITS - 1));
+                            const int d1 = dp4a_uu((unsigned)kv.y, wv, 0);
+                            const int d2 = dp4a_su((unsigned)kv.z, wv, 0);
+                            const int tot = (d2 << 16) + ((d1 << 8) + d0);
+                            hv[px] = lut[(tot >> PREC_BITS) + 128];     // |tot >> 22| < 128 beyond [0, 255]: the table clamps
+                        }
+                        *reinterpret_cast<uint2*>(o + (2 - c) * plane) = make_uint2(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16));
+                    }
+                }
+            }
+            rb0 = rb1;
+            if (rb0 < n_runs) __syncthreads();              // the next band overwrites tmp
+        }
+    }
+}
+
 // crops -> three work lists: [0] fast (crop_resize_up_kernel), [1] tiled / small smem, [2] tiled / large smem
 __global__ void crop_classify_kernel(const CropDesc* __restrict__ crops, int n, int* __restrict__ counts,
-                                     int* __restrict__ lists) {
+                                     int* __restrict__ lists, int v1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int w = crops[i].w, h = crops[i].h;
     if (w <= 0 || h <= 0) return;
-    const int cls = k9_fast_ok(w, h) ? 0 : (k9_smem_need(w, h) <= (size_t)K9_SMEM_SMALL ? 1 : 2);
+    const bool fast = v1 ? k9_fast_ok(w, h) : k9_up2_ok(w, h);
+    const int cls = fast ? 0 : (k9_smem_need(w, h) <= (size_t)K9_SMEM_SMALL ? 1 : 2);
     lists[(long long)cls * n + atomicAdd(counts + cls, 1)] = i;
 }
 
@@ -654,22 +875,30 @@ static size_t k9_list_bytes(int n) { return 64 + sizeof(int) * 3 * (size_t)n; }
 int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int layout, int* err, int* lists_scratch,
                        cudaStream_t stream) {
     static bool attr_set = false;
+    static int k9_v1 = 0;
     if (!attr_set) {
         MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           K9_SMEM_BYTES));
         MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM));
+        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+        const char* e = getenv("MB_K9_V1");
+        k9_v1 = (e && e[0] == '1') ? 1 : 0;
         attr_set = true;
     }
     int* counts = lists_scratch;
     int* lists = lists_scratch + 16;
     MB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), stream));
     MB_CUDA(ctx, cudaMemsetAsync(counts, 0, 4 * sizeof(int), stream));
-    crop_classify_kernel<<<mb_cdiv(n, 256), 256, 0, stream>>>(descs, n, counts, lists);
+    crop_classify_kernel<<<mb_cdiv(n, 256), 256, 0, stream>>>(descs, n, counts, lists, k9_v1);
     MB_LAUNCH_CHECK(ctx);
     const int sms = ctx->num_sms;
-    // common case: one CTA per crop, two resident per SM
-    crop_resize_up_kernel<<<n < 2 * sms * 8 ? n : 2 * sms * 8, UP_THREADS, UP_SMEM, stream>>>(descs, lists, counts, out,
-                                                                                              layout, ctx->f16);
+    // common case: one CTA per crop (grid-stride), three resident per SM
+    if (k9_v1)
+        crop_resize_up_kernel<<<n < 2 * sms * 8 ? n : 2 * sms * 8, UP_THREADS, UP_SMEM, stream>>>(descs, lists, counts, out,
+                                                                                                  layout, ctx->f16);
+    else
+        crop_resize_up2_kernel<<<n < 3 * sms * 4 ? n : 3 * sms * 4, UP2_THREADS, UP2_SMEM, stream>>>(descs, lists, counts, out,
+                                                                                                     layout, ctx->f16);
     MB_LAUNCH_CHECK(ctx);
     constexpr int TPC = 4;            // row tiles per CTA in the small-smem tiled launch
     const int gy = n < sms * 4 ? n : sms * 4;
