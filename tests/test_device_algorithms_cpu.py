@@ -264,3 +264,81 @@ def test_row_extremes_from_text_bit_runs():
                 xs = np.nonzero((labels[y, x0:x0 + bw] == k) & tx[y, x0:x0 + bw])[0]
                 want = (x0 + int(xs.min()), x0 + int(xs.max())) if len(xs) else (0x7fff, -1)
                 assert (mn, mx) == want, (seed, k, r)
+
+
+def test_k9_v2_quads_digits_windows_reproduce_pillow():
+    """Replay of crop_resize_up2_kernel (csrc/imgproc.cu) in numpy: at most FOUR taps on an up-scaled axis (exhaustive over
+    in_size 1..384), three-digit coefficient split for dp4a (k0, k1 unsigned bytes, k2 signed byte), shifted four-column
+    horizontal window, row-quad words + byte-select windows, runs of rows with one window and the band walk over quads —
+    equal to the oracle's Pillow restatement on random crops, including bands (small quad budget) and borders."""
+    from oracle import resample
+    # 1. four taps, digits in range
+    for in_size in range(1, 385):
+        b, kk = resample.pil_coeffs(in_size, 384)
+        assert b[:, 1].max() <= 4
+        k = np.asarray(kk, np.int64)
+        assert (k[:, 4:] == 0).all()
+        k2 = k >> 16
+        assert k2.min() >= -128 and k2.max() <= 127
+        assert (k == (k2 << 16) + (((k >> 8) & 255) << 8) + (k & 255)).all()
+        # window of four source rows / columns never leaves the axis once shifted (in_size >= 4)
+        if in_size >= 4:
+            hx = np.minimum(b[:, 0], in_size - 4)
+            assert (hx >= 0).all() and (b[:, 0] + b[:, 1] <= hx + 4).all()
+
+    def replay(img, QB):
+        h, w, _ = img.shape
+        bv, kv = resample.pil_coeffs(h, 384)
+        bh, kh = resample.pil_coeffs(w, 384)
+        kv = np.asarray(kv, np.int64)[:, :4]
+        kh = np.asarray(kh, np.int64)[:, :4]
+        # horizontal pass through the shifted window
+        hx = np.minimum(bh[:, 0], w - 4)
+        sh = bh[:, 0] - hx
+        hk = np.zeros((384, 4), np.int64)
+        for x in range(384):
+            for j in range(4):
+                if 0 <= j - sh[x] < 4:
+                    hk[x, j] = kh[x, j - sh[x]]
+        nq_total = (h + 3) // 4
+        ymin = bv[:, 0].astype(np.int64)
+        first = np.ones(384, bool)
+        first[1:] = ymin[1:] != ymin[:-1]
+        run_y0 = list(np.nonzero(first)[0]) + [384]
+        n_runs = len(run_y0) - 1
+        out = np.zeros((384, 384, 3), np.uint8)
+        d0k, d1k, d2k = kv & 255, (kv >> 8) & 255, kv >> 16
+        rb0 = 0
+        while rb0 < n_runs:
+            bq0 = int(ymin[run_y0[rb0]] >> 2)
+            rb1 = rb0
+            while rb1 < n_runs and (ymin[run_y0[rb1]] >> 2) <= bq0 + QB - 2:
+                rb1 += 1
+            assert rb1 > rb0
+            nq = min(bq0 + QB, nq_total) - bq0
+            tmp = np.full((QB + 1, 384 * 3, 4), 173, np.int64)          # garbage where nothing is computed
+            for q in range(nq):
+                for r in range(4):
+                    row = min((bq0 + q) * 4 + r, h - 1)
+                    src = img[row].astype(np.int64)
+                    cols = hx[:, None] + np.arange(4)[None, :]
+                    acc = (src[cols] * hk[:, :, None]).sum(1) + (1 << 21)
+                    tmp[q, :, r] = np.clip(acc >> 22, 0, 255).reshape(-1)
+            for r in range(rb0, rb1):
+                y0, y1 = run_y0[r], run_y0[r + 1]
+                q0, off = int(ymin[y0] >> 2) - bq0, int(ymin[y0] & 3)
+                both = np.concatenate([tmp[q0], tmp[q0 + 1]], axis=1)   # 8 bytes: lo quad, hi quad
+                win = both[:, off:off + 4]
+                for yy in range(y0, y1):
+                    tot = ((win * d2k[yy]).sum(1) << 16) + ((win * d1k[yy]).sum(1) << 8) + (win * d0k[yy]).sum(1) + (1 << 21)
+                    idx = (tot >> 22) + 128
+                    assert idx.min() >= 0 and idx.max() < 512
+                    out[yy] = np.clip(tot >> 22, 0, 255).reshape(384, 3)
+            rb0 = rb1
+        return out
+
+    rng = np.random.default_rng(5)
+    for (h, w, QB) in [(63, 170, 21), (63, 170, 5), (5, 4, 13), (1, 9, 13), (384, 384, 13), (200, 33, 6), (97, 384, 13), (30, 7, 2)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = resample.pil_bicubic_resize_u8(img)
+        assert np.array_equal(replay(img, QB), ref), (h, w, QB)
