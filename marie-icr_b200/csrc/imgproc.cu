@@ -615,8 +615,9 @@ crop_resize_up_kernel(const CropDesc* __restrict__ crops, const int* __restrict_
 //   * an up-scaled axis has at most FOUR taps (exhaustive over in_size = 1..384, tests/test_device_algorithms_cpu.py), so
 //     the u8 intermediate is stored as ROW QUADS, tmp[q][x*3+c] = rows 4q..4q+3 of one value in one 32-bit word, and a tap
 //     window at any row offset is one PRMT of two quad words;
-//   * every coefficient k (|k| < 2^23) is split exactly as k = k2*2^16 + k1*2^8 + k0 (k0, k1 unsigned bytes, k2 signed), the
-//     four taps of a digit sit in one word, and a value is THREE dp4a: sum k*v = (d2 << 16) + (d1 << 8) + d0;
+//   * every coefficient k (|k| < 2^23) is split exactly as k = kh*2^16 + kl (kl = k & 0xFFFF unsigned, kh = k >> 16 a signed
+//     byte); a value is two dp2a over the 16-bit halves (taps 0,1 / 2,3) chained through the accumulator, one dp4a over
+//     the four high bytes and one shift-add: sum k*v = (sum kh*v << 16) + sum kl*v;
 //   * consecutive output rows with the same first tap (a "run", 384 / h rows) share the window: a warp third owns a run,
 //     builds the windows of its 4 px x 3 channels once and walks the run with one coefficient fetch per row;
 //   * the horizontal pass keeps the thread's four coefficients in registers (thread = output column) and packs four rows
@@ -627,7 +628,7 @@ crop_resize_up_kernel(const CropDesc* __restrict__ crops, const int* __restrict_
 constexpr int UP2_THREADS = OUT;           // thread t = output column t (horizontal pass) = output row t (tables)
 constexpr int UP2_SMEM = 75 * 1024;        // three CTAs per SM
 constexpr int UP2_QWORDS = OUT * 3;        // words per row quad
-constexpr int UP2_FIXED = OUT * 16 + (OUT + 8) * 4 + 512 * 2 + 64;   // vtab | run_y0 | lut | warp counts
+constexpr int UP2_FIXED = OUT * 16 + (OUT + 8) * 4 + 64;   // vtab | run_y0 | warp counts
 
 __host__ __device__ inline size_t k9_up2_tables(int w) {
     return (size_t)UP2_FIXED + (w > OUT ? (size_t)OUT * 8 + (size_t)OUT * k9_ksize(w) * 4 : 0);
@@ -636,9 +637,14 @@ __host__ __device__ inline bool k9_up2_ok(int w, int h) {
     if (h > OUT || h <= 0 || w < 4) return false;
     return k9_up2_tables(w) + (size_t)6 * UP2_QWORDS * 4 <= (size_t)UP2_SMEM;      // at least five quads + the spare
 }
-__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, int c) {
+__device__ __forceinline__ int dp2a_lo_uu(unsigned a, unsigned b, int c) {
     int d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_uu(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 __device__ __forceinline__ int dp4a_su(unsigned a, unsigned b, int c) {
@@ -658,17 +664,10 @@ __global__ void __launch_bounds__(UP2_THREADS, 3)
 crop_resize_up2_kernel(const CropDesc* __restrict__ crops, const int* __restrict__ list, const int* __restrict__ count,
                        bf16* __restrict__ out, int layout, int f16) {
     extern __shared__ __align__(16) unsigned char smem[];
-    int4* vtab = reinterpret_cast<int4*>(smem);                                  // [OUT] (k0, k1, k2 digit words, ymin)
+    int4* vtab = reinterpret_cast<int4*>(smem);                                  // [OUT] (kl taps 0,1 | kl taps 2,3 | kh bytes | ymin)
     int* run_y0 = reinterpret_cast<int*>(vtab + OUT);                            // [n_runs + 1] first output row of a run
-    unsigned short* lut = reinterpret_cast<unsigned short*>(run_y0 + OUT + 8);   // [512]: index (v >> 22) + 128, clamped
-    int* wcnt = reinterpret_cast<int*>(lut + 512);                               // [16]
+    int* wcnt = run_y0 + OUT + 8;                                                // [16]
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    for (int i = t; i < 512; i += UP2_THREADS) {
-        int u = i - 128;
-        u = u < 0 ? 0 : (u > 255 ? 255 : u);
-        const float v = (((float)u / 255.0f) - 0.5f) / 0.5f;
-        lut[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
-    }
     const int n_list = *count;
     for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int crop = list[li];
@@ -686,14 +685,12 @@ crop_resize_up2_kernel(const CropDesc* __restrict__ crops, const int* __restrict
         {
             int kk[5], ymin, n;
             pil_coef_up(h, t, &ymin, &n, kk);
-            unsigned k0 = 0, k1 = 0, k2 = 0;
+            const unsigned l01 = (unsigned)(kk[0] & 0xFFFF) | ((unsigned)(kk[1] & 0xFFFF) << 16);
+            const unsigned l23 = (unsigned)(kk[2] & 0xFFFF) | ((unsigned)(kk[3] & 0xFFFF) << 16);
+            unsigned k2 = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                k0 |= (unsigned)(kk[i] & 255) << (8 * i);
-                k1 |= (unsigned)((kk[i] >> 8) & 255) << (8 * i);
-                k2 |= (unsigned)((kk[i] >> 16) & 255) << (8 * i);
-            }
-            vtab[t] = make_int4((int)k0, (int)k1, (int)k2, ymin);
+            for (int i = 0; i < 4; ++i) k2 |= (unsigned)((kk[i] >> 16) & 255) << (8 * i);
+            vtab[t] = make_int4((int)l01, (int)l23, (int)k2, ymin);
             if (!wide) {
                 int xmin;
                 pil_coef_up(w, t, &xmin, &n, kk);
@@ -809,17 +806,20 @@ crop_resize_up2_kernel(const CropDesc* __restrict__ crops, const int* __restrict
                     // source order is B, G, R (value j = px*3 + c): plane 0 = R (c = 2), plane 1 = G, plane 2 = B
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        unsigned hv[4];
+                        float fv[4];
 #pragma unroll
                         for (int px = 0; px < 4; ++px) {
                             const unsigned wv = win[px * 3 + c];
-                            const int d0 = dp4a_uu((unsigned)kv.x, wv, 1 << (PREC_BITS - 1));
-                            const int d1 = dp4a_uu((unsigned)kv.y, wv, 0);
-                            const int d2 = dp4a_su((unsigned)kv.z, wv, 0);
-                            const int tot = (d2 << 16) + ((d1 << 8) + d0);
-                            hv[px] = lut[(tot >> PREC_BITS) + 128];     // |tot >> 22| < 128 beyond [0, 255]: the table clamps
+                            int dl = dp2a_lo_uu((unsigned)kv.x, wv, 1 << (PREC_BITS - 1));
+                            dl = dp2a_hi_uu((unsigned)kv.y, wv, dl);
+                            const int dh = dp4a_su((unsigned)kv.z, wv, 0);
+                            const int tot = (dh << 16) + dl;
+                            // clip8, then ToTensor + Normalize(0.5, 0.5) as ONE fma: RN16(fma(u, fl32(2/255), -1)) equals
+                            // RN16(((u / 255) - 0.5) / 0.5) for all 256 values, fp16 and bf16 (tests/test_device_algorithms_cpu.py);
+                            // the table lookup this replaces was a third of the kernel's L1 wavefronts (ncu, r02)
+                            fv[px] = fmaf((float)__vimin_s32_relu(tot >> PREC_BITS, 255), 2.0f / 255.0f, -1.0f);
                         }
-                        *reinterpret_cast<uint2*>(o + (2 - c) * plane) = make_uint2(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16));
+                        *reinterpret_cast<uint2*>(o + (2 - c) * plane) = make_uint2(pack2(fv[0], fv[1], f16), pack2(fv[2], fv[3], f16));
                     }
                 }
             }

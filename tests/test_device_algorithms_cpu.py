@@ -268,7 +268,7 @@ def test_row_extremes_from_text_bit_runs():
 
 def test_k9_v2_quads_digits_windows_reproduce_pillow():
     """Replay of crop_resize_up2_kernel (csrc/imgproc.cu) in numpy: at most FOUR taps on an up-scaled axis (exhaustive over
-    in_size 1..384), three-digit coefficient split for dp4a (k0, k1 unsigned bytes, k2 signed byte), shifted four-column
+    in_size 1..384), the 16 + 8 bit coefficient split (kl = k & 0xFFFF for dp2a, kh = k >> 16 a signed byte for dp4a), shifted four-column
     horizontal window, row-quad words + byte-select windows, runs of rows with one window and the band walk over quads —
     equal to the oracle's Pillow restatement on random crops, including bands (small quad budget) and borders."""
     from oracle import resample
@@ -280,7 +280,7 @@ def test_k9_v2_quads_digits_windows_reproduce_pillow():
         assert (k[:, 4:] == 0).all()
         k2 = k >> 16
         assert k2.min() >= -128 and k2.max() <= 127
-        assert (k == (k2 << 16) + (((k >> 8) & 255) << 8) + (k & 255)).all()
+        assert (k == (k2 << 16) + (k & 0xFFFF)).all()
         # window of four source rows / columns never leaves the axis once shifted (in_size >= 4)
         if in_size >= 4:
             hx = np.minimum(b[:, 0], in_size - 4)
@@ -307,7 +307,7 @@ def test_k9_v2_quads_digits_windows_reproduce_pillow():
         run_y0 = list(np.nonzero(first)[0]) + [384]
         n_runs = len(run_y0) - 1
         out = np.zeros((384, 384, 3), np.uint8)
-        d0k, d1k, d2k = kv & 255, (kv >> 8) & 255, kv >> 16
+        klk, khk = kv & 0xFFFF, kv >> 16
         rb0 = 0
         while rb0 < n_runs:
             bq0 = int(ymin[run_y0[rb0]] >> 2)
@@ -330,7 +330,9 @@ def test_k9_v2_quads_digits_windows_reproduce_pillow():
                 both = np.concatenate([tmp[q0], tmp[q0 + 1]], axis=1)   # 8 bytes: lo quad, hi quad
                 win = both[:, off:off + 4]
                 for yy in range(y0, y1):
-                    tot = ((win * d2k[yy]).sum(1) << 16) + ((win * d1k[yy]).sum(1) << 8) + (win * d0k[yy]).sum(1) + (1 << 21)
+                    dl = (win * klk[yy]).sum(1) + (1 << 21)
+                    assert dl.max() < 2 ** 31
+                    tot = ((win * khk[yy]).sum(1) << 16) + dl
                     idx = (tot >> 22) + 128
                     assert idx.min() >= 0 and idx.max() < 512
                     out[yy] = np.clip(tot >> 22, 0, 255).reshape(384, 3)
@@ -342,3 +344,15 @@ def test_k9_v2_quads_digits_windows_reproduce_pillow():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         ref = resample.pil_bicubic_resize_u8(img)
         assert np.array_equal(replay(img, QB), ref), (h, w, QB)
+
+
+def test_k9_normalise_as_one_fma_is_exact():
+    """crop_resize_up2_kernel replaces the (u / 255 - 0.5) / 0.5 table by fma(u, fl32(2/255), -1) rounded to the 16-bit
+    element type: identical for all 256 pixel values in fp16 and bf16 (the fp32 values themselves differ)."""
+    import torch
+    u = np.arange(256, dtype=np.float32)
+    ref32 = ((u / np.float32(255)) - np.float32(0.5)) / np.float32(0.5)
+    a = np.float32(2.0 / 255.0)
+    y = (u.astype(np.float64) * np.float64(a) - 1.0).astype(np.float32)      # exact product + one rounding = fma
+    for dt in (torch.float16, torch.bfloat16):
+        assert torch.equal(torch.from_numpy(y).to(dt), torch.from_numpy(ref32).to(dt))
