@@ -1,4 +1,3 @@
 set -x
-timeout 300 python -m pytest tests/test_imgproc_gpu.py -x -q -m gpu > gpurun_out/s10_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s10_pytest.log
-python tools/gpu_probe_hbm_stages.py > gpurun_out/s10_hbm_v2.log 2>&1
-tail -3 gpurun_out/s10_pytest.log; cat gpurun_out/s10_hbm_v2.log
+NCROPS=512 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'attn_tc_persist' --launch-skip 2 -c 1 -f -o gpurun_out/s14_attn_pair python tools/gpu_probe_attn.py > gpurun_out/s14_ncu.log 2>&1
+ls -la gpurun_out/s14*
