@@ -1,20 +1,22 @@
 """CPU restatement of the TrOCR recogniser in plain PyTorch fp32 (TEST INFRASTRUCTURE — see oracle/__init__.py).
 
-PARITY UNPINNED against the reference itself: the arithmetic of this half lives in fairseq (unpinned git HEAD) and
-timm==0.6.12, neither vendored under /root/reference nor installed here, and the reference holds no golden vectors
-for it.  What pins this file instead: (i) the reference's own call sites and configuration —
-  encoder   AdaptedVisionTransformer.forward_features   marie/models/unilm/trocr/deit.py:105-146
-            beit_base/large_patch16_384 (qkv_bias=False, LN eps 1e-6)        deit.py:323-337
-            TrOCREncoder.forward (T x B x C, zero padding mask)               trocr_models.py:508-524
-  decoder   fairseq TransformerDecoder built at trocr_models.py:142-147 with the arch defaults of :423-447
-            (dim 1024, ffn 4096, 16 heads, 12 layers, post-LN, ReLU, sinusoidal positions, embed scale sqrt(d),
-            untied bias-free output projection, cross-attention kdim = encoder dim)
-  search    TextRecognitionGenerator._generate                               generator.py:11-374
-            (fairseq BeamSearch.step / finalize_hypos / EnsembleModel.forward_decoder semantics; bos = eos = 2,
-            pad 1, unk 3, min_len 1, max_len = min(max_len_b, 1023), len-normalised scores, 2*beam candidates)
-  text      get_text                                                          marie/document/trocr_ocr_processor.py:142-180
-(ii) an independent cross-check against HuggingFace transformers' port of the same checkpoints
-(tests/test_oracle_trocr.py: ViTModel / TrOCRForCausalLM on identical weights).
+Pinning status, part by part (tests/test_oracle_vs_reference.py, run against /root/reference in the build container):
+  encoder   PINNED on reference-held code: `encoder_forward` == the reference's own
+            AdaptedVisionTransformer.forward_features (marie/models/unilm/trocr/deit.py:105-146) running on the ViT blocks
+            the reference vendors (marie/boxes/dit/ditod/deit.py:44-167; only `timm.models.layers` helpers are stubbed),
+            strict state-dict load, tiny widths and one crop at the beit_base_patch16_384 factory geometry (deit.py:323-329).
+  search    PINNED on the reference's own loop: `generate` == TextRecognitionGenerator._generate (generator.py:11-374)
+            executed from the reference file on the same incremental decoder — tokens, scores and positional scores of every
+            finalised hypothesis, beams 1 / 2 / 3 / 5, batch compaction and max_len EOS forcing.  fairseq's BeamSearch.step /
+            finalize_hypos, which that loop calls, are restated (oracle/ref_loader.load_generator): fairseq is absent.
+  text      PINNED: GPT-2 BPE decode == the reference's GPT2BPEEnhancedSpace.decode (bpe.py:59-67).
+  decoder   PARITY UNPINNED against the reference itself: the layer arithmetic is fairseq's TransformerDecoder (unpinned git
+            HEAD in the reference's requirements, not vendored, not installed; no golden vectors).  Pinned by the reference's
+            construction site and arch defaults instead — trocr_models.py:142-147, :423-447 (dim 1024, ffn 4096, 16 heads,
+            12 layers, post-LN, ReLU, sinusoidal positions, embed scale sqrt(d), untied bias-free output projection,
+            cross-attention kdim = encoder dim), TrOCREncoder.forward (trocr_models.py:508-524) — and by an independent
+            cross-check against HuggingFace transformers' port on identical weights (tests/test_oracle_trocr.py: ViTModel /
+            TrOCRForCausalLM agree to 1e-4).
 
 State-dict keys are fairseq's (`encoder.deit.*`, `decoder.*`), so a real TrOCR checkpoint's `model` dict can be
 passed to the same functions and to marie-icr_b200/weights.py:pack_trocr.
