@@ -68,6 +68,7 @@ class PagePipeline:
         self.ctx = Context.get(self.device)
         self.micro_batch = micro_batch
         self.crop_chunk = crop_chunk          # crops per decode batch (larger = fewer, better filled decoder steps)
+        self.patch_budget_bytes = 24 << 30    # K9 output of one decode batch kept whole up to this size
         self.encode_chunk = encode_chunk      # crops per K9 + encoder pass inside a decode batch (measured: the encoder is
                                               # fastest around 2048 crops, the decoder keeps gaining up to 8192)
         self.max_labels, self.max_boxes = max_labels, max_boxes
@@ -169,16 +170,30 @@ class PagePipeline:
         for i0 in range(0, n, batch):
             m = min(batch, n - i0)
             enc = torch.empty((m, dims["tokens"], dims["enc_dim"]), dtype=self.dtype, device=dev)
+            # K9 for the whole decode batch in one launch set when its patch rows fit the budget (0.88 MB per crop: 14.5 GB
+            # for 16384 crops): one classification / one error check instead of one per encoder pass, and the kernel is
+            # not a 0.6 ms island between two power-capped encoder passes
+            whole = m * 576 * 768 * 2 <= self.patch_budget_bytes
+            patches_all = None
+            if whole:
+                e = self.timer.start()
+                patches_all = ops.pack_crops(pages_dev, rects[i0:i0 + m].contiguous(), page_idx[i0:i0 + m].contiguous(), layout=1)
+                self.timer.stop("k9_crops", e, m)
             for j0 in range(0, m, self.encode_chunk):
-                r = rects[i0 + j0:i0 + min(j0 + self.encode_chunk, m)].contiguous()
-                p = page_idx[i0 + j0:i0 + min(j0 + self.encode_chunk, m)].contiguous()
+                j1 = min(j0 + self.encode_chunk, m)
+                if whole:
+                    patches = patches_all[j0 * 576:j1 * 576]
+                else:
+                    r = rects[i0 + j0:i0 + j1].contiguous()
+                    p = page_idx[i0 + j0:i0 + j1].contiguous()
+                    e = self.timer.start()
+                    patches = ops.pack_crops(pages_dev, r, p, layout=1)
+                    self.timer.stop("k9_crops", e, j1 - j0)
                 e = self.timer.start()
-                patches = ops.pack_crops(pages_dev, r, p, layout=1)
-                self.timer.stop("k9_crops", e, r.shape[0])
-                e = self.timer.start()
-                ops.trocr_encode(patches, out=enc[j0:j0 + r.shape[0]])
-                self.timer.stop("k10_encoder", e, r.shape[0])
+                ops.trocr_encode(patches, out=enc[j0:j1])
+                self.timer.stop("k10_encoder", e, j1 - j0)
                 del patches
+            del patches_all
             e = self.timer.start()
             t, l, s, _ = ops.trocr_decode(enc, beam=beam, max_len_b=max_len_b, out_ld=out_ld)
             self.timer.stop("k11_12_decode", e, m)
