@@ -187,6 +187,12 @@ int mb_layernorm16(mb_ctx* ctx, const void* in_dev, void* out_dev, const float* 
  * -> out [n*T, D].  mode 0 = tcgen05/TMEM kernel (encoder), 1 = mma.sync flash kernel (decoder cross-attention). */
 int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, int n, int T, int D, float scale, int mode,
                    void* stream);
+/* Test hook for the greedy cross-attention core (the per-step attention of fairseq's decoder layers over the encoder
+ * states, marie/models/unilm/trocr/trocr_models.py:142-147, with the K / V projections hoisted out): qp [rows, heads*E]
+ * per-head projected queries, enc [rows*T, E] -> out [rows, heads*E].  mode 0 = tcgen05 / TMA kernel, 1 = mma.sync
+ * kernel.  finished (or null): rows to skip; live_ws: rows + 1 ints of scratch (mode 0 with a finished mask). */
+int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_dev, void* out_dev, int rows, int T, int heads, int E,
+                   const unsigned char* finished_dev, int32_t* live_ws_dev, int mode, void* stream);
 int mb_trocr_dims(mb_ctx* ctx, int* dims4_host);
 /* cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded} */
 int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3_host);

@@ -889,6 +889,24 @@ int mb_encode_2d_map(mb_ctx* ctx, CUtensorMap* m, const void* base, long long co
     return 0;
 }
 
+// 3-D 16-bit tensor [d2][d1][d0] (d0 contiguous, pitches ld1 / ld2 in elements) -> TMA map with a {b0, b1, 1} box,
+// 128-byte swizzle (xattn_tc.cu: encoder states [crops][T][E]; rows beyond d1 are zero-filled, never fetched).
+int mb_encode_3d_map(mb_ctx* ctx, CUtensorMap* m, const void* base, long long d0, long long d1, long long d2, long long ld1,
+                     long long ld2, int b0, int b1) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld1 * 2, (cuuint64_t)ld2 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, ctx->f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                    const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return mb_set_err(ctx, MB_ERR_CUDA, "cuTensorMapEncodeTiled(3d %lld x %lld x %lld) -> %d", d0, d1, d2, (int)r);
+    return 0;
+}
+
 int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     MB_REQUIRE(ctx, g.a0 && g.wgt && g.out, "tap_gemm: null pointer");
     MB_REQUIRE(ctx, g.c0 > 0 && g.c0 % BLOCK_K == 0 && g.c1 >= 0 && g.c1 % BLOCK_K == 0,

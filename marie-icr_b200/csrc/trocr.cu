@@ -23,6 +23,11 @@
 
 int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D, int heads, float scale_log2e,
                     cudaStream_t stream);
+// xattn_tc.cu: greedy cross-attention over the encoder states on tcgen05 / TMA
+bool mb_cross_enc_tc_supported(int E, int heads);
+int mb_live_list(mb_ctx* ctx, const unsigned char* finished, int n, int* live_ws, cudaStream_t s);
+int mb_cross_enc_tc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* out, int rows, int T, int heads, int E,
+                    const int* live_ws, cudaStream_t s);
 
 namespace {
 
@@ -1008,6 +1013,7 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
 }
 
 struct DecodeWs {
+    int* live = nullptr;          // greedy mode, tcgen05 cross-attention: compacted list of open crops + its counter (n + 1)
     bf16 *cross_kv, *kcache, *vcache, *x, *qkv, *att, *tmp, *ffn;
     int kv_cap = 0;               // steps the K / V caches currently hold per layer
     bf16 *qp, *ctxe;              // greedy mode: per-head projected queries / attended encoder states [R, heads*E]
@@ -1015,6 +1021,13 @@ struct DecodeWs {
     float* logits; float* cand_val; int* cand_idx;
     SearchState st;
 };
+
+// the tcgen05 / TMA cross-attention (xattn_tc.cu) is the default greedy kernel; MB_XE_TC=0 selects the mma.sync kernel
+bool cross_tc(const TrocrModel* m) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MB_XE_TC"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1 && mb_cross_enc_tc_supported(m->enc_dim, m->dec_heads);
+}
 
 // beam 1 attends over the encoder states directly (dec_cross_enc_kernel); MB_CROSS_CACHED=1 forces the K/V-cache path
 bool cross_uncached(const TrocrModel* m, int beam) {
@@ -1033,6 +1046,7 @@ size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* b
         w->cross_kv = nullptr;
         w->qp = a.take<bf16>((size_t)R * m->dec_heads * m->enc_dim);
         w->ctxe = a.take<bf16>((size_t)R * m->dec_heads * m->enc_dim);
+        w->live = a.take<int>((size_t)n + 1);
     } else {
         w->qp = w->ctxe = nullptr;
         w->cross_kv = a.take<bf16>((size_t)L * n * T * 2 * H);
@@ -1092,6 +1106,9 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     // -> P E, three barriers), not by arithmetic: 16-key tiles through a four-stage ring (three tiles = 72 KB in flight per
     // CTA, two CTAs / SM) measured 8.70 ms per decode step at 2048 live crops against 9.66 for 32-key tiles x 2 stages
     // (tools/gpu_probe_decode.py; MB_XE_MODE = 0: 32 x 2, 1: 16 x 2 (4 CTAs / SM, 11.8 ms), 2: 16 x 3 (8.8), 3: 16 x 4, 4: 8 warps (12.2)).
+    if (cross_tc(m)) {
+        rc = mb_cross_enc_tc(ctx, w.qp, enc_out, w.ctxe, n, T, heads, E, w.live, s);
+    } else {
     static int xe_mode = -1;
     if (xe_mode < 0) { const char* e = getenv("MB_XE_MODE"); xe_mode = e ? atoi(e) : 3; if (xe_mode < 0 || xe_mode > 4) xe_mode = 3; }
     if (E == 768 && xe_mode == 1) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 2, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
@@ -1102,6 +1119,7 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     else if (E == 1024) rc = ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 256, 4, 2>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
     else if (E == 128) rc = ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 32, 4, 3>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
     else return mb_set_err(ctx, MB_ERR_STATE, "cross_enc_attention: unsupported encoder width %d", E);
+    }
     if (rc) return rc;
     TapGemm v;                                    // att^h = Wv^h ctx^h + bv^h : [R, H]
     v.a0 = w.ctxe; v.c0 = E; v.a0_ld = heads * E; v.n = 1; v.h = 1; v.w = n;
@@ -1160,6 +1178,7 @@ int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const bf16* enc_out, i
     RC(ensure_kv(ctx, m, w, R, step + 1, step, max_len + 1, s));
     dec_embed_kernel<<<R, 128, 0, s>>>(w.st.tokens, max_len + 2, step, m->embed, m->pe, w.x, R, H, sqrtf((float)H), ctx->f16);
     MB_LAUNCH_CHECK(ctx);
+    if (w.greedy && cross_tc(m)) RC(mb_live_list(ctx, w.st.finished, n, w.live, s));   // open crops of this step, all layers
     for (int l = 0; l < m->dec_layers; ++l) {
         const DecLayer& L = m->dec[l];
         const size_t cache_off = (size_t)l * w.kv_cap * R * H;
@@ -1323,6 +1342,34 @@ extern "C" int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, i
     else attention_kernel<false><<<grid, 128, ATT_SMEM, s>>>(q, 3LL * D, q + D, q + 2 * D, 3LL * D, (bf16*)out_dev, D, T, T, scale_log2e);
     MB_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// Test hook: the greedy cross-attention core on its own.  qp [rows, heads*E] (per-head projected queries), enc [rows*T, E]
+// -> out [rows, heads*E] = softmax_t(qp^h . e_t) . e.  mode 0: tcgen05 / TMA kernel (xattn_tc.cu), 1: mma.sync kernel.
+// finished (or null): rows to skip; live_ws: rows + 1 ints of scratch for mode 0's compacted row list.
+extern "C" int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_dev, void* out_dev, int rows, int T, int heads,
+                              int E, const unsigned char* finished_dev, int32_t* live_ws_dev, int mode, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
+    if (!ctx) return MB_ERR_ARG;
+    MB_REQUIRE(ctx, rows > 0 && T > 0 && heads > 0 && heads <= 16, "cross_enc16: bad geometry");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bf16* qp = (const bf16*)qp_dev;
+    const bf16* enc = (const bf16*)enc_dev;
+    bf16* out = (bf16*)out_dev;
+    if (mode == 0) {
+        if (finished_dev) {
+            MB_REQUIRE(ctx, live_ws_dev != nullptr, "cross_enc16: live_ws is required with a finished mask");
+            RC(mb_live_list(ctx, finished_dev, rows, live_ws_dev, s));
+        }
+        return mb_cross_enc_tc(ctx, qp, enc, out, rows, T, heads, E, finished_dev ? live_ws_dev : nullptr, s);
+    }
+    if (E == 768) return ctx->f16 ? launch_cross_enc<true, 192, 4, 4, 16>(ctx, qp, enc, out, rows, T, heads, finished_dev, s)
+                                  : launch_cross_enc<false, 192, 4, 4, 16>(ctx, qp, enc, out, rows, T, heads, finished_dev, s);
+    if (E == 1024) return ctx->f16 ? launch_cross_enc<true, 256, 4, 2>(ctx, qp, enc, out, rows, T, heads, finished_dev, s)
+                                   : launch_cross_enc<false, 256, 4, 2>(ctx, qp, enc, out, rows, T, heads, finished_dev, s);
+    if (E == 128) return ctx->f16 ? launch_cross_enc<true, 32, 4, 3>(ctx, qp, enc, out, rows, T, heads, finished_dev, s)
+                                  : launch_cross_enc<false, 32, 4, 3>(ctx, qp, enc, out, rows, T, heads, finished_dev, s);
+    return mb_set_err(ctx, MB_ERR_ARG, "cross_enc16: unsupported encoder width %d", E);
 }
 
 // cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded}

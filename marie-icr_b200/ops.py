@@ -290,6 +290,18 @@ def attention16(qkv, n, T, scale=0.125, mode=0):
     return out
 
 
+def cross_enc16(qp, enc, T, heads, finished=None, mode=0):
+    """Greedy cross-attention core.  qp [rows, heads*E], enc [rows*T, E] 16-bit -> [rows, heads*E].
+    mode 0: tcgen05 / TMA kernel, 1: mma.sync kernel.  finished: optional [rows] uint8 mask of rows to skip."""
+    rows = qp.shape[0]
+    E = enc.shape[1]
+    out = torch.zeros_like(qp)
+    live = torch.empty((rows + 1,), dtype=torch.int32, device=qp.device)
+    _ctx(qp).call("mb_cross_enc16", ptr(qp.contiguous()), ptr(enc.contiguous()), ptr(out), c_int(rows), c_int(T), c_int(heads),
+                  c_int(E), ptr(finished), ptr(live), c_int(mode), cur_stream())
+    return out
+
+
 def gemm16_batched(a, w, batches, n, k, a_col_stride, w_row_stride, out_col_stride, out_cols, bias=None, act=ACT_NONE):
     """Block-diagonal GEMM (see mb_gemm16_batched).  a [M, lda], w [rows, k] -> out [M, out_cols]."""
     M = a.shape[0]

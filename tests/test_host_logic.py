@@ -392,3 +392,16 @@ def test_frames_from_tiff_and_burst(tmp_path):
     before = [os.path.getmtime(n) for n in names]
     burst_frames("s3://bucket/doc.tif", frames, str(tmp_path / "assets"))         # same page count: skipped
     assert before == [os.path.getmtime(n) for n in names]
+
+
+def test_decode_batches_cover_all_crops_and_respect_the_chunk():
+    from marie_icr_b200.pipeline import decode_batches
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        n, c = int(rng.integers(0, 40000)), int(rng.integers(1, 20000))
+        b = decode_batches(n, c)
+        assert sum(b) == n and all(0 < x <= c for x in b)
+        if n <= c:
+            assert b == ([n] if n else [])
+    # the bench's configuration: two full batches and a short last one (host post-processing tail)
+    assert decode_batches(32945, 16384) == [14120, 14120, 4705]
