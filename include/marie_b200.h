@@ -187,6 +187,12 @@ int mb_layernorm16(mb_ctx* ctx, const void* in_dev, void* out_dev, const float* 
  * -> out [n*T, D].  mode 0 = tcgen05/TMEM kernel (encoder), 1 = mma.sync flash kernel (decoder cross-attention). */
 int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, int n, int T, int D, float scale, int mode,
                    void* stream);
+/* Test hook for the residual GEMM that leaves the next LayerNorm's row statistics behind (encoder proj / fc2 in front of
+ * the folded LayerNorms, marie/models/unilm/trocr/deit.py:105-146): out = a W^T + bias + residual, stats_out [M, 2] fp32 =
+ * (-mean, rstd) of the written rows.  part_ws: M * 4 * ceil(N / 256) floats of scratch. */
+int mb_gemm16_res_stats(mb_ctx* ctx, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+                        void* out_dev, long long M, int N, int K, float eps, float* part_ws_dev, float* stats_out_dev,
+                        void* stream);
 /* Test hook for the greedy cross-attention core (the per-step attention of fairseq's decoder layers over the encoder
  * states, marie/models/unilm/trocr/trocr_models.py:142-147, with the K / V projections hoisted out): qp [rows, heads*E]
  * per-head projected queries, enc [rows*T, E] -> out [rows, heads*E].  mode 0 = tcgen05 / TMA kernel, 1 = mma.sync

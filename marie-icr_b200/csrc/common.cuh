@@ -115,6 +115,11 @@ struct TapGemm {
     // bias[n] = b[n] + sum_k beta_k W[n, k].  ln_stats: per row (-mean, rstd) pairs (trocr.cu ln_stats_kernel).
     const float* ln_stats = nullptr;
     const float* ln_c = nullptr;
+    // Row statistics of the OUTPUT, for the LayerNorm that follows a residual GEMM (encoder proj / fc2): the TMA epilogue
+    // adds up x and x^2 of the values it writes (fp32, before the 16-bit rounding) and stores one (sum, sum of squares)
+    // pair per row, 256-column N tile and epilogue-warp half: stat_out[row * 2 * n_tiles + 2 * tile + half] as float2.
+    // Needs block_n = 256 (set it), a residual, no activation, the TMA epilogue; saves the separate pass over the stream.
+    float* stat_out = nullptr;
 };
 int mb_tap_gemm(mb_ctx* ctx, const TapGemm& p, cudaStream_t stream);
 void mb_profile_drain(mb_ctx* ctx);

@@ -64,6 +64,7 @@ struct KParams {
     int batches, a_col_stride, w_row_stride, out_col_stride;   // block-diagonal (per-head) GEMMs
     const float2* ln_stats;   // LNF: per row (-mean, rstd)
     const float* ln_c;        // LNF: per column sum_k W'[n, k]
+    float2* stat_out;         // STATS: per row, N tile and epilogue-warp half (sum, sum of squares) of the written values
     unsigned int* diag;
     unsigned backoff;         // ns slept between polls of the long waits (0 = poll continuously)
     // 3x3 (dilation 1) convolutions: a stage holds the A tile of one image row WITH a one-pixel halo (130 pixel rows) and
@@ -138,7 +139,7 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2t(float a, float b)
 // staging tile and hands it to the TMA (cp.async.bulk.tensor store, ragged edges clipped by the tensor map); the residual
 // tile arrives the same way (TMA load, one chunk ahead).  No fp32 staging round trip, no per-thread global address
 // arithmetic, no separate ragged path.
-template <int ACT, int OUT, bool RES, bool F16, bool CG2, bool LNF = false, bool TMAOUT = false>
+template <int ACT, int OUT, bool RES, bool F16, bool CG2, bool LNF = false, bool TMAOUT = false, bool STATS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -461,6 +462,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const TileC t = coords(tile);
             const long long pix0 = ((long long)t.nn * p.h + t.hh) * p.w + t.wrow;
             f32x2 nm2 = 0, rstd2 = 0;
+            f32x2 st_s = 0, st_q = 0;                    // STATS: this lane's row, this warp's chunks of the tile
             if (LNF) {
                 const float2 st = lane < t.rows_valid ? __ldg(p.ln_stats + pix0 + lane) : make_float2(0.f, 0.f);
                 nm2 = pk2(st.x, st.x);
@@ -524,6 +526,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         xa = add2(xa, pk2(r0.x, r0.y));
                         xb = add2(xb, pk2(r1.x, r1.y));
                     }
+                    if (STATS) {
+                        st_s = add2(st_s, add2(xa, xb));
+                        st_q = fma2(xa, xa, st_q);
+                        st_q = fma2(xb, xb, st_q);
+                    }
                     float f0, f1, f2, f3;
                     upk2(xa, f0, f1);
                     upk2(xb, f2, f3);
@@ -557,6 +564,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) release_tile(as);
+            }
+            if (STATS) {
+                if (lane < t.rows_valid) {
+                    float s0, s1, q0, q1;
+                    upk2(st_s, s0, s1);
+                    upk2(st_q, q0, q1);
+                    p.stat_out[(pix0 + lane) * (2 * p.n_tiles) + 2 * (t.ntile0 / p.block_n) + half] = make_float2(s0 + s1, q0 + q1);
+                }
             }
             as ^= 1;
             if (as == 0) aphase ^= 1;
@@ -958,8 +973,11 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     // two-CTA mode (cta_group::2): big 16-bit-output problems with full 256-wide N tiles; MB_GEMM2=0 disables it
     static int gemm2_env = -1;
     if (gemm2_env < 0) { const char* e = getenv("MB_GEMM2"); gemm2_env = (e && e[0] == '1') ? 1 : 0; }
+    const bool stats = g.stat_out != nullptr;
+    MB_REQUIRE(ctx, !stats || (tma_out && res && !lnf && g.act == MB_ACT_NONE && nbatch == 1 && g.n_out % 32 == 0 && block_n == 256),
+               "tap_gemm: row statistics need the TMA epilogue of a residual GEMM with block_n = 256");
     const bool cg2 = gemm2_env == 1 && block_n == 256 && g.out_mode == MB_OUT_BF16 && p.m_tiles >= 2 * ctx->num_sms &&
-                     (g.batches <= 1) && (!lnf || tma_out);
+                     (g.batches <= 1) && (!lnf || tma_out) && !stats;
     // halo mode: 3x3 / dilation 1 convolutions (one A load per image row instead of three); small layers also keep the whole
     // weight matrix in shared memory.  MB_HALO=0 switches it off (A/B timing).
     const char* halo_env = getenv("MB_HALO");
@@ -989,6 +1007,7 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
     p.batches = g.batches > 0 ? g.batches : 1;
     p.a_col_stride = g.a_col_stride; p.w_row_stride = g.w_row_stride; p.out_col_stride = g.out_col_stride;
     p.ln_stats = reinterpret_cast<const float2*>(g.ln_stats); p.ln_c = g.ln_c;
+    p.stat_out = reinterpret_cast<float2*>(g.stat_out);
     p.diag = ctx->dev_diag;
     { const char* e = getenv("MB_SPIN_SLEEP"); p.backoff = e ? (unsigned)atoi(e) : 0u; }
     MB_REQUIRE(ctx, !lnf || (g.ln_c && g.out_mode == MB_OUT_BF16 && !g.residual && g.taps == 1 && g.n == 1 && g.h == 1),
@@ -1062,6 +1081,9 @@ int mb_tap_gemm(mb_ctx* ctx, const TapGemm& g, cudaStream_t stream) {
         MB_PICKT(MB_ACT_RELU, true, false) MB_PICKT(MB_ACT_GELU, false, false) MB_PICKT(MB_ACT_GELU, true, false)
         MB_PICKT(MB_ACT_NONE, false, true) MB_PICKT(MB_ACT_GELU, false, true)
 #undef MB_PICKT
+        if (stats)
+            fn = h ? (KernelFn)tap_gemm_kernel<MB_ACT_NONE, MB_OUT_BF16, true, true, false, false, true, true>
+                   : (KernelFn)tap_gemm_kernel<MB_ACT_NONE, MB_OUT_BF16, true, false, false, false, true, true>;
     }
 #undef MB_PICK
 #undef MB_PICK2

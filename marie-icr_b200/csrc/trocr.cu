@@ -897,6 +897,23 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const bf16* __restrict__ 
     }
 }
 
+// (sum, sum of squares) partials written by the residual GEMM's epilogue (TapGemm::stat_out) -> (-mean, rstd) per row.
+// var = E[x^2] - mean^2 in fp32: the stream's row means are small against its spread, the cancellation costs ~1e-6.
+__global__ void __launch_bounds__(256) ln_stats_finish_kernel(const float2* __restrict__ part, float2* __restrict__ stats,
+                                                              long long rows, int slots, float inv_d, float eps) {
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int i = 0; i < slots; ++i) {
+            const float2 v = part[row * slots + i];
+            s += v.x;
+            q += v.y;
+        }
+        const float mean = s * inv_d;
+        const float var = fmaxf(fmaf(-mean, mean, q * inv_d), 0.f);
+        stats[row] = make_float2(-mean, rsqrtf(var + eps));
+    }
+}
+
 int attention_setup(mb_ctx* ctx) {
     static bool done = false;
     if (done) return 0;
@@ -918,6 +935,29 @@ int gemm(mb_ctx* ctx, const bf16* a, int K, const bf16* w, int rows_w, long long
     g.residual = residual; g.res_ld = N;
     g.out = out; g.out_ld = N; g.out_mode = out_mode;
     return mb_tap_gemm(ctx, g, s);
+}
+
+// residual GEMM (out = a W^T + b + residual) that also leaves the LayerNorm statistics of its output rows in `stats`
+int gemm_res_stats(mb_ctx* ctx, const bf16* a, int K, const bf16* w, long long M, int N, const float* bias, const bf16* residual,
+                   bf16* out, float* part, float* stats, float eps, cudaStream_t s) {
+    TapGemm g;
+    g.a0 = a; g.c0 = K; g.a0_ld = K;
+    g.n = 1; g.h = 1; g.w = (int)M;
+    g.wgt = w; g.n_rows_w = N; g.n_out = N;
+    g.bias = bias; g.act = MB_ACT_NONE;
+    g.residual = residual; g.res_ld = N;
+    g.out = out; g.out_ld = N; g.out_mode = MB_OUT_BF16;
+    g.block_n = 256;
+    g.stat_out = part;
+    int rc = mb_tap_gemm(ctx, g, s);
+    if (rc) return rc;
+    const int slots = 2 * mb_cdiv(N, 256);
+    const long long blocks = (M + 255) / 256;
+    const long long cap = (long long)ctx->num_sms * 8;
+    ln_stats_finish_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(reinterpret_cast<const float2*>(part),
+                                                                                  reinterpret_cast<float2*>(stats), M, slots, 1.0f / (float)N, eps);
+    MB_LAUNCH_CHECK(ctx);
+    return 0;
 }
 
 int layernorm(mb_ctx* ctx, const bf16* in, bf16* out, const float* g, const float* b, long long rows, int D, float eps,
@@ -963,7 +1003,7 @@ int grid1d(mb_ctx* ctx, long long total, int threads) {
 
 // patches [n*576, 768] -> enc_out [n*577, D]; ws must hold x, y [n*577*D] and big [n*577*max(3D, ffn)]
 int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out, bf16* x, bf16* y, bf16* big,
-           float* stats, cudaStream_t s) {
+           float* stats, float* stat_part, cudaStream_t s) {
     const int D = m->enc_dim, T = m->tokens, F = m->enc_ffn;
     const long long M = (long long)n * T;
     // patch embedding (Conv2d k=s=16 == GEMM over patch rows) into `big`, then cls/pos assembly into x
@@ -978,11 +1018,24 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
     // its in-situ cost (sustained clocks, warm L2) is the difference of two runs.  Results are garbage when set.
     const char* skip_env = getenv("MB_PROBE_SKIP");
     const std::string skip = skip_env ? skip_env : "";
+    // the residual GEMMs (proj, fc2) leave the row statistics of the stream they write for the LayerNorm fold of the next
+    // GEMM: the separate 2 B / element pass of ln_stats_kernel only runs in front of the first layer.  MB_LNSTAT_FUSE=0
+    // (and the two-CTA GEMM mode) keep the separate pass.
+    static int fuse_env = -1;
+    if (fuse_env < 0) {
+        const char* e = getenv("MB_LNSTAT_FUSE");
+        const char* g2 = getenv("MB_GEMM2");
+        const char* et = getenv("MB_EPI_TMA");
+        fuse_env = ((e && e[0] == '0') || (g2 && g2[0] == '1') || (et && et[0] == '0')) ? 0 : 1;
+    }
+    const bool fuse = fuse_env == 1 && stat_part != nullptr && D % 32 == 0 && skip.empty();
+    bool have_stats = false;                       // `stats` already describes x (written by the previous residual GEMM)
     for (int l = 0; l < m->enc_layers; ++l) {
         const EncLayer& L = m->enc[l];
         const bool fold = m->ln_fold && L.qkv_wf && L.fc1_wf;
+        const bool next_fold = l + 1 < m->enc_layers && m->ln_fold && m->enc[l + 1].qkv_wf && m->enc[l + 1].fc1_wf;
         if (fold) {
-            if (skip != "ln") RC(ln_stats(ctx, x, stats, M, D, 1e-6f, s));
+            if (skip != "ln" && !have_stats) RC(ln_stats(ctx, x, stats, M, D, 1e-6f, s));
             if (skip != "qkv") RC(gemm_ln(ctx, x, D, L.qkv_wf, M, 3 * D, L.qkv_bf, L.qkv_c, stats, MB_ACT_NONE, big, s));
         } else {
             RC(layernorm(ctx, x, y, L.ln1_w, L.ln1_b, M, D, 1e-6f, s));
@@ -998,15 +1051,23 @@ int encode(mb_ctx* ctx, TrocrModel* m, const bf16* patches, int n, bf16* enc_out
             else attention_kernel<false><<<grid, 128, ATT_SMEM, s>>>(big, 3LL * D, big + D, big + 2 * D, 3LL * D, y, D, T, T, scale_log2e);
             MB_LAUNCH_CHECK(ctx);
         }
-        if (skip != "proj") RC(gemm(ctx, y, D, L.proj_w, D, M, D, L.proj_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
+        have_stats = false;
+        if (fold && fuse) {
+            RC(gemm_res_stats(ctx, y, D, L.proj_w, M, D, L.proj_b, x, x, stat_part, stats, 1e-6f, s));
+            have_stats = true;
+        } else if (skip != "proj") RC(gemm(ctx, y, D, L.proj_w, D, M, D, L.proj_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
         if (fold) {
-            if (skip != "ln") RC(ln_stats(ctx, x, stats, M, D, 1e-6f, s));
+            if (skip != "ln" && !have_stats) RC(ln_stats(ctx, x, stats, M, D, 1e-6f, s));
             if (skip != "fc1") RC(gemm_ln(ctx, x, D, L.fc1_wf, M, F, L.fc1_bf, L.fc1_c, stats, MB_ACT_GELU, big, s));
         } else {
             RC(layernorm(ctx, x, y, L.ln2_w, L.ln2_b, M, D, 1e-6f, s));
             RC(gemm(ctx, y, D, L.fc1_w, F, M, F, L.fc1_b, MB_ACT_GELU, nullptr, big, MB_OUT_BF16, s));
         }
-        if (skip != "fc2") RC(gemm(ctx, big, F, L.fc2_w, D, M, D, L.fc2_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
+        have_stats = false;
+        if (fuse && next_fold) {
+            RC(gemm_res_stats(ctx, big, F, L.fc2_w, M, D, L.fc2_b, x, x, stat_part, stats, 1e-6f, s));
+            have_stats = true;
+        } else if (skip != "fc2") RC(gemm(ctx, big, F, L.fc2_w, D, M, D, L.fc2_b, MB_ACT_NONE, x, x, MB_OUT_BF16, s));
     }
     RC(layernorm(ctx, x, enc_out, m->norm_w, m->norm_b, M, D, 1e-6f, s));
     return 0;
@@ -1344,6 +1405,18 @@ extern "C" int mb_attention16(mb_ctx* ctx, const void* qkv_dev, void* out_dev, i
     return 0;
 }
 
+// Test hook: out = a W^T + bias + residual (16-bit) through the residual GEMM whose epilogue also produces the LayerNorm
+// statistics of the rows it writes: stats_out [M, 2] fp32 = (-mean, rstd).  part_ws: M * 4 * ceil(N / 256) floats.
+extern "C" int mb_gemm16_res_stats(mb_ctx* ctx, const void* a_dev, const void* w_dev, const float* bias_dev,
+                                   const void* residual_dev, void* out_dev, long long M, int N, int K, float eps,
+                                   float* part_ws_dev, float* stats_out_dev, void* stream) {
+    MbDeviceGuard _mb_guard(ctx);
+    if (!ctx) return MB_ERR_ARG;
+    MB_REQUIRE(ctx, M > 0 && N > 0 && K > 0 && part_ws_dev && stats_out_dev, "gemm16_res_stats: bad arguments");
+    return gemm_res_stats(ctx, (const bf16*)a_dev, K, (const bf16*)w_dev, M, N, bias_dev, (const bf16*)residual_dev,
+                          (bf16*)out_dev, part_ws_dev, stats_out_dev, eps, (cudaStream_t)stream);
+}
+
 // Test hook: the greedy cross-attention core on its own.  qp [rows, heads*E] (per-head projected queries), enc [rows*T, E]
 // -> out [rows, heads*E] = softmax_t(qp^h . e_t) . e.  mode 0: tcgen05 / TMA kernel (xattn_tc.cu), 1: mma.sync kernel.
 // finished (or null): rows to skip; live_ws: rows + 1 ints of scratch for mode 0's compacted row list.
@@ -1389,14 +1462,16 @@ extern "C" int mb_trocr_encode(mb_ctx* ctx, const void* patches_dev, int n, void
     const int D = m->enc_dim, T = m->tokens;
     const size_t wide = (size_t)(3 * D > m->enc_ffn ? 3 * D : m->enc_ffn);
     const size_t M = (size_t)n * T;
-    const size_t bytes = (2 * M * D + M * wide) * 2 + M * 8 + 2048;
+    const size_t part_floats = M * 4 * (size_t)mb_cdiv(D, 256);           // (sum, sum of squares) x 2 halves x N tiles per row
+    const size_t bytes = (2 * M * D + M * wide) * 2 + M * 8 + part_floats * 4 + 4096;
     RC(ensure_arena(ctx, m, bytes));
     Arena a{(unsigned char*)m->arena, 0, 0};
     bf16* x = a.take<bf16>(M * D);
     bf16* y = a.take<bf16>(M * D);
     bf16* big = a.take<bf16>(M * wide);
     float* stats = a.take<float>(M * 2);
-    return encode(ctx, m, (const bf16*)patches_dev, n, (bf16*)enc_out_dev, x, y, big, stats, (cudaStream_t)stream);
+    float* stat_part = a.take<float>(part_floats);
+    return encode(ctx, m, (const bf16*)patches_dev, n, (bf16*)enc_out_dev, x, y, big, stats, stat_part, (cudaStream_t)stream);
 }
 
 // Greedy (beam 1) / beam search over encoder states.  tokens_out [n, out_ld] i32 (hypothesis incl. the final EOS,

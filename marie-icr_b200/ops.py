@@ -290,6 +290,19 @@ def attention16(qkv, n, T, scale=0.125, mode=0):
     return out
 
 
+def gemm16_res_stats(a, w, bias, residual, eps=1e-6):
+    """out = a @ w.T + bias + residual (16-bit) and the LayerNorm statistics (-mean, rstd) [M, 2] fp32 of its rows,
+    produced by the GEMM's own epilogue (mb_gemm16_res_stats)."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    part = torch.empty((M * 4 * ((N + 255) // 256),), dtype=torch.float32, device=a.device)
+    stats = torch.empty((M, 2), dtype=torch.float32, device=a.device)
+    _ctx(a).call("mb_gemm16_res_stats", ptr(a.contiguous()), ptr(w.contiguous()), ptr(bias), ptr(residual.contiguous()), ptr(out),
+                 c_ll(M), c_int(N), c_int(K), c_float(eps), ptr(part), ptr(stats), cur_stream())
+    return out, stats
+
+
 def cross_enc16(qp, enc, T, heads, finished=None, mode=0):
     """Greedy cross-attention core.  qp [rows, heads*E], enc [rows*T, E] 16-bit -> [rows, heads*E].
     mode 0: tcgen05 / TMA kernel, 1: mma.sync kernel.  finished: optional [rows] uint8 mask of rows to skip."""

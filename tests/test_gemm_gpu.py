@@ -141,3 +141,26 @@ def test_tma_epilogue_equals_register_epilogue(cuda_ctx, dtype16, M, N, K):
     finally:
         os.environ.pop("MB_EPI_TMA", None)
     assert torch.equal(x, ops.gemm16(a, w, bias=bias, residual=res))
+
+
+@pytest.mark.parametrize("M,N,K", [(577 * 3, 768, 768), (1000, 768, 3072), (130, 1024, 1024), (257, 128, 256), (5, 768, 768)])
+def test_residual_gemm_leaves_layernorm_statistics(cuda_ctx, dtype16, M, N, K):
+    """The residual GEMM's epilogue sums x and x^2 of the rows it writes (TapGemm::stat_out); the finished (-mean, rstd)
+    pairs must describe the stored rows like ln_stats_kernel's two-pass statistics do (encoder proj / fc2 in front of the
+    folded LayerNorms)."""
+    import torch
+    from marie_icr_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(dtype16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype16)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = (torch.randn(M, N, device="cuda") * 2 + 0.7).to(dtype16)        # non-zero row means
+    out, stats = ops.gemm16_res_stats(a, w, bias, res)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    tol = 2e-3 if dtype16 == torch.float16 else 1.6e-2
+    assert ((out.float() - ref).norm() / ref.norm()).item() <= tol
+    x = out.float()                                                       # statistics of what was stored
+    mean, var = x.mean(1), x.var(1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-6)
+    assert (stats[:, 0] + mean).abs().max().item() <= 2e-3 * x.abs().max().item()
+    assert ((stats[:, 1] - rstd).abs() / rstd).max().item() <= 2e-3
