@@ -660,9 +660,12 @@ __device__ __forceinline__ unsigned pack_sat4(int a0, int a1, int a2, int a3) {
     return d;
 }
 
+template <bool HWORD, int LAYOUT>
 __global__ void __launch_bounds__(UP2_THREADS, 3)
 crop_resize_up2_kernel(const CropDesc* __restrict__ crops, const int* __restrict__ list, const int* __restrict__ count,
-                       bf16* __restrict__ out, int layout, int f16) {
+                       bf16* __restrict__ out, int f16) {
+    constexpr bool hword = HWORD;
+    constexpr int layout = LAYOUT;
     extern __shared__ __align__(16) unsigned char smem[];
     int4* vtab = reinterpret_cast<int4*>(smem);                                  // [OUT] (kl taps 0,1 | kl taps 2,3 | kh bytes | ymin)
     int* run_y0 = reinterpret_cast<int*>(vtab + OUT);                            // [n_runs + 1] first output row of a run
@@ -738,7 +741,43 @@ crop_resize_up2_kernel(const CropDesc* __restrict__ crops, const int* __restrict
             const int rb1 = lo;
             const int nq = min(bq0 + QB, (h + 3) >> 2) - bq0;        // quads with source rows in this band
             // ---- horizontal pass: thread = output column, item = row quad
-            if (!wide) {
+            if (!wide && hword) {
+                // the window's twelve bytes (4 px x 3 channels from hsrc + row * pitch, any alignment) as aligned 32-bit
+                // loads + funnel shifts instead of twelve LDG.U8: ncu (r02) had the byte loads at 2.25 sectors per request,
+                // 38 % of the wavefronts of an L1-data-pipe-bound kernel.  Per channel the four taps are gathered into one
+                // word (two PRMT) and weighted with the same exact 16 + 8 bit digit split as the vertical pass.
+                const unsigned hl01 = (unsigned)(hk0 & 0xFFFF) | ((unsigned)(hk1 & 0xFFFF) << 16);
+                const unsigned hl23 = (unsigned)(hk2 & 0xFFFF) | ((unsigned)(hk3 & 0xFFFF) << 16);
+                const unsigned hkh = (unsigned)((hk0 >> 16) & 255) | ((unsigned)((hk1 >> 16) & 255) << 8) |
+                                     ((unsigned)((hk2 >> 16) & 255) << 16) | ((unsigned)((hk3 >> 16) & 255) << 24);
+                for (int q = 0; q < nq; ++q) {
+                    int a[3][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int row = min((bq0 + q) * 4 + r, h - 1);
+                        const uintptr_t ap = reinterpret_cast<uintptr_t>(hsrc + (long long)row * cd.pitch);
+                        const unsigned* wp = reinterpret_cast<const unsigned*>(ap & ~(uintptr_t)3);
+                        const unsigned sh = ((unsigned)ap & 3u) * 8u;
+                        const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                        const unsigned w3 = sh ? __ldg(wp + 3) : 0u;     // aligned window: the twelve bytes end inside w2
+                        const unsigned r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh), r2 = __funnelshift_r(w2, w3, sh);
+                        // channel c: bytes c, 3 + c, 6 + c, 9 + c of (r0 | r1 | r2)
+                        const unsigned v[3] = {__byte_perm(__byte_perm(r0, r1, 0x0630), r2, 0x5210),
+                                               __byte_perm(__byte_perm(r0, r1, 0x0741), r2, 0x6210),
+                                               __byte_perm(__byte_perm(r0, r1, 0x0052), r2, 0x7410)};
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            int dl = dp2a_lo_uu(hl01, v[c], 1 << (PREC_BITS - 1));
+                            dl = dp2a_hi_uu(hl23, v[c], dl);
+                            const int dh = dp4a_su(hkh, v[c], 0);
+                            a[c][r] = ((dh << 16) + dl) >> PREC_BITS;
+                        }
+                    }
+                    unsigned* d = tmpw + q * UP2_QWORDS + t * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d[c] = pack_sat4(a[c][0], a[c][1], a[c][2], a[c][3]);
+                }
+            } else if (!wide) {
                 for (int q = 0; q < nq; ++q) {
                     int a[3][4];
 #pragma unroll
@@ -875,14 +914,19 @@ static size_t k9_list_bytes(int n) { return 64 + sizeof(int) * 3 * (size_t)n; }
 int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int layout, int* err, int* lists_scratch,
                        cudaStream_t stream) {
     static bool attr_set = false;
-    static int k9_v1 = 0;
+    static int k9_v1 = 0, k9_hword = 1;
     if (!attr_set) {
         MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           K9_SMEM_BYTES));
         MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM));
-        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up2_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+        MB_CUDA(ctx, cudaFuncSetAttribute(crop_resize_up2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
         const char* e = getenv("MB_K9_V1");
         k9_v1 = (e && e[0] == '1') ? 1 : 0;
+        const char* hw = getenv("MB_K9_HBYTE");               // 1: the horizontal pass with byte loads (r02 form)
+        k9_hword = (hw && hw[0] == '1') ? 0 : 1;
         attr_set = true;
     }
     int* counts = lists_scratch;
@@ -896,9 +940,13 @@ int launch_crop_resize(mb_ctx* ctx, const CropDesc* descs, int n, bf16* out, int
     if (k9_v1)
         crop_resize_up_kernel<<<n < 2 * sms * 8 ? n : 2 * sms * 8, UP_THREADS, UP_SMEM, stream>>>(descs, lists, counts, out,
                                                                                                   layout, ctx->f16);
-    else
-        crop_resize_up2_kernel<<<n < 3 * sms * 4 ? n : 3 * sms * 4, UP2_THREADS, UP2_SMEM, stream>>>(descs, lists, counts, out,
-                                                                                                     layout, ctx->f16);
+    else {
+        const int g2 = n < 3 * sms * 4 ? n : 3 * sms * 4;
+        if (k9_hword && layout == 1) crop_resize_up2_kernel<true, 1><<<g2, UP2_THREADS, UP2_SMEM, stream>>>(descs, lists, counts, out, ctx->f16);
+        else if (k9_hword) crop_resize_up2_kernel<true, 0><<<g2, UP2_THREADS, UP2_SMEM, stream>>>(descs, lists, counts, out, ctx->f16);
+        else if (layout == 1) crop_resize_up2_kernel<false, 1><<<g2, UP2_THREADS, UP2_SMEM, stream>>>(descs, lists, counts, out, ctx->f16);
+        else crop_resize_up2_kernel<false, 0><<<g2, UP2_THREADS, UP2_SMEM, stream>>>(descs, lists, counts, out, ctx->f16);
+    }
     MB_LAUNCH_CHECK(ctx);
     constexpr int TPC = 4;            // row tiles per CTA in the small-smem tiled launch
     const int gy = n < sms * 4 ? n : sms * 4;
