@@ -16,14 +16,17 @@ from .plugin_api import MODEL_PATH, BoxProcessor, PSMode
 
 class BoxProcessorCraftB200(BoxProcessor):
     def __init__(self, work_dir="/tmp/boxes", models_dir=os.path.join(MODEL_PATH, "craft"), cuda=True, config=None, *,
-                 state_dict=None, pipeline=None, device=0, line_refiner_state_dict=None):
+                 state_dict=None, pipeline=None, device=0, line_refiner_state_dict=None, poly=False):
         """models_dir is the CRAFT directory itself, as in the reference (default `<model_zoo>/craft`,
         craft_box_processor.py:245-249).  state_dict: CRAFT weights (keys of marie/models/craft/craft.py); when omitted
         the reference's checkpoint `<models_dir>/craft_mlt_25k.pth` is loaded (:260-277).
         line_refiner_state_dict: RefineNet weights (marie/models/craft/refinenet.py) — enables the line branch of
         get_prediction (craft_box_processor.py:150-217), which the reference keeps switched off (`:287-312`: the
         refiner is never loaded, so `lines_bboxes` is always [] and every box gets line -1).  With it, `lines_bboxes`
-        and the per-box line numbers are produced exactly as that branch would."""
+        and the per-box line numbers are produced exactly as that branch would.
+        poly: the `poly` argument of get_prediction (craft_box_processor.py:76-135), False in every preset of the
+        reference; True adds the polygon refinement of getPoly_core to `prediction_result["polys"]` (host routine over
+        the device's label map, polys.py) — boxes, rects and fragments do not depend on it."""
         super().__init__(work_dir, models_dir, cuda, config or {})
         if not cuda:
             raise RuntimeError("BoxProcessorCraftB200 has no CPU path: cuda=True and a B200 are required")
@@ -36,6 +39,7 @@ class BoxProcessorCraftB200(BoxProcessor):
         if state_dict is not None:
             self.pipeline.load_craft(_weights.pack_craft(state_dict, self.pipeline.dtype))
         self.device = f"cuda:{self.pipeline.device}"
+        self.poly = bool(poly)
         self.line_refiner = line_refiner_state_dict is not None
         if self.line_refiner:
             from . import ops as _ops
@@ -48,9 +52,17 @@ class BoxProcessorCraftB200(BoxProcessor):
     # ------------------------------------------------------------------ PSM presets (get_prediction, :76-146)
     def _predict(self, image, mode):
         pages = torch.from_numpy(np.ascontiguousarray(image[None])).to(self.device)
-        det = self.pipeline.detect(pages, PSM_PRESETS[mode], line_refiner=self.line_refiner)
+        det = self.pipeline.detect(pages, PSM_PRESETS[mode], line_refiner=self.line_refiner, keep_post=self.poly)
         bboxes = det["boxes"].cpu().numpy()
-        polys = [b for b in bboxes]                      # poly=False: polys[k] = boxes[k] (:133-135)
+        if self.poly:
+            from .polys import adjust_polys, get_poly_core
+            nb = det["counts"][0]
+            post = det["post"]
+            raw = get_poly_core(list(post["det"][0, :nb].cpu().numpy()), post["labels"][0].cpu().numpy(),
+                                post["mapper"][0, :nb].cpu().numpy())
+            polys = adjust_polys(raw, [b for b in bboxes], 1.0 / det["ratio"], 1.0 / det["ratio"])
+        else:
+            polys = [b for b in bboxes]                  # poly=False: polys[k] = boxes[k] (:133-135)
         self._last_rects = det["rects"].cpu().numpy()
         return bboxes, polys, None, det.get("lines", [[]])[0]
 

@@ -109,7 +109,8 @@ class PagePipeline:
         self.has_trocr = True
 
     # ------------------------------------------------------------------------------------------ detection
-    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False, line_refiner=False, ready=None):
+    def detect(self, pages_dev, preset=PSM_PRESETS["sparse"], keep_maps=False, line_refiner=False, ready=None,
+               keep_post=False):
         """pages_dev [n,H,W,3] u8 (BGR) on the device -> dict with per-crop `rects` [N,4] i32 (x,y,w,h), `page_idx`
         [N] i32, `boxes` [N,4,2] f32 (page coordinates, adjustResultCoordinates output), `counts` (host list).
         ready(i0, i1): optional hook called before pages [i0, i1) are first read (run_frames: the compute stream waits
@@ -165,6 +166,9 @@ class PagePipeline:
                 res["refined_link"] = refined_all
         if keep_maps:
             res["scores"] = scores_all
+        if keep_post:       # K5-K7 outputs at heat-map scale (polygon refinement, polys.py) and the resize ratio of K1
+            res["post"] = dict(labels=out["labels"], det=out["det"], mapper=out["mapper"])
+            res["ratio"] = ratio
         return res
 
     # ------------------------------------------------------------------------------------------ recognition

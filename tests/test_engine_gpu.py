@@ -171,3 +171,42 @@ def test_engine_regions(engine):
     assert [r["id"] for r in mixed["regions"]] == ["z", "z", "r0"] and all(r["text"] == "" for r in mixed["regions"])
     with pytest.raises(Exception, match="Required key missing"):
         eng.extract([page], regions=[{"id": "q", "pageIndex": 0, "x": 1}])
+
+
+def test_box_processor_poly_option(engine):
+    """poly=True (get_prediction's `poly`, craft_box_processor.py:76-135; off in every preset): prediction_result["polys"]
+    comes from the polygon refinement over the DEVICE's label map / boxes / mapper and equals the same routine fed with
+    the cv2-based oracle's post-processing of the device's score maps; boxes, rects and fragments are unchanged."""
+    import cv2
+    from marie_icr_b200 import ops
+    from marie_icr_b200.boxes import BoxProcessorCraftB200
+    from marie_icr_b200.plugin_api import PSMode
+    from marie_icr_b200.polys import adjust_polys, get_poly_core
+    from oracle import craft_post
+    eng, pages, _, _, _ = engine
+    page = pages[2].copy()
+    xs = np.arange(60, 440, 2)
+    for y0, amp in ((250, 16.0), (420, 22.0)):                       # two curved 'words' of ink
+        pts = np.stack([xs, y0 + amp * np.sin((xs - 60) * 2 * np.pi / 380.0)], 1).astype(np.int32).reshape(-1, 1, 2)
+        cv2.rectangle(page, (40, y0 - 40), (470, y0 + 40), (255, 255, 255), -1)
+        cv2.polylines(page, [pts], False, (0, 0, 0), thickness=14)
+    plain = eng.box_processor
+    curved = BoxProcessorCraftB200(pipeline=plain.pipeline, poly=True)
+    r0, f0, l0, p0, _ = plain.extract_bounding_boxes("id", "key", page, PSMode.SPARSE)
+    r1, f1, l1, p1, _ = curved.extract_bounding_boxes("id", "key", page, PSMode.SPARSE)
+    assert r0 == r1 and l0 == l1 and np.array_equal(p0["bboxes"], p1["bboxes"])
+    assert all(np.array_equal(a, b) for a, b in zip(f0, f1))
+    assert all(np.array_equal(a, b) for a, b in zip(p0["polys"], p0["bboxes"]))
+    # the same refinement on the oracle's labels / boxes of the device's own score maps
+    dev = torch.from_numpy(page[None]).cuda()
+    x, ratio = ops.page_preprocess(dev)
+    scores = ops.craft_forward(x)
+    det, labels, mapper = craft_post.det_boxes_cv(scores[0, 0].cpu().numpy(), scores[1, 0].cpu().numpy(), 0.7, 0.45, 0.3)
+    want = adjust_polys(get_poly_core([np.asarray(b, np.float32) for b in det], labels.astype(np.int32), mapper),
+                        [b for b in p1["bboxes"]], 1 / ratio, 1 / ratio)
+    assert len(want) == len(p1["polys"]) == len(r1)
+    n14 = 0
+    for a, b in zip(p1["polys"], want):
+        assert a.shape == b.shape and np.array_equal(a, b)
+        n14 += a.shape[0] == 14
+    assert n14 >= 1, "no curved component produced a polygon"
