@@ -305,7 +305,8 @@ def build_arm(args, cfg, ctx, local_rank, dtype_name):
     beam = args.beam or cfg["beam"]
     craft_sd, tsd, tcfg, rsd = make_weights(cfg, dt)
     # beam >= 2 keeps a cross-attention K/V cache of 28 MB per crop (12 layers x 577 x 2 x 1024 x 2 B): bound the decode batch
-    crop_chunk = args.crop_chunk or (16384 if beam == 1 else 2048)
+    from marie_icr_b200.pipeline import default_crop_chunk
+    crop_chunk = args.crop_chunk or default_crop_chunk(beam, tcfg.enc_dim)
     micro = 8 if cfg["page"] != "4096" else 2
     pipe = PagePipeline(device=local_rank, craft_blob=weights.pack_craft(craft_sd, dt), trocr_blob=weights.pack_trocr(tsd, tcfg, dt),
                         micro_batch=micro, crop_chunk=crop_chunk, encode_chunk=args.encode_chunk)

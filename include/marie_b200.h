@@ -196,9 +196,10 @@ int mb_gemm16_res_stats(mb_ctx* ctx, const void* a_dev, const void* w_dev, const
 /* Test hook for the greedy cross-attention core (the per-step attention of fairseq's decoder layers over the encoder
  * states, marie/models/unilm/trocr/trocr_models.py:142-147, with the K / V projections hoisted out): qp [rows, heads*E]
  * per-head projected queries, enc [rows*T, E] -> out [rows, heads*E].  mode 0 = tcgen05 / TMA kernel, 1 = mma.sync
- * kernel.  finished (or null): rows to skip; live_ws: rows + 1 ints of scratch (mode 0 with a finished mask). */
-int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_dev, void* out_dev, int rows, int T, int heads, int E,
-                   const unsigned char* finished_dev, int32_t* live_ws_dev, int mode, void* stream);
+ * kernel.  rows = crops; beam > 1 (mode 0 only): qp / out hold rows * beam hypotheses ([crop][beam]) that share the crop's
+ * encoder states in one pass.  finished (or null): crops to skip; live_ws: rows + 1 ints of scratch (mode 0 with a mask). */
+int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_dev, void* out_dev, int rows, int beam, int T, int heads,
+                   int E, const unsigned char* finished_dev, int32_t* live_ws_dev, int mode, void* stream);
 int mb_trocr_dims(mb_ctx* ctx, int* dims4_host);
 /* cumulative search statistics: {mb_trocr_decode calls, decoder steps executed, rows (crops * beam) decoded} */
 int mb_trocr_stats(mb_ctx* ctx, unsigned long long* out3_host);

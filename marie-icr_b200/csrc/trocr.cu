@@ -25,8 +25,9 @@ int mb_attention_tc(mb_ctx* ctx, const bf16* qkv, bf16* out, int n, int T, int D
                     cudaStream_t stream);
 // xattn_tc.cu: greedy cross-attention over the encoder states on tcgen05 / TMA
 bool mb_cross_enc_tc_supported(int E, int heads);
+int mb_cross_enc_tc_groups(int E, int beam);
 int mb_live_list(mb_ctx* ctx, const unsigned char* finished, int n, int* live_ws, cudaStream_t s);
-int mb_cross_enc_tc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* out, int rows, int T, int heads, int E,
+int mb_cross_enc_tc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* out, int n, int beam, int T, int heads, int E,
                     const int* live_ws, cudaStream_t s);
 
 namespace {
@@ -1094,7 +1095,15 @@ bool cross_tc(const TrocrModel* m) {
 bool cross_uncached(const TrocrModel* m, int beam) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("MB_CROSS_CACHED"); forced = (e && e[0] == '1') ? 1 : 0; }
-    return beam == 1 && !forced && m->dec_heads <= 16 && (m->enc_dim == 128 || m->enc_dim == 768 || m->enc_dim == 1024);
+    // beam >= 2: the tcgen05 kernel shares one pass over a crop's encoder states between its hypotheses — as long as they
+    // fit one pass (TMEM: three for E = 768, two for E = 1024).  Measured on B200 (64 letter pages, TrOCR-base): beam 3
+    // 9.05 vs 8.17 pages/s with the K/V cache; beam 5 (two passes, and per-hypothesis q' / context rows that cost as much
+    // as the cache saved) 7.69 vs 8.15 — more than one pass keeps the cache.  MB_CROSS_UNCACHED=1 forces the cache-free
+    // form for every beam (tests).
+    static int force_un = -1;
+    if (force_un < 0) { const char* e = getenv("MB_CROSS_UNCACHED"); force_un = (e && e[0] == '1') ? 1 : 0; }
+    const bool beams_ok = beam == 1 || (cross_tc(m) && beam <= MAX_BEAM && (force_un || mb_cross_enc_tc_groups(m->enc_dim, beam) == 1));
+    return beams_ok && !forced && m->dec_heads <= 16 && (m->enc_dim == 128 || m->enc_dim == 768 || m->enc_dim == 1024);
 }
 
 size_t plan_decode(TrocrModel* m, int n, int beam, int max_len, unsigned char* base, DecodeWs* w) {
@@ -1152,10 +1161,12 @@ int launch_cross_enc(mb_ctx* ctx, const bf16* qp, const bf16* enc, bf16* ctxe, i
 }
 
 // greedy cross-attention of one layer: q [R, H] (in w.qkv) -> w.att [R, H]
-int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer& L, const bf16* enc_out, int n, cudaStream_t s) {
+int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer& L, const bf16* enc_out, int n, int beam,
+                        cudaStream_t s) {
     const int H = m->dec_dim, E = m->enc_dim, heads = m->dec_heads, T = m->tokens;
+    const int R = n * beam;
     TapGemm g;                                    // q'^h = Wk^h^T q^h  : [R, heads*E]
-    g.a0 = w.qkv; g.c0 = DH; g.a0_ld = H; g.n = 1; g.h = 1; g.w = n;
+    g.a0 = w.qkv; g.c0 = DH; g.a0_ld = H; g.n = 1; g.h = 1; g.w = R;
     g.wgt = L.ckT_w; g.n_rows_w = heads * E; g.n_out = E;
     g.out = w.qp; g.out_ld = (long long)heads * E; g.out_mode = MB_OUT_BF16;
     g.batches = heads; g.a_col_stride = DH; g.w_row_stride = E; g.out_col_stride = E;
@@ -1168,8 +1179,9 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     // CTA, two CTAs / SM) measured 8.70 ms per decode step at 2048 live crops against 9.66 for 32-key tiles x 2 stages
     // (tools/gpu_probe_decode.py; MB_XE_MODE = 0: 32 x 2, 1: 16 x 2 (4 CTAs / SM, 11.8 ms), 2: 16 x 3 (8.8), 3: 16 x 4, 4: 8 warps (12.2)).
     if (cross_tc(m)) {
-        rc = mb_cross_enc_tc(ctx, w.qp, enc_out, w.ctxe, n, T, heads, E, w.live, s);
+        rc = mb_cross_enc_tc(ctx, w.qp, enc_out, w.ctxe, n, beam, T, heads, E, w.live, s);
     } else {
+    if (beam != 1) return mb_set_err(ctx, MB_ERR_STATE, "cross_enc_attention: the mma.sync kernel is greedy-only");
     static int xe_mode = -1;
     if (xe_mode < 0) { const char* e = getenv("MB_XE_MODE"); xe_mode = e ? atoi(e) : 3; if (xe_mode < 0 || xe_mode > 4) xe_mode = 3; }
     if (E == 768 && xe_mode == 1) rc = ctx->f16 ? launch_cross_enc<true, 192, 4, 2, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s) : launch_cross_enc<false, 192, 4, 2, 16>(ctx, w.qp, enc_out, w.ctxe, n, T, heads, w.st.finished, s);
@@ -1183,7 +1195,7 @@ int cross_enc_attention(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const DecLayer&
     }
     if (rc) return rc;
     TapGemm v;                                    // att^h = Wv^h ctx^h + bv^h : [R, H]
-    v.a0 = w.ctxe; v.c0 = E; v.a0_ld = heads * E; v.n = 1; v.h = 1; v.w = n;
+    v.a0 = w.ctxe; v.c0 = E; v.a0_ld = heads * E; v.n = 1; v.h = 1; v.w = R;
     v.wgt = L.ckv_w + (size_t)H * E; v.n_rows_w = H; v.n_out = DH;
     v.bias = L.ckv_b + H;
     v.out = w.att; v.out_ld = H; v.out_mode = MB_OUT_BF16;
@@ -1251,7 +1263,7 @@ int decoder_step(mb_ctx* ctx, TrocrModel* m, DecodeWs& w, const bf16* enc_out, i
         RC(layernorm(ctx, w.tmp, w.x, L.ln1_w, L.ln1_b, R, H, 1e-5f, s));
         RC(gemm(ctx, w.x, H, L.cq_w, H, R, H, L.cq_b, MB_ACT_NONE, nullptr, w.qkv, MB_OUT_BF16, s));
         if (w.greedy) {
-            RC(cross_enc_attention(ctx, m, w, L, enc_out, n, s));
+            RC(cross_enc_attention(ctx, m, w, L, enc_out, n, beam, s));
         } else {
             // all beams of a crop share one pass over the crop's cached K/V (q is pre-scaled: weights carry d^-0.5)
             const bf16* kvl = w.cross_kv + (size_t)l * n * T * 2 * H;
@@ -1419,12 +1431,15 @@ extern "C" int mb_gemm16_res_stats(mb_ctx* ctx, const void* a_dev, const void* w
 
 // Test hook: the greedy cross-attention core on its own.  qp [rows, heads*E] (per-head projected queries), enc [rows*T, E]
 // -> out [rows, heads*E] = softmax_t(qp^h . e_t) . e.  mode 0: tcgen05 / TMA kernel (xattn_tc.cu), 1: mma.sync kernel.
-// finished (or null): rows to skip; live_ws: rows + 1 ints of scratch for mode 0's compacted row list.
-extern "C" int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_dev, void* out_dev, int rows, int T, int heads,
-                              int E, const unsigned char* finished_dev, int32_t* live_ws_dev, int mode, void* stream) {
+// rows = crops; with beam > 1 (mode 0) qp / out hold rows * beam hypotheses, [crop][beam], sharing the crop's states.
+// finished (or null): crops to skip; live_ws: rows + 1 ints of scratch for mode 0's compacted crop list.
+extern "C" int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_dev, void* out_dev, int rows, int beam, int T,
+                              int heads, int E, const unsigned char* finished_dev, int32_t* live_ws_dev, int mode,
+                              void* stream) {
     MbDeviceGuard _mb_guard(ctx);
     if (!ctx) return MB_ERR_ARG;
-    MB_REQUIRE(ctx, rows > 0 && T > 0 && heads > 0 && heads <= 16, "cross_enc16: bad geometry");
+    MB_REQUIRE(ctx, rows > 0 && beam >= 1 && T > 0 && heads > 0 && heads <= 16, "cross_enc16: bad geometry");
+    MB_REQUIRE(ctx, mode == 0 || beam == 1, "cross_enc16: the mma.sync kernel takes one hypothesis per crop");
     cudaStream_t s = (cudaStream_t)stream;
     const bf16* qp = (const bf16*)qp_dev;
     const bf16* enc = (const bf16*)enc_dev;
@@ -1434,7 +1449,7 @@ extern "C" int mb_cross_enc16(mb_ctx* ctx, const void* qp_dev, const void* enc_d
             MB_REQUIRE(ctx, live_ws_dev != nullptr, "cross_enc16: live_ws is required with a finished mask");
             RC(mb_live_list(ctx, finished_dev, rows, live_ws_dev, s));
         }
-        return mb_cross_enc_tc(ctx, qp, enc, out, rows, T, heads, E, finished_dev ? live_ws_dev : nullptr, s);
+        return mb_cross_enc_tc(ctx, qp, enc, out, rows, beam, T, heads, E, finished_dev ? live_ws_dev : nullptr, s);
     }
     if (E == 768) return ctx->f16 ? launch_cross_enc<true, 192, 4, 4, 16>(ctx, qp, enc, out, rows, T, heads, finished_dev, s)
                                   : launch_cross_enc<false, 192, 4, 4, 16>(ctx, qp, enc, out, rows, T, heads, finished_dev, s);

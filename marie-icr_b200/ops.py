@@ -303,15 +303,16 @@ def gemm16_res_stats(a, w, bias, residual, eps=1e-6):
     return out, stats
 
 
-def cross_enc16(qp, enc, T, heads, finished=None, mode=0):
-    """Greedy cross-attention core.  qp [rows, heads*E], enc [rows*T, E] 16-bit -> [rows, heads*E].
-    mode 0: tcgen05 / TMA kernel, 1: mma.sync kernel.  finished: optional [rows] uint8 mask of rows to skip."""
-    rows = qp.shape[0]
+def cross_enc16(qp, enc, T, heads, finished=None, mode=0, beam=1):
+    """Cross-attention core over the encoder states.  qp [crops*beam, heads*E] ([crop][beam] rows), enc [crops*T, E]
+    16-bit -> [crops*beam, heads*E].  mode 0: tcgen05 / TMA kernel (the hypotheses of a crop share the pass), 1: mma.sync
+    kernel (beam 1 only).  finished: optional [crops] uint8 mask of crops to skip."""
+    rows = qp.shape[0] // beam
     E = enc.shape[1]
     out = torch.zeros_like(qp)
     live = torch.empty((rows + 1,), dtype=torch.int32, device=qp.device)
-    _ctx(qp).call("mb_cross_enc16", ptr(qp.contiguous()), ptr(enc.contiguous()), ptr(out), c_int(rows), c_int(T), c_int(heads),
-                  c_int(E), ptr(finished), ptr(live), c_int(mode), cur_stream())
+    _ctx(qp).call("mb_cross_enc16", ptr(qp.contiguous()), ptr(enc.contiguous()), ptr(out), c_int(rows), c_int(beam), c_int(T),
+                  c_int(heads), c_int(E), ptr(finished), ptr(live), c_int(mode), cur_stream())
     return out
 
 

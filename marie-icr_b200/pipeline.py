@@ -76,6 +76,16 @@ def decode_batches(n, chunk):
     return [a] * (k - 1) + [n - a * (k - 1)]
 
 
+def default_crop_chunk(beam, enc_dim):
+    """Crops per decode batch that the bench / engine use by default.  Greedy decode and beams that share ONE pass over a
+    crop's encoder states (up to three hypotheses for E = 768, two for E = 1024: xattn_tc.cu) keep no cross-attention K/V
+    cache, so the batch is bounded by the logits and the self-attention caches only; wider beams keep the 2.36 MB per crop
+    and layer cache (29 GB per 1024 crops of TrOCR-base) and stay at 2048 crops."""
+    if beam == 1:
+        return 16384
+    return 8192 if beam <= (2 if enc_dim == 1024 else 3) else 2048
+
+
 class PagePipeline:
     """Owns the per-device context and the loaded models."""
 

@@ -9,18 +9,18 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _ref(qp, enc, rows, T, heads):
+def _ref(qp, enc, rows, T, heads, beam=1):
     E = enc.shape[1]
-    q = qp.float().view(rows, heads, E)
+    q = qp.float().view(rows, beam * heads, E)                 # the hypotheses of a crop attend over the same states
     e = enc.float().view(rows, T, E)
     p = torch.softmax(torch.einsum("rhe,rte->rht", q, e), -1)
-    return torch.einsum("rht,rte->rhe", p, e).reshape(rows, heads * E)
+    return torch.einsum("rht,rte->rhe", p, e).reshape(rows * beam, heads * E)
 
 
-def _inputs(rows, T, heads, E, dtype, seed, qscale=0.05):
+def _inputs(rows, T, heads, E, dtype, seed, qscale=0.05, beam=1):
     torch.manual_seed(seed)
     enc = torch.randn(rows * T, E, device="cuda").to(dtype)
-    qp = (torch.randn(rows, heads * E, device="cuda") * qscale).to(dtype)
+    qp = (torch.randn(rows * beam, heads * E, device="cuda") * qscale).to(dtype)
     return qp, enc
 
 
@@ -83,3 +83,33 @@ def test_cross_enc_kernels_agree_on_decoder_like_inputs(cuda_ctx):
     a = ops.cross_enc16(qp, enc, T, heads, mode=0).float()
     b = ops.cross_enc16(qp, enc, T, heads, mode=1).float()
     assert ((a - b).norm() / b.norm()).item() <= 3e-3
+
+
+@pytest.mark.parametrize("rows,beam,T,heads,E", [(4, 3, 577, 16, 768), (3, 5, 577, 16, 768), (3, 3, 577, 16, 1024),
+                                                 (5, 2, 50, 2, 128), (2, 4, 130, 16, 768), (150, 3, 70, 16, 768),
+                                                 (3, 8, 100, 16, 768), (2, 5, 65, 16, 1024), (7, 5, 33, 2, 128)])
+def test_cross_enc_beams_share_the_pass(cuda_ctx, dtype16, rows, beam, T, heads, E):
+    """beam >= 2: the hypotheses of a crop ([crop][beam] rows of qp) go through the tcgen05 kernel together — up to three
+    per pass over the crop's encoder states (two for E = 1024), further groups as further passes."""
+    from marie_icr_b200 import ops
+    qp, enc = _inputs(rows, T, heads, E, dtype16, rows * T + beam, beam=beam)
+    out = ops.cross_enc16(qp, enc, T, heads, mode=0, beam=beam).float()
+    ref = _ref(qp, enc, rows, T, heads, beam)
+    assert torch.isfinite(out).all()
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel <= (3e-3 if dtype16 == torch.float16 else 2e-2), rel
+    worst = ((out - ref).view(rows * beam, -1).norm(dim=1) / ref.view(rows * beam, -1).norm(dim=1)).max().item()
+    assert worst <= (6e-3 if dtype16 == torch.float16 else 4e-2), worst
+
+
+def test_cross_enc_beams_skip_finished_crops(cuda_ctx):
+    from marie_icr_b200 import ops
+    rows, beam, T, heads, E = 200, 5, 70, 16, 768
+    qp, enc = _inputs(rows, T, heads, E, torch.float16, 13, beam=beam)
+    torch.manual_seed(6)
+    fin = (torch.rand(rows, device="cuda") < 0.5).to(torch.uint8)
+    out = ops.cross_enc16(qp, enc, T, heads, finished=fin, mode=0, beam=beam).float()
+    ref = _ref(qp, enc, rows, T, heads, beam)
+    live = (fin == 0).repeat_interleave(beam)
+    assert ((out[live] - ref[live]).norm() / ref[live].norm()).item() <= 3e-3
+    assert (out[~live] == 0).all()
