@@ -1095,14 +1095,13 @@ bool cross_tc(const TrocrModel* m) {
 bool cross_uncached(const TrocrModel* m, int beam) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("MB_CROSS_CACHED"); forced = (e && e[0] == '1') ? 1 : 0; }
-    // beam >= 2: the tcgen05 kernel shares one pass over a crop's encoder states between its hypotheses — as long as they
-    // fit one pass (TMEM: three for E = 768, two for E = 1024).  Measured on B200 (64 letter pages, TrOCR-base): beam 3
-    // 9.05 vs 8.17 pages/s with the K/V cache; beam 5 (two passes, and per-hypothesis q' / context rows that cost as much
-    // as the cache saved) 7.69 vs 8.15 — more than one pass keeps the cache.  MB_CROSS_UNCACHED=1 forces the cache-free
-    // form for every beam (tests).
-    static int force_un = -1;
-    if (force_un < 0) { const char* e = getenv("MB_CROSS_UNCACHED"); force_un = (e && e[0] == '1') ? 1 : 0; }
-    const bool beams_ok = beam == 1 || (cross_tc(m) && beam <= MAX_BEAM && (force_un || mb_cross_enc_tc_groups(m->enc_dim, beam) == 1));
+    // beam >= 2: the tcgen05 kernel shares a pass over a crop's encoder states between up to three of its hypotheses (two
+    // for E = 1024); wider beams take ceil(beam / 3) passes, the second one mostly out of L2.  Measured on B200 against the
+    // K/V-cache path (which also pays 12 projection GEMMs per crop and caps the decode batch at 2048 crops: 29 GB of cache
+    // per 1024 crops): TrOCR-base beam 3 9.7 vs 8.2 pages/s, beam 5 decode 3.21 vs 3.47 s per 64 pages, TrOCR-large beam 3
+    // decode 1.22 vs 1.47 s per 16 dense pages.  MB_CROSS_CACHED=1 keeps the cache (A/B, and the only path without the
+    // tcgen05 kernel).
+    const bool beams_ok = beam == 1 || (cross_tc(m) && beam <= MAX_BEAM);
     return beams_ok && !forced && m->dec_heads <= 16 && (m->enc_dim == 128 || m->enc_dim == 768 || m->enc_dim == 1024);
 }
 

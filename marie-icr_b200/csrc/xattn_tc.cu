@@ -94,9 +94,10 @@ dec_cross_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(xt_smem + C::OFF_BAR);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
     volatile uint32_t* flags = reinterpret_cast<volatile uint32_t*>(bars + 13);      // [2 buffers][4 warps]
-    volatile float* tmax = reinterpret_cast<volatile float*>(bars + 20);             // [2 key warps][N]
-    volatile float* mref = tmax + 2 * N;                                             // [N] softmax references (log2 units)
-    volatile float* fsc = mref + N;                                                  // [N] rescale factors of the last move
+    // exchanged across the named barrier (its asm carries a memory clobber, so plain loads are re-issued after it)
+    float* tmax = reinterpret_cast<float*>(bars + 20);                               // [2 key warps][N]
+    float* mref = tmax + 2 * N;                                                      // [N] softmax references (log2 units)
+    float* fsc = mref + N;                                                           // [N] rescale factors of the last move
     const uint32_t tile_full = smem_u32(&bars[0]), tile_empty = smem_u32(&bars[2]);
     const uint32_t q_full = smem_u32(&bars[4]), q_empty = smem_u32(&bars[5]);
     const uint32_t s_full = smem_u32(&bars[6]), p_full = smem_u32(&bars[8]), ctx_done = smem_u32(&bars[10]);
@@ -262,9 +263,15 @@ dec_cross_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
                         uint32_t v[16];
                         tmem_ld16(ts + (uint32_t)(c16 * 16), v);
                         tmem_wait_ld();
+                        float rf[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(mref + c16 * 16 + 4 * i);
+                            rf[4 * i] = r4.x; rf[4 * i + 1] = r4.y; rf[4 * i + 2] = r4.z; rf[4 * i + 3] = r4.w;
+                        }
 #pragma unroll
                         for (int h = 0; h < 16; ++h) {
-                            over |= valid && (__uint_as_float(v[h]) * L2E > mref[c16 * 16 + h] + 8.0f);
+                            over |= valid && (__uint_as_float(v[h]) * L2E > rf[h] + 8.0f);
                             if (NB == 1) vk[h] = v[h];
                         }
                     }
@@ -331,11 +338,17 @@ dec_cross_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
                             tmem_ld16(ts + (uint32_t)(c16 * 16), v);
                             tmem_wait_ld();
                         }
+                        float rf[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(mref + c16 * 16 + 4 * i);
+                            rf[4 * i] = r4.x; rf[4 * i + 1] = r4.y; rf[4 * i + 2] = r4.z; rf[4 * i + 3] = r4.w;
+                        }
 #pragma unroll
                         for (int h = 0; h < 16; ++h) {
                             if (NB == 1) v[h] = vk[h];
                             const int col = c16 * 16 + h;
-                            const float pv = valid ? ex2a(__uint_as_float(v[h]) * L2E - mref[col]) : 0.f;
+                            const float pv = valid ? ex2a(__uint_as_float(v[h]) * L2E - rf[h]) : 0.f;
                             const uint32_t pk = pack2(pv, 0.f, F16 ? 1 : 0);
                             *reinterpret_cast<unsigned short*>(pbuf + col * 128 + ((((uint32_t)t >> 3) ^ (uint32_t)(col & 7)) << 4)) =
                                 (unsigned short)(pk & 0xFFFFu);

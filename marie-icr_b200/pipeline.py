@@ -76,14 +76,14 @@ def decode_batches(n, chunk):
     return [a] * (k - 1) + [n - a * (k - 1)]
 
 
-def default_crop_chunk(beam, enc_dim):
-    """Crops per decode batch that the bench / engine use by default.  Greedy decode and beams that share ONE pass over a
-    crop's encoder states (up to three hypotheses for E = 768, two for E = 1024: xattn_tc.cu) keep no cross-attention K/V
-    cache, so the batch is bounded by the logits and the self-attention caches only; wider beams keep the 2.36 MB per crop
-    and layer cache (29 GB per 1024 crops of TrOCR-base) and stay at 2048 crops."""
-    if beam == 1:
+def default_crop_chunk(beam, enc_dim=768):
+    """Crops per decode batch that the bench / engine use by default.  No cross-attention K/V cache is kept (xattn_tc.cu
+    attends over the encoder states themselves, for every beam width), so the batch is bounded by what grows with the rows
+    = crops x beam: the fp32 logits (0.2 MB per row) and the self-attention K / V caches (1.5 MB per row at 32 steps).
+    16384 crops greedy; beams: about 41 k rows."""
+    if beam <= 1:
         return 16384
-    return 8192 if beam <= (2 if enc_dim == 1024 else 3) else 2048
+    return max(1024, min(8192, (40960 // beam) // 512 * 512))
 
 
 class PagePipeline:
