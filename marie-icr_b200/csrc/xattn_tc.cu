@@ -19,6 +19,10 @@
 // accumulators are then rescaled in TMEM, all four warps; P stays far inside fp16 range) -> P^T in shared memory; after
 // the last tile ctx^T / l -> global.  The S^T MMA runs with M = 128 although a tile has KT <= 64 keys: rows beyond the
 // tile read whatever follows in shared memory and land in TMEM lanes nobody reads.
+// Beams: the hypotheses of a crop attend over the same encoder states, so up to NB = 3 of them (2 for E = 1024; TMEM holds
+// (3 + E / 128) * 16 * NB columns) go through one pass as N = 16 * NB columns of every MMA — q' rows [crop][beam][head] are
+// one TMA box, TMEM column c belongs to q' row row0 + c; a wider beam is ceil(beam / NB) work items per crop (the second
+// pass over the crop's states mostly hits L2).  No beam width keeps a cross-attention K/V cache.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>

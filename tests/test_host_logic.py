@@ -405,3 +405,12 @@ def test_decode_batches_cover_all_crops_and_respect_the_chunk():
             assert b == ([n] if n else [])
     # the bench's configuration: two full batches and a short last one (host post-processing tail)
     assert decode_batches(32945, 16384) == [14120, 14120, 4705]
+
+
+def test_default_crop_chunk_bounds_the_decode_rows():
+    from marie_icr_b200.pipeline import default_crop_chunk
+    assert default_crop_chunk(1) == 16384
+    for beam in range(2, 9):
+        c = default_crop_chunk(beam)
+        assert 1024 <= c <= 8192 and c % 512 == 0 and c * beam <= 40960 + 512 * beam
+    assert default_crop_chunk(3) == 8192 and default_crop_chunk(5) == 8192 and default_crop_chunk(8) == 5120
