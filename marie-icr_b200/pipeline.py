@@ -310,10 +310,13 @@ class PagePipeline:
         staged = [threading.Event() for _ in range(0, n, mb)]
 
         def stager():
-            for k, i0 in enumerate(range(0, n, mb)):
-                for i in range(i0, min(i0 + mb, n)):
-                    np.copyto(stage_np[i], frames[i])
-                staged[k].set()
+            # the pages of a micro-batch are copied by a few threads at once (np.copyto releases the GIL): only the first
+            # micro-batch's staging is exposed in front of the device work, the others run one batch ahead of it
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=4) as pool:
+                for k, i0 in enumerate(range(0, n, mb)):
+                    list(pool.map(lambda i: np.copyto(stage_np[i], frames[i]), range(i0, min(i0 + mb, n))))
+                    staged[k].set()
 
         th = threading.Thread(target=stager, daemon=True)
         th.start()
