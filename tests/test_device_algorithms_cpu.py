@@ -356,3 +356,81 @@ def test_k9_normalise_as_one_fma_is_exact():
     y = (u.astype(np.float64) * np.float64(a) - 1.0).astype(np.float32)      # exact product + one rounding = fma
     for dt in (torch.float16, torch.bfloat16):
         assert torch.equal(torch.from_numpy(y).to(dt), torch.from_numpy(ref32).to(dt))
+
+
+# ------------------------------------------------------------------------------------------------ xattn_tc.cu layouts
+def _sw128(byte_off):
+    """128-byte swizzle of TMA / tcgen05 descriptors: bits [4,7) of a shared-memory offset XOR bits [7,10)."""
+    return byte_off ^ (((byte_off >> 7) & 7) << 4)
+
+
+def test_cross_attention_tile_serves_both_mmas_and_the_k9_window_gather():
+    """dec_cross_tc_kernel (csrc/xattn_tc.cu) reads ONE shared-memory encoder tile twice: K-major for S^T = E_tile . q'^T and
+    MN-major for ctx^T += E_tile^T . P^T.  Emulates the byte layout the TMA writes (boxes of [KT keys x 64 columns], 128-byte
+    swizzle), the canonical K-major / MN-major descriptor walks (SBO = 1024; MN-major LBO = box stride), the P^T tile the
+    softmax threads write (K-major, [16 x beams] rows x 64 keys) and the smem-free column -> q' row mapping, and checks that
+    the two contractions computed through these address maps equal plain matrix products.  Also the PRMT selectors of the
+    K9 horizontal pass (csrc/imgproc.cu): bytes c, 3 + c, 6 + c, 9 + c of a 12-byte window."""
+    rng = np.random.default_rng(3)
+    for E, KT, NB in ((768, 64, 1), (768, 32, 3), (1024, 32, 2), (128, 64, 2)):
+        N, NCH, CHUNK = 16 * NB, E // 64, KT * 128
+        enc = rng.standard_normal((KT, E)).astype(np.float32)
+        q = rng.standard_normal((N, E)).astype(np.float32)
+        # --- what the TMA leaves in shared memory (16-bit elements, modelled as a dict byte offset -> value)
+        tile = {}
+        for c in range(NCH):
+            for r in range(KT):
+                for e in range(64):
+                    tile[c * CHUNK + _sw128(r * 128 + e * 2)] = enc[r, c * 64 + e]
+        qs = {}
+        for c in range(NCH):
+            for r in range(N):
+                for e in range(64):
+                    qs[c * N * 128 + _sw128(r * 128 + e * 2)] = q[r, c * 64 + e]
+        # --- S^T: A K-major (row m of the MMA = key, 8-row groups SBO = 1024 apart, k-step = +32 B), B = q' K-major
+        S = np.zeros((KT, N), np.float32)
+        for c in range(NCH):
+            for k in range(4):
+                for kk in range(16):
+                    a = np.array([tile[c * CHUNK + _sw128((m // 8) * 1024 + (m % 8) * 128 + k * 32 + kk * 2)] for m in range(KT)])
+                    b = np.array([qs[c * N * 128 + _sw128((n // 8) * 1024 + (n % 8) * 128 + k * 32 + kk * 2)] for n in range(N)])
+                    S += np.outer(a, b)
+        assert np.allclose(S, enc @ q.T, rtol=1e-4, atol=1e-3)
+        # --- P^T as the softmax threads store it: thread t (key), column col -> row col of a K-major [N x 64 keys] tile
+        P = rng.random((KT, N)).astype(np.float32)
+        ps = {}
+        for t in range(KT):
+            for col in range(N):
+                ps[col * 128 + (((t >> 3) ^ (col & 7)) << 4) + (t & 7) * 2] = P[t, col]
+        # --- ctx^T: A MN-major (m = e column: 64-element atoms LBO = CHUNK apart; k = key: 8-row groups SBO = 1024, a k-step of
+        #     16 keys = +2048 B), B = P^T K-major (k-step = +32 B)
+        ctx = np.zeros((E, N), np.float32)
+        for mt in range(E // 128):
+            for k in range(KT // 16):
+                for kk in range(16):
+                    base = 2 * mt * CHUNK + k * 2048
+                    a = np.array([tile[base + (m // 64) * CHUNK + _sw128((kk // 8) * 1024 + (kk % 8) * 128 + (m % 64) * 2)]
+                                  for m in range(128)])
+                    b = np.array([ps[_sw128((n // 8) * 1024 + (n % 8) * 128 + k * 32 + kk * 2)] for n in range(N)])
+                    ctx[mt * 128:(mt + 1) * 128] += np.outer(a, b)
+        assert np.allclose(ctx, enc.T @ P, rtol=1e-4, atol=1e-3)
+    # --- work items: (crop, group) -> first q' row and the rows that are stored, heads = 16 and heads = 2
+    for beam, NB, heads in ((5, 3, 16), (3, 3, 16), (3, 2, 16), (5, 3, 2), (8, 3, 16)):
+        groups = -(-beam // NB)
+        seen = []
+        for crop in range(3):
+            for grp in range(groups):
+                b0 = grp * NB
+                row0 = (crop * beam + b0) * heads
+                row_end = (crop * beam + min(b0 + NB, beam)) * heads
+                seen += [row0 + c for c in range(16 * NB) if row0 + c < row_end]
+        assert seen == list(range(3 * beam * heads))             # every (crop, hypothesis, head) row exactly once, in order
+    # --- K9 horizontal pass: PRMT selectors gather the four taps of a channel from three little-endian words
+    def prmt(a, b, sel):
+        by = [(a >> (8 * i)) & 255 for i in range(4)] + [(b >> (8 * i)) & 255 for i in range(4)]
+        return sum(by[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4))
+    w = rng.integers(0, 256, 12).tolist()
+    r0, r1, r2 = (sum(w[4 * j + i] << (8 * i) for i in range(4)) for j in range(3))
+    for c, (s1, s2) in enumerate(((0x0630, 0x5210), (0x0741, 0x6210), (0x0052, 0x7410))):
+        v = prmt(prmt(r0, r1, s1), r2, s2)
+        assert [(v >> (8 * i)) & 255 for i in range(4)] == [w[c], w[3 + c], w[6 + c], w[9 + c]]
