@@ -186,8 +186,10 @@ def test_recognize_chunks_and_beam5(cuda_ctx):
 
 
 def test_greedy_cross_attention_paths_agree(cuda_ctx):
-    """Greedy decoding uses the cache-free cross-attention (attend over encoder states with per-head projected queries);
-    forced logits of that path must match the oracle like the K/V-cache path does (beam >= 2 exercises the latter)."""
+    """Decoding attends over the encoder states themselves (per-head projected queries, no cross-attention K/V cache):
+    greedy with one hypothesis per crop, beam 2 with both hypotheses of a crop sharing the pass (xattn_tc.cu).  Both must
+    reproduce the oracle's hypotheses.  (The K/V-cache and mma.sync paths behind MB_CROSS_CACHED / MB_XE_TC run this test
+    in tests/test_switches_gpu.py.)"""
     from marie_icr_b200 import ops
     from oracle import trocr
     cfg = trocr.trocr_tiny()
@@ -198,8 +200,8 @@ def test_greedy_cross_attention_paths_agree(cuda_ctx):
     with torch.no_grad():
         g1 = trocr.generate(sd, cfg, enc, beam=1, max_len_b=16)
         g2 = trocr.generate(sd, cfg, enc, beam=2, max_len_b=16)
-    t1, l1, s1, _ = ops.trocr_decode(enc_dev, beam=1, max_len_b=16)       # cache-free path
-    t2, l2, s2, _ = ops.trocr_decode(enc_dev, beam=2, max_len_b=16)       # K/V-cache path
+    t1, l1, s1, _ = ops.trocr_decode(enc_dev, beam=1, max_len_b=16)
+    t2, l2, s2, _ = ops.trocr_decode(enc_dev, beam=2, max_len_b=16)
     for i in range(7):
         assert t1[i, :int(l1[i])].cpu().tolist() == g1[i][0]["tokens"].tolist()
         assert t2[i, :int(l2[i])].cpu().tolist() == g2[i][0]["tokens"].tolist()
