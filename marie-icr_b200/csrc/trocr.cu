@@ -604,31 +604,32 @@ __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) { 
 
 __global__ void __launch_bounds__(TOPK_THREADS) logits_topk_kernel(const float* __restrict__ logits, int V, int ld,
                                                                    int cand, int eos_banned, int only_eos,
-                                                                   float* __restrict__ cand_val, int* __restrict__ cand_idx) {
-    __shared__ float red[TOPK_THREADS / 32];
+                                                                   float* __restrict__ cand_val, int* __restrict__ cand_idx,
+                                                                   const unsigned char* __restrict__ finished, int beam) {
+    __shared__ float red_m[TOPK_THREADS / 32], red_s[TOPK_THREADS / 32];
     __shared__ float s_stat[2];
     __shared__ float sv[TOPK_THREADS / 32][MAX_CAND];
     __shared__ int si[TOPK_THREADS / 32][MAX_CAND];
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // a crop whose sentence is done takes no further candidates (search_step_kernel returns on it): its rows are skipped
+    if (finished != nullptr && finished[r / beam]) return;
     const float* x = logits + (long long)r * ld;
-    // pass 1: max (for the softmax) — every vocabulary entry takes part in the normaliser, masked or not
-    float mx = -INFINITY;
-    for (int i = tid; i < V; i += TOPK_THREADS) { const float v = x[i]; if (v == v) mx = fmaxf(mx, v); }
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    if (tid == 0) { float m = red[0]; for (int w = 1; w < TOPK_THREADS / 32; ++w) m = fmaxf(m, red[w]); s_stat[0] = m; }
-    __syncthreads();
-    mx = s_stat[0];
-    // pass 2: sum exp, and per-thread top list of the unmasked logits
+    // ONE pass over the row's 200 KB: running (max, sum of exp) per thread — every vocabulary entry takes part in the
+    // normaliser, masked or not — and the per-thread top list of the unmasked logits.  (The first version read the row
+    // twice: a max pass, then the sums.)
     float tv[MAX_CAND];
     int ti[MAX_CAND];
 #pragma unroll
     for (int k = 0; k < MAX_CAND; ++k) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
-    float sum = 0.f;
+    float mx = -INFINITY, sum = 0.f;
     for (int i = tid; i < V; i += TOPK_THREADS) {
         float v = x[i];
-        if (v == v) sum += __expf(v - mx); else v = -INFINITY;
+        if (v == v) {
+            if (v > mx) { sum = sum * __expf(mx - v) + 1.f; mx = v; }       // first entry: 0 * exp(-inf) + 1
+            else sum += __expf(v - mx);
+        } else {
+            v = -INFINITY;
+        }
         if (i == TOK_PAD || (eos_banned && i == TOK_EOS) || (only_eos && i != TOK_EOS)) v = -INFINITY;
         if (cand_better(v, i, tv[cand - 1], ti[cand - 1])) {
             int k = cand - 1;
@@ -636,11 +637,24 @@ __global__ void __launch_bounds__(TOPK_THREADS) logits_topk_kernel(const float* 
             tv[k] = v; ti[k] = i;
         }
     }
-    sum = warp_sum(sum);
+    // merge the (max, sum) pairs: warp, then block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, mx, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float M = fmaxf(mx, m2);
+        sum = (M == -INFINITY) ? 0.f : sum * __expf(mx - M) + s2 * __expf(m2 - M);
+        mx = M;
+    }
+    if (lane == 0) { red_m[warp] = mx; red_s[warp] = sum; }
     __syncthreads();
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
-    if (tid == 0) { float s = 0.f; for (int w = 0; w < TOPK_THREADS / 32; ++w) s += red[w]; s_stat[1] = logf(s); }
+    if (tid == 0) {
+        float M = red_m[0];
+        for (int w = 1; w < TOPK_THREADS / 32; ++w) M = fmaxf(M, red_m[w]);
+        float S = 0.f;
+        for (int w = 0; w < TOPK_THREADS / 32; ++w) S += (red_m[w] == -INFINITY) ? 0.f : red_s[w] * __expf(red_m[w] - M);
+        s_stat[0] = M;
+        s_stat[1] = logf(S);
+    }
     // warp-level merge: repeatedly take the best head among the 32 sorted lists
     int head = 0;
     for (int k = 0; k < cand; ++k) {
@@ -1512,7 +1526,7 @@ extern "C" int mb_trocr_decode(mb_ctx* ctx, const void* enc_out_dev, int n, int 
     for (; step <= max_len; ++step) {
         RC(decoder_step(ctx, m, w, (const bf16*)enc_out_dev, n, beam, step, max_len, s));
         logits_topk_kernel<<<R, TOPK_THREADS, 0, s>>>(w.logits, m->vocab, m->vocab, cand, step < 1, step >= max_len,
-                                                     w.cand_val, w.cand_idx);
+                                                     w.cand_val, w.cand_idx, w.st.finished, beam);
         MB_LAUNCH_CHECK(ctx);
         search_step_kernel<<<mb_cdiv(n, 64), 64, 0, s>>>(w.st, w.cand_val, w.cand_idx, n, beam, step, max_len);
         MB_LAUNCH_CHECK(ctx);
